@@ -1,0 +1,193 @@
+/* hjb200.h -- C-ABI of the B200-native explicit Hamilton-Jacobi time-stepping hot path.
+ *
+ * Drop-in boundary for robotsorcerer/LevelSetPy's WENO5 + global Lax-Friedrichs + TVD-RK3 path.
+ * The reference has no FFI layer (it is Python callables stored in Bundles); each
+ * entry point below names the reference callable whose work it performs.  Paths are relative to the
+ * reference checkout.
+ *
+ * Conventions
+ *   - plain C: opaque context, raw pointers, sizes; no C++/torch types; no exceptions cross.
+ *   - every function returns 0 on success, a negative hj_status on failure; hj_last_error() gives text.
+ *   - all fields are fp64, C-order ("dense": last dim contiguous, exactly y.reshape(grid.shape)).
+ *     Inside the context fields live in a pitched layout (innermost row padded to an even count so
+ *     rows are 16-byte aligned for TMA / vector access); upload/download convert.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All device work is
+ *     enqueued on it.  Functions documented "synchronises" wait for that stream before returning.
+ *   - one context per (process, device, slab).  Not thread-safe per context.
+ *   - the caller owns every buffer it passes; the context owns its state, scratch and reductions.
+ *   - there is NO CPU fallback: without a CUDA device hj_create fails.
+ */
+#ifndef HJB200_H
+#define HJB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJ_MAX_DIM 6
+#define HJ_MAX_PARAMS 96
+#define HJ_MAX_TABLES 8
+#define HJ_GHOST 3 /* stencil half-width of upwindFirstWENO5a (ENO3aHelper.py:61) */
+
+typedef struct hj_ctx hj_ctx;
+
+typedef enum hj_status {
+  HJ_OK = 0,
+  HJ_ERR_INVALID = -1,      /* bad argument (the reference raises ValueError / assert)      */
+  HJ_ERR_CUDA = -2,         /* CUDA runtime / driver error                                  */
+  HJ_ERR_UNSUPPORTED = -3,  /* valid in the reference but outside this library's hot path   */
+  HJ_ERR_STATE = -4,        /* call order (e.g. step before system/state is set)            */
+  HJ_ERR_NAN = -5           /* NaN met in the integrated field (hji_solver.py:544)          */
+} hj_status;
+
+/* grid.bdry[d]: BoundaryCondition/add_ghost_extrapolate.py:16, add_ghost_periodic.py:12.
+ * HJ_BC_HALO: the 3 ghost planes are stored in the field itself (slab decomposition, dim 0 only). */
+typedef enum hj_bc { HJ_BC_EXTRAPOLATE = 0, HJ_BC_PERIODIC = 1, HJ_BC_HALO = 2 } hj_bc;
+
+/* SpatialDerivative/upwind_first_weno5a.py:13-196 semantics. */
+typedef enum hj_weno {
+  HJ_WENO_AS_SHIPPED = 0, /* bug-compatible: aliasing at :97 => fixed-weight 5th-order upwind      */
+  HJ_WENO_INTENDED = 1    /* true WENO5 smoothness indicators + weights (ENO3bHelper.py:136-160)   */
+} hj_weno;
+
+/* Compiled device functors for schemeData.hamFunc / schemeData.partialFunc.  Parameter blocks: see
+ * INTEGRATION.md ("system parameter blocks").
+ *   DUBINS_REL      DynamicalSystems/dubins_relative.py:63-111   3-D
+ *   DOUBLE_INT      DynamicalSystems/double_integrator.py:49-89  2-D
+ *   FLOCK           DynamicalSystems/flock.py:190-258 + bird.py:235-372 (also a lone Bird)  3-D
+ *   DUBINS_REL_PAIR product of two DUBINS_REL on dims 0-2 / 3-5  6-D  
+ *   DOUBLE_INT_PAIR product of two DOUBLE_INT on dims 0-1 / 2-3  4-D        */
+typedef enum hj_system {
+  HJ_SYS_NONE = 0,
+  HJ_SYS_DUBINS_REL = 1,
+  HJ_SYS_DOUBLE_INT = 2,
+  HJ_SYS_FLOCK = 3,
+  HJ_SYS_DUBINS_REL_PAIR = 4,
+  HJ_SYS_DOUBLE_INT_PAIR = 5
+} hj_system;
+
+/* Driver epilogue fused into the last RK stage (ValueFuncs/hji_solver.py:566-599). */
+typedef enum hj_comp {
+  HJ_COMP_NONE = 0,          /* 'set' / 'none'                                   */
+  HJ_COMP_MIN_OVER_TIME = 1, /* 'minVOverTime': y = min(y, yLast)   :571-573     */
+  HJ_COMP_MAX_OVER_TIME = 2, /* 'maxVOverTime'                                   */
+  HJ_COMP_MIN_WITH_AUX = 3,  /* 'minVWithTarget' / 'minVWithV0': y = min(y, aux) */
+  HJ_COMP_MAX_WITH_AUX = 4   /* 'maxVWithTarget' / 'maxVWithV0'                  */
+} hj_comp;
+
+typedef enum hj_field { HJ_FIELD_STATE = 0, HJ_FIELD_AUX = 1, HJ_FIELD_OBSTACLE = 2 } hj_field;
+
+/* Kernel family used by hj_step / hj_rhs. */
+typedef enum hj_backend {
+  HJ_BACKEND_AUTO = 0,
+  HJ_BACKEND_GATHER = 1, /* one thread per node, neighbours through L1/L2 (any shape)             */
+  HJ_BACKEND_TMA = 2     /* TMA-staged shared-memory plane ring, streamed along dim D-3            */
+} hj_backend;
+
+/* Layout of the reduction record written by hj_rhs / hj_step (doubles):
+ *   [0 .. D)      alphaMax_d  = max_x alpha_d        (artificial_diss_glf.py:104)
+ *   [D .. 2D)     derivMin_d  = min(min L_d, min R_d) (:82-84)
+ *   [2D .. 3D)    derivMax_d                          (:86-88)
+ *   [3D]          nan flag (1.0 if any output was NaN, hji_solver.py:544)                         */
+#define HJ_REDUCE_LEN(D) (3 * (D) + 1)
+
+const char* hj_version(void);
+const char* hj_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t hj_launch_count(void);
+
+/* Grid + scheme.  Replaces the reads of grid.{dim,N,dx,bdry,bdryData} done by
+ * upwindFirstENO3aHelper (SpatialDerivative/ENO3aHelper.py:57-64) and termLaxFriedrichs
+ * (ExplicitIntegration/Term/term_lax_friedrich.py:91-97).
+ *   N[d]              nodes along dim d of THIS context's slab (excluding halo planes)
+ *   dx[d]             grid.dx[d]
+ *   bc_kind[d]        hj_bc; HJ_BC_HALO only for d == 0
+ *   bc_toward_zero[d] grid.bdryData[d].towardZero (extrapolate only)                              */
+int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double* dx, const int* bc_kind,
+              const int* bc_toward_zero, int weno_mode);
+int hj_destroy(hj_ctx* ctx);
+int hj_set_backend(hj_ctx* ctx, int backend);
+
+/* grid.vs[d] (Grids/process_grid.py:204): the n == N[d] node coordinates of dim d, host pointer. */
+int hj_set_axis(hj_ctx* ctx, int dim, const double* vs_host, int64_t n);
+
+/* Host-evaluated 1-D table attached to dim `dim` (e.g. numpy cos/sin of grid.vs[2], so device values
+ * are bit-identical to the reference's cp.cos(grid.xs[2]), dubins_relative.py:81-82).              */
+int hj_set_table(hj_ctx* ctx, int slot, const double* tab_host, int64_t n);
+
+/* schemeData.hamFunc / partialFunc -> device functor + scalar parameter block. */
+int hj_set_system(hj_ctx* ctx, int system_id, const double* params, int nparams);
+
+/* Resident fields.  `dense` is host memory (is_host != 0; pageable or pinned) or device memory. */
+int hj_upload(hj_ctx* ctx, void* stream, int field, const double* dense, int is_host);
+int hj_download(hj_ctx* ctx, void* stream, int field, double* dense, int is_host); /* synchronises if is_host */
+int64_t hj_num_nodes(const hj_ctx* ctx);          /* prod N[d]                      */
+int64_t hj_field_elems(const hj_ctx* ctx);        /* pitched elements incl. halos   */
+/* Device pointer + element offset of halo plane blocks of the resident state (slab exchange).    */
+int hj_state_ptr(hj_ctx* ctx, int which_buffer, double** dev_ptr);
+int64_t hj_plane_elems(const hj_ctx* ctx);        /* pitched elements of one dim-0 plane */
+
+/* upwindFirstWENO5a(grid, data, dim) -> (derivL, derivR)   SpatialDerivative/upwind_first_weno5a.py:13.
+ * data/derivL/derivR: dense device arrays of hj_num_nodes doubles (HJ_BC_HALO contexts: not supported). */
+int hj_deriv(hj_ctx* ctx, void* stream, const double* data_dev, int dim, double* derivL_dev, double* derivR_dev);
+
+/* addGhostExtrapolate / addGhostPeriodic (dataIn, dim, width) -> dataOut, dense device arrays.
+ * BoundaryCondition/add_ghost_extrapolate.py:16, add_ghost_periodic.py:12.                          */
+int hj_add_ghost(hj_ctx* ctx, void* stream, const double* data_dev, int dim, int width, double* out_dev);
+
+/* termLaxFriedrichs(t, y, schemeData) -> (ydot, stepBound)  ExplicitIntegration/Term/term_lax_friedrich.py:8
+ * with dissFunc = artificialDissipationGLF (ExplicitIntegration/Dissipation/artificial_diss_glf.py:7).
+ * y/ydot dense device arrays.  reduce_host[HJ_REDUCE_LEN(D)] and *step_bound are filled; synchronises. */
+int hj_rhs(hj_ctx* ctx, void* stream, double t, const double* y_dev, double* ydot_dev, double* step_bound,
+           double* reduce_host);
+
+/* max_x alpha_d for d = 0..D-1 without touching a field (state-only partialFunc); synchronises.
+ * stepBound = 1 / sum_d alpha_max[d] / dx[d]  (artificial_diss_glf.py:104-109).                       */
+int hj_alpha_max(hj_ctx* ctx, void* stream, double t, double* alpha_max_host, double* step_bound);
+
+/* One TVD-RK3 step of the resident state with a caller-chosen dt: the loop body of odeCFL3
+ * (ExplicitIntegration/Integration/ode_cfl_3.py:125-251) as three fused stage kernels, plus the driver
+ * epilogue of hji_solver.py:566-644 fused into stage 3.
+ *   stage_params  NULL, or 3*nparams doubles: the system parameter block for each of the three RHS
+ *                 evaluations (Flock mutates its headings on every hamFunc call, flock.py:213).
+ *   comp          hj_comp;  use_obstacle != 0: y = max(y, -obstacle) afterwards (:641-644, pointwise).
+ *   want_reduce   != 0: also produce the per-stage reduction records (device side, no sync).
+ * Asynchronous: nothing is read back.                                                                 */
+int hj_step(hj_ctx* ctx, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,
+            int want_reduce);
+/* The three reduction records of the last hj_step(want_reduce=1): 3*HJ_REDUCE_LEN(D) doubles; synchronises. */
+int hj_step_reductions(hj_ctx* ctx, void* stream, double* reduce_host);
+
+/* Multi-GPU slab support: run stage `stage` (1..3) only, so the caller can exchange halos between stages.
+ * hj_step == hj_stage(1); hj_stage(2); hj_stage(3) on a single device.                                  */
+int hj_stage(hj_ctx* ctx, void* stream, int stage, double t, double dt, const double* params, int comp,
+             int use_obstacle, int want_reduce);
+/* Which internal buffer (0..2) stage `stage` reads with its stencil (needs valid halos) / writes. */
+int hj_stage_io(const hj_ctx* ctx, int stage, int* in_buffer, int* out_buffer);
+/* intended-WENO only: per-dim max(D1^2) prepass of buffer `buf` into the context's eps record
+ * (upwind_first_weno5a.py:154-156).  eps_dev returns the device address of the D raw maxima
+ * (ordered-uint64 encoded) so a slab job can max-allreduce them before the stage.                       */
+int hj_eps_prepass(hj_ctx* ctx, void* stream, int buf, uint64_t** eps_dev);
+
+/* odeCFL3(schemeFunc, [t, t_end], y, options{factorCFL,maxStep,singleStep='on'}, schemeData)
+ * ExplicitIntegration/Integration/ode_cfl_3.py:11 for one CFL-limited step on a dense array that may live
+ * on the host (is_host) -- upload, dt = min(factorCFL*stepBound, t_end-t, maxStep) (:142-143), step,
+ * download.  Synchronises.  This is the "host buffers in, host buffers out" call the e2e number times.     */
+int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
+                       double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out);
+
+/* Plain device-memory helpers so a host language without its own CUDA binding can drive the dense-array entry
+ * points (the Python shim uses them when it is handed numpy arrays).  kind: 1 = H2D, 2 = D2H, 3 = D2D.       */
+int hj_device_count(void);
+int hj_dev_alloc(int device, int64_t bytes, void** out);
+int hj_dev_free(void* p);
+int hj_memcpy(void* dst, const void* src, int64_t bytes, int kind, void* stream, int sync);
+int hj_stream_sync(void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HJB200_H */

@@ -1,0 +1,562 @@
+// hj_api.cu -- the C-ABI (include/hjb200.h): context, resident fields, operator entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hj_internal.h"
+#include "hj_systems.cuh"
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void hj_count_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(HJ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+struct hj_ctx {
+  int device = 0, D = 0, weno = 0, backend = HJ_BACKEND_AUTO, system_id = HJ_SYS_NONE, nparams = 0;
+  int halo0 = 0;                 // dim 0 carries stored halo planes (slab decomposition)
+  long long pitch = 0;           // padded innermost extent
+  long long plane = 0;           // pitched elements of one dim-0 plane
+  long long elems = 0;           // pitched elements of a whole field incl. halo planes
+  long long origin = 0;          // element offset of the first interior node
+  long long nodes = 0;           // prod N
+  KGrid gp{}, gd{};              // pitched (resident fields) and dense (user arrays) views
+  KSys ks{};
+  double* vs_dev[HJ_MAX_DIM] = {};
+  double* tab_dev[HJ_MAX_TABLES] = {};
+  unsigned axes_set = 0;
+  double* buf[3] = {};           // y, y1, yHalf (base pointers incl. halo planes)
+  double* aux = nullptr;
+  double* obs = nullptr;
+  double* staging = nullptr;     // dense staging for host <-> pitched conversion
+  unsigned long long* red = nullptr;  // 4 reduction records (3 stages + scratch) + eps record
+  unsigned long long* eps = nullptr;
+  double* pinned = nullptr;      // host scratch
+  bool have_state = false, alpha_valid = false;
+  double alpha_cache[HJ_MAX_DIM] = {};
+  double step_bound_cache = 0.0;
+  HjTmaPlan* plan = nullptr;
+  bool plan_tried = false;
+  std::string plan_err;
+};
+
+static const int RED_STRIDE = 32;  // slots per reduction record (>= HJ_REDUCE_LEN(6) = 19)
+
+extern "C" {
+
+static int ensure_buffers(hj_ctx* c);
+
+const char* hj_version(void) { return "levelsetpy_b200 0.1 (sm_100a)"; }
+const char* hj_last_error(void) { return g_err.c_str(); }
+int64_t hj_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double* dx, const int* bc_kind,
+              const int* bc_toward_zero, int weno_mode) {
+  if (!out || !N || !dx || !bc_kind) return fail(HJ_ERR_INVALID, "hj_create: null argument");
+  if (ndim < 2 || ndim > HJ_MAX_DIM) return fail(HJ_ERR_UNSUPPORTED, "hj_create: grid.dim must be 2..%d, got %d", HJ_MAX_DIM, ndim);
+  if (weno_mode != HJ_WENO_AS_SHIPPED && weno_mode != HJ_WENO_INTENDED) return fail(HJ_ERR_INVALID, "hj_create: bad weno_mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(HJ_ERR_CUDA, "hj_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(HJ_ERR_INVALID, "hj_create: device %d out of range", device);
+  CK(cudaSetDevice(device));
+  hj_ctx* c = new hj_ctx();
+  c->device = device;
+  c->D = ndim;
+  c->weno = weno_mode;
+  for (int d = 0; d < ndim; ++d) {
+    if (N[d] < 2 * HJ_GHOST - 2 || N[d] > 0x7fffffff) { delete c; return fail(HJ_ERR_INVALID, "hj_create: N[%d]=%lld unsupported (need >= 4)", d, (long long)N[d]); }
+    if (!(dx[d] > 0.0)) { delete c; return fail(HJ_ERR_INVALID, "hj_create: grid cell size dx must be strictly positive"); }
+    if (bc_kind[d] != HJ_BC_EXTRAPOLATE && bc_kind[d] != HJ_BC_PERIODIC && !(bc_kind[d] == HJ_BC_HALO && d == 0)) {
+      delete c;
+      return fail(HJ_ERR_UNSUPPORTED, "hj_create: boundary kind %d on dim %d unsupported", bc_kind[d], d);
+    }
+  }
+  c->halo0 = bc_kind[0] == HJ_BC_HALO;
+  const int D = ndim;
+  c->pitch = (N[D - 1] + 1) & ~1LL;
+  KGrid& gp = c->gp;
+  KGrid& gd = c->gd;
+  gp.D = gd.D = D;
+  long long sp = 1, sd = 1;
+  c->nodes = 1;
+  for (int d = D - 1; d >= 0; --d) {
+    gp.N[d] = gd.N[d] = (int)N[d];
+    gp.dx[d] = gd.dx[d] = dx[d];
+    gp.dxinv[d] = gd.dxinv[d] = 1 / dx[d];
+    gp.bc[d] = gd.bc[d] = bc_kind[d];
+    gp.slope_mult[d] = gd.slope_mult[d] = (bc_toward_zero && bc_toward_zero[d]) ? -1.0 : 1.0;
+    gp.stride[d] = sp;
+    gd.stride[d] = sd;
+    sp *= (d == D - 1) ? c->pitch : N[d];
+    sd *= N[d];
+    c->nodes *= N[d];
+  }
+  c->plane = gp.stride[0];
+  c->origin = c->halo0 ? HJ_GHOST * c->plane : 0;
+  c->elems = c->plane * (N[0] + (c->halo0 ? 2 * HJ_GHOST : 0));
+  cudaError_t e = cudaMalloc(&c->red, 5 * RED_STRIDE * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(c->red, 0, 5 * RED_STRIDE * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&c->pinned, 5 * RED_STRIDE * sizeof(double));
+  if (e != cudaSuccess) {
+    hj_destroy(c);
+    return fail(HJ_ERR_CUDA, "hj_create: allocation failed: %s", cudaGetErrorString(e));
+  }
+  c->eps = c->red + 4 * RED_STRIDE;
+  *out = c;
+  return HJ_OK;
+}
+
+int hj_destroy(hj_ctx* c) {
+  if (!c) return HJ_OK;
+  cudaSetDevice(c->device);
+  if (c->plan) hj_tma_plan_destroy(c->plan);
+  for (int b = 0; b < 3; ++b) cudaFree(c->buf[b]);
+  for (int d = 0; d < HJ_MAX_DIM; ++d) cudaFree(c->vs_dev[d]);
+  for (int t = 0; t < HJ_MAX_TABLES; ++t) cudaFree(c->tab_dev[t]);
+  cudaFree(c->aux);
+  cudaFree(c->obs);
+  cudaFree(c->staging);
+  cudaFree(c->red);
+  cudaFreeHost(c->pinned);
+  delete c;
+  return HJ_OK;
+}
+
+int hj_set_backend(hj_ctx* c, int backend) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (backend < HJ_BACKEND_AUTO || backend > HJ_BACKEND_TMA) return fail(HJ_ERR_INVALID, "hj_set_backend: bad backend %d", backend);
+  c->backend = backend;
+  return HJ_OK;
+}
+
+static int upload_vec(double** dst, const double* host, int64_t n) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  CK(cudaMalloc(dst, n * sizeof(double)));
+  CK(cudaMemcpy(*dst, host, n * sizeof(double), cudaMemcpyHostToDevice));
+  return HJ_OK;
+}
+
+int hj_set_axis(hj_ctx* c, int dim, const double* vs_host, int64_t n) {
+  if (!c || !vs_host) return fail(HJ_ERR_INVALID, "hj_set_axis: null argument");
+  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "hj_set_axis: Illegal dim parameter");
+  if (n != c->gp.N[dim]) return fail(HJ_ERR_INVALID, "hj_set_axis: vs[%d] has %lld entries, grid.N is %d", dim, (long long)n, c->gp.N[dim]);
+  CK(cudaSetDevice(c->device));
+  int r = upload_vec(&c->vs_dev[dim], vs_host, n);
+  if (r) return r;
+  c->gp.vs[dim] = c->gd.vs[dim] = c->vs_dev[dim];
+  c->axes_set |= 1u << dim;
+  c->alpha_valid = false;
+  return HJ_OK;
+}
+
+int hj_set_table(hj_ctx* c, int slot, const double* tab_host, int64_t n) {
+  if (!c || !tab_host) return fail(HJ_ERR_INVALID, "hj_set_table: null argument");
+  if (slot < 0 || slot >= HJ_MAX_TABLES || n <= 0) return fail(HJ_ERR_INVALID, "hj_set_table: bad slot/size");
+  CK(cudaSetDevice(c->device));
+  int r = upload_vec(&c->tab_dev[slot], tab_host, n);
+  if (r) return r;
+  c->ks.tab[slot] = c->tab_dev[slot];
+  c->alpha_valid = false;
+  return HJ_OK;
+}
+
+int hj_set_system(hj_ctx* c, int system_id, const double* params, int nparams) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  const int nd = hj_system_ndim(system_id);
+  if (nd < 0) return fail(HJ_ERR_UNSUPPORTED, "hj_set_system: system id %d has no registered device functor", system_id);
+  if (nd != c->D) return fail(HJ_ERR_INVALID, "hj_set_system: system is %d-D but the grid is %d-D", nd, c->D);
+  if (nparams < 0 || nparams > HJ_MAX_PARAMS || (nparams && !params)) return fail(HJ_ERR_INVALID, "hj_set_system: bad parameter block");
+  if (system_id == HJ_SYS_FLOCK) {
+    if (nparams < HJ_FLOCK_HDR) return fail(HJ_ERR_INVALID, "hj_set_system: flock block needs >= %d doubles", HJ_FLOCK_HDR);
+    const int K = (int)params[0];
+    if (K < 0 || HJ_FLOCK_HDR + 3 * K > nparams) return fail(HJ_ERR_INVALID, "hj_set_system: flock block too short for %d birds", K);
+  }
+  c->system_id = system_id;
+  c->nparams = nparams;
+  std::memset(c->ks.p, 0, sizeof c->ks.p);
+  if (nparams) std::memcpy(c->ks.p, params, nparams * sizeof(double));
+  c->alpha_valid = false;
+  return HJ_OK;
+}
+
+int64_t hj_num_nodes(const hj_ctx* c) { return c ? c->nodes : 0; }
+int64_t hj_field_elems(const hj_ctx* c) { return c ? c->elems : 0; }
+int64_t hj_plane_elems(const hj_ctx* c) { return c ? c->plane : 0; }
+
+int hj_state_ptr(hj_ctx* c, int which, double** p) {
+  if (!c || !p || which < 0 || which > 2) return fail(HJ_ERR_INVALID, "hj_state_ptr: bad argument");
+  CK(cudaSetDevice(c->device));
+  int r = ensure_buffers(c);
+  if (r) return r;
+  *p = c->buf[which];
+  return HJ_OK;
+}
+
+// the three RK buffers are allocated on first use so that operator-only contexts (hj_deriv, hj_add_ghost,
+// hj_rhs on dense arrays) stay light
+static int ensure_buffers(hj_ctx* c) {
+  for (int b = 0; b < 3; ++b) {
+    if (c->buf[b]) continue;
+    cudaError_t e = cudaMalloc(&c->buf[b], c->elems * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(c->buf[b], 0, c->elems * sizeof(double));
+    if (e != cudaSuccess)
+      return fail(HJ_ERR_CUDA, "allocation of RK buffer %d (%.2f GB) failed: %s", b, c->elems * 8e-9, cudaGetErrorString(e));
+  }
+  return HJ_OK;
+}
+
+static double** field_slot(hj_ctx* c, int field) {
+  switch (field) {
+    case HJ_FIELD_STATE: return &c->buf[0];
+    case HJ_FIELD_AUX: return &c->aux;
+    case HJ_FIELD_OBSTACLE: return &c->obs;
+    default: return nullptr;
+  }
+}
+
+static int need_staging(hj_ctx* c) {
+  if (!c->staging) CK(cudaMalloc(&c->staging, c->nodes * sizeof(double)));
+  return HJ_OK;
+}
+
+int hj_upload(hj_ctx* c, void* stream, int field, const double* dense, int is_host) {
+  if (!c || !dense) return fail(HJ_ERR_INVALID, "hj_upload: null argument");
+  double** slot = field_slot(c, field);
+  if (!slot) return fail(HJ_ERR_INVALID, "hj_upload: bad field %d", field);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (field == HJ_FIELD_STATE) {
+    int r = ensure_buffers(c);
+    if (r) return r;
+  }
+  if (!*slot) {
+    CK(cudaMalloc(slot, c->elems * sizeof(double)));
+    CK(cudaMemsetAsync(*slot, 0, c->elems * sizeof(double), s));
+  }
+  double* dst = *slot + c->origin;
+  const bool same_layout = c->pitch == c->gp.N[c->D - 1];
+  if (same_layout) {
+    CK(cudaMemcpyAsync(dst, dense, c->nodes * sizeof(double), is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  } else {
+    const double* src = dense;
+    if (is_host) {
+      int r = need_staging(c);
+      if (r) return r;
+      CK(cudaMemcpyAsync(c->staging, dense, c->nodes * sizeof(double), cudaMemcpyHostToDevice, s));
+      src = c->staging;
+    }
+    CK(hj_launch_pack(src, dst, c->gd, c->gp, s));
+  }
+  if (field == HJ_FIELD_STATE) c->have_state = true;
+  return HJ_OK;
+}
+
+int hj_download(hj_ctx* c, void* stream, int field, double* dense, int is_host) {
+  if (!c || !dense) return fail(HJ_ERR_INVALID, "hj_download: null argument");
+  double** slot = field_slot(c, field);
+  if (!slot || !*slot) return fail(HJ_ERR_STATE, "hj_download: field %d not resident", field);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const double* src = *slot + c->origin;
+  const bool same_layout = c->pitch == c->gp.N[c->D - 1];
+  if (same_layout) {
+    CK(cudaMemcpyAsync(dense, src, c->nodes * sizeof(double), is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  } else if (is_host) {
+    int r = need_staging(c);
+    if (r) return r;
+    CK(hj_launch_unpack(src, c->staging, c->gd, c->gp, s));
+    CK(cudaMemcpyAsync(dense, c->staging, c->nodes * sizeof(double), cudaMemcpyDeviceToHost, s));
+  } else {
+    CK(hj_launch_unpack(src, dense, c->gd, c->gp, s));
+  }
+  if (is_host) CK(cudaStreamSynchronize(s));
+  return HJ_OK;
+}
+
+static int check_ready(hj_ctx* c, bool need_system) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (need_system) {
+    if (c->system_id == HJ_SYS_NONE) return fail(HJ_ERR_STATE, "no system registered: call hj_set_system first");
+    if (c->axes_set != (1u << c->D) - 1) return fail(HJ_ERR_STATE, "grid.vs not set for every dim: call hj_set_axis");
+  }
+  return HJ_OK;
+}
+
+int hj_deriv(hj_ctx* c, void* stream, const double* data_dev, int dim, double* dl, double* dr) {
+  if (!c || !data_dev || !dl || !dr) return fail(HJ_ERR_INVALID, "hj_deriv: null argument");
+  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "Illegal dim parameter");   // upwind_first_weno5a.py:60
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_deriv: not available on a slab (halo) context");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->weno == HJ_WENO_INTENDED) {
+    CK(hj_launch_init_eps(c->eps, c->D, s));
+    CK(hj_launch_maxd1sq(c->gd, data_dev, c->eps, dim, s));
+  }
+  CK(hj_launch_deriv(c->weno, c->gd, data_dev, dim, dl, dr, c->eps, s));
+  return HJ_OK;
+}
+
+int hj_add_ghost(hj_ctx* c, void* stream, const double* data_dev, int dim, int width, double* out_dev) {
+  if (!c || !data_dev || !out_dev) return fail(HJ_ERR_INVALID, "hj_add_ghost: null argument");
+  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "Illegal dim parameter");
+  if (width < 0 || width > c->gd.N[dim]) return fail(HJ_ERR_INVALID, "Illegal width parameter");  // add_ghost_extrapolate.py:58
+  if (c->gd.bc[dim] == HJ_BC_HALO) return fail(HJ_ERR_UNSUPPORTED, "hj_add_ghost: halo dim");
+  CK(cudaSetDevice(c->device));
+  CK(hj_launch_add_ghost(c->gd, data_dev, dim, width, out_dev, (cudaStream_t)stream));
+  return HJ_OK;
+}
+
+static void decode_record(const unsigned long long* enc, int D, double* out) {
+  for (int i = 0; i < 3 * D; ++i) {
+    unsigned long long e = enc[i];
+    unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    std::memcpy(&out[i], &b, 8);
+  }
+  out[3 * D] = enc[3 * D] ? 1.0 : 0.0;
+}
+
+static double step_bound_from_alpha(const hj_ctx* c, const double* amax) {
+  double inv = 0;
+  for (int d = 0; d < c->D; ++d) inv = inv + (amax[d] / c->gp.dx[d]);   // artificial_diss_glf.py:107, dims in order
+  return 1 / inv;                                                       // :109
+}
+
+int hj_rhs(hj_ctx* c, void* stream, double t, const double* y_dev, double* ydot_dev, double* step_bound,
+           double* reduce_host) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (!y_dev || !ydot_dev) return fail(HJ_ERR_INVALID, "hj_rhs: null argument");
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_rhs: dense-array entry point is not available on a slab context");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* red = c->red + 3 * RED_STRIDE;
+  CK(hj_launch_init_reduce(red, c->D, s));
+  if (c->weno == HJ_WENO_INTENDED) {
+    CK(hj_launch_init_eps(c->eps, c->D, s));
+    CK(hj_launch_maxd1sq(c->gd, y_dev, c->eps, -1, s));
+  }
+  KStage st{};
+  st.stage = 0;
+  st.want_reduce = 1;
+  st.in = y_dev;
+  st.out = ydot_dev;
+  for (int d = 0; d < c->D; ++d) st.out_stride[d] = c->gd.stride[d];
+  st.red = red;
+  st.epsmax = c->eps;
+  CK(hj_launch_stage_gather(c->system_id, c->weno, c->gd, c->ks, st, s));
+  CK(cudaMemcpyAsync(c->pinned, red, RED_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double rec[RED_STRIDE];
+  decode_record((const unsigned long long*)c->pinned, c->D, rec);
+  if (reduce_host) std::memcpy(reduce_host, rec, HJ_REDUCE_LEN(c->D) * sizeof(double));
+  if (step_bound) *step_bound = step_bound_from_alpha(c, rec);
+  return HJ_OK;
+}
+
+int hj_alpha_max(hj_ctx* c, void* stream, double t, double* alpha_max_host, double* step_bound) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!c->alpha_valid) {
+    unsigned long long* red = c->red + 3 * RED_STRIDE;
+    CK(hj_launch_init_reduce(red, c->D, s));
+    CK(hj_launch_alpha_max(c->system_id, c->gp, c->ks, red, s));
+    CK(cudaMemcpyAsync(c->pinned, red, RED_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    double rec[RED_STRIDE];
+    decode_record((const unsigned long long*)c->pinned, c->D, rec);
+    for (int d = 0; d < c->D; ++d) c->alpha_cache[d] = rec[d];
+    c->step_bound_cache = step_bound_from_alpha(c, rec);
+    c->alpha_valid = true;
+  }
+  if (alpha_max_host) std::memcpy(alpha_max_host, c->alpha_cache, c->D * sizeof(double));
+  if (step_bound) *step_bound = c->step_bound_cache;
+  return HJ_OK;
+}
+
+int hj_stage_io(const hj_ctx* c, int stage, int* in_buffer, int* out_buffer) {
+  if (!c || stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage_io: stage must be 1..3");
+  static const int in_[4] = {0, 0, 1, 2}, out_[4] = {0, 1, 2, 0};
+  if (in_buffer) *in_buffer = in_[stage];
+  if (out_buffer) *out_buffer = out_[stage];
+  return HJ_OK;
+}
+
+int hj_eps_prepass(hj_ctx* c, void* stream, int buf, uint64_t** eps_dev) {
+  if (!c || buf < 0 || buf > 2) return fail(HJ_ERR_INVALID, "hj_eps_prepass: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(hj_launch_init_eps(c->eps, c->D, s));
+  CK(hj_launch_maxd1sq(c->gp, c->buf[buf] + c->origin, c->eps, -1, s));
+  if (eps_dev) *eps_dev = (uint64_t*)c->eps;
+  return HJ_OK;
+}
+
+int hj_dev_alloc(int device, int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(HJ_ERR_INVALID, "hj_dev_alloc: bad argument");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(out, (size_t)(bytes > 0 ? bytes : 8)));
+  return HJ_OK;
+}
+int hj_dev_free(void* p) {
+  if (p) CK(cudaFree(p));
+  return HJ_OK;
+}
+int hj_memcpy(void* dst, const void* src, int64_t bytes, int kind, void* stream, int sync) {
+  // kind: 1 = host->device, 2 = device->host, 3 = device->device
+  cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  CK(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+  if (sync) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return HJ_OK;
+}
+int hj_stream_sync(void* stream) {
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return HJ_OK;
+}
+int hj_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static bool use_tma(hj_ctx* c) {
+  if (c->backend == HJ_BACKEND_GATHER) return false;
+  if (!c->plan_tried) {
+    c->plan_tried = true;
+    char err[256] = {0};
+    c->plan = hj_tma_plan_create(c->gp, c->system_id, c->weno, c->buf, c->halo0, err, sizeof err);
+    c->plan_err = err;
+  }
+  return c->plan != nullptr;
+}
+
+static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
+                      int want_reduce, bool run_prepass) {
+  static const int in_[4] = {0, 0, 1, 2}, out_[4] = {0, 1, 2, 0};
+  KSys ks = c->ks;
+  if (params) std::memcpy(ks.p, params, c->nparams * sizeof(double));
+  KStage st{};
+  st.stage = stage;
+  st.comp = (stage == 3) ? comp : HJ_COMP_NONE;
+  st.use_obs = (stage == 3) ? use_obs : 0;
+  st.want_reduce = want_reduce;
+  st.dt = dt;
+  st.in = c->buf[in_[stage]] + c->origin;
+  st.y0 = c->buf[0] + c->origin;
+  st.aux = c->aux ? c->aux + c->origin : nullptr;
+  st.obs = c->obs ? c->obs + c->origin : nullptr;
+  st.out = c->buf[out_[stage]] + c->origin;
+  for (int d = 0; d < c->D; ++d) st.out_stride[d] = c->gp.stride[d];
+  st.red = c->red + (stage - 1) * RED_STRIDE;
+  st.epsmax = c->eps;
+  if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX)
+    if (!st.aux) return fail(HJ_ERR_STATE, "Need to define target function l(x)!");   // hji_solver.py:584
+  if (st.use_obs && !st.obs) return fail(HJ_ERR_STATE, "obstacle field not uploaded");
+  if (want_reduce) CK(hj_launch_init_reduce(st.red, c->D, s));
+  if (c->weno == HJ_WENO_INTENDED && run_prepass) {
+    CK(hj_launch_init_eps(c->eps, c->D, s));
+    CK(hj_launch_maxd1sq(c->gp, st.in, c->eps, -1, s));
+  }
+  if (use_tma(c)) {
+    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s));
+  } else {
+    if (c->backend == HJ_BACKEND_TMA)
+      return fail(HJ_ERR_UNSUPPORTED, "TMA backend unavailable for this grid: %s", c->plan_err.c_str());
+    CK(hj_launch_stage_gather(c->system_id, c->weno, c->gp, ks, st, s));
+  }
+  return HJ_OK;
+}
+
+int hj_stage(hj_ctx* c, void* stream, int stage, double t, double dt, const double* params, int comp, int use_obstacle,
+             int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage: no resident state (hj_upload first)");
+  if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage: stage must be 1..3");
+  CK(cudaSetDevice(c->device));
+  // on a slab the caller runs hj_eps_prepass + allreduce itself before each stage
+  return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0);
+}
+
+int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,
+            int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_step: no resident state (hj_upload first)");
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_step: on a slab context drive hj_stage and exchange halos between stages");
+  CK(cudaSetDevice(c->device));
+  for (int stage = 1; stage <= 3; ++stage) {
+    const double* p = stage_params ? stage_params + (stage - 1) * c->nparams : nullptr;
+    r = stage_impl(c, (cudaStream_t)stream, stage, dt, p, comp, use_obstacle, want_reduce, true);
+    if (r) return r;
+  }
+  return HJ_OK;
+}
+
+int hj_step_reductions(hj_ctx* c, void* stream, double* reduce_host) {
+  if (!c || !reduce_host) return fail(HJ_ERR_INVALID, "hj_step_reductions: null argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(c->pinned, c->red, 3 * RED_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int L = HJ_REDUCE_LEN(c->D);
+  for (int k = 0; k < 3; ++k) decode_record((const unsigned long long*)c->pinned + k * RED_STRIDE, c->D, reduce_host + k * L);
+  return HJ_OK;
+}
+
+int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double factor_cfl, double max_step,
+                       double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out) {
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (!y_inout) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_single: null y");
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab context");
+  if (factor_cfl < 0.0) return fail(HJ_ERR_INVALID, "FactorCFL must be a positive scalar double value");   // ode_cfl_set.py:104
+  if (max_step < 0.0) return fail(HJ_ERR_INVALID, "MaxStep must be a positive scalar double value");       // ode_cfl_set.py:106
+  r = hj_upload(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+  if (r) return r;
+  double sb = 0;
+  r = hj_alpha_max(c, stream, t, nullptr, &sb);
+  if (r) return r;
+  // ode_cfl_3.py:142-143
+  double dt = factor_cfl * sb;
+  if (t_end - t < dt) dt = t_end - t;
+  if (max_step < dt) dt = max_step;
+  r = hj_step(c, stream, t, dt, nullptr, comp, use_obstacle, 0);
+  if (r) return r;
+  r = hj_download(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+  if (r) return r;
+  if (!is_host) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  // ode_cfl_3.py:145,178,187,220,236 -- time arithmetic kept verbatim
+  const double t1 = t + dt;
+  const double t2 = t1 + dt;
+  const double t_half = 0.25 * (3 * t + t2);
+  const double t_three_half = t_half + dt;
+  if (t_new) *t_new = (1.0 / 3.0) * (t + 2 * t_three_half);
+  if (dt_out) *dt_out = dt;
+  return HJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// hj_common.cuh -- shared device code: kernel parameter blocks, on-the-fly ghost cells, the fifth-order
+// upwind schemes, RK stage algebra and block reductions.  sm_100a only.
+//
+// Reference behaviour restated here (paths relative to the LevelSetPy checkout):
+//   ghost cells        BoundaryCondition/add_ghost_extrapolate.py:88-110, add_ghost_periodic.py:78-87
+//   candidates/weights SpatialDerivative/ENO3aHelper.py:76-189, upwind_first_weno5a.py:107-196
+//   LF term            ExplicitIntegration/Term/term_lax_friedrich.py:106-128
+//   GLF dissipation    ExplicitIntegration/Dissipation/artificial_diss_glf.py:80-109
+//   RK3 stage algebra  ExplicitIntegration/Integration/ode_cfl_3.py:151-241
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hjb200.h"
+
+#define HJ_DEV __device__ __forceinline__
+
+struct KGrid {
+  int D;
+  int N[HJ_MAX_DIM];            // nodes per dim (this slab, without halo planes)
+  long long stride[HJ_MAX_DIM]; // element stride per dim of the field being read
+  double dx[HJ_MAX_DIM];
+  double dxinv[HJ_MAX_DIM];     // 1/dx as the host computed it (ENO3aHelper.py:57)
+  int bc[HJ_MAX_DIM];           // hj_bc
+  double slope_mult[HJ_MAX_DIM];// +1 / -1 (towardZero), add_ghost_extrapolate.py:61-64
+  const double* vs[HJ_MAX_DIM]; // grid.vs[d] on the device
+};
+
+struct KSys {
+  double p[HJ_MAX_PARAMS];
+  const double* tab[HJ_MAX_TABLES];
+};
+
+struct KStage {
+  int stage;        // 0: ydot only (termLaxFriedrichs); 1,2,3: fused RK3 stages
+  int comp;         // hj_comp (stage 3 only)
+  int use_obs;      // stage 3 only
+  int want_reduce;
+  double dt;
+  const double* in;   // field the stencil reads
+  const double* y0;   // y at the start of the step (stages 2,3), pointwise
+  const double* aux;  // target / V0 (stage 3, comp 3/4)
+  const double* obs;  // obstacle (stage 3)
+  double* out;
+  long long out_stride[HJ_MAX_DIM];  // stride of out/y0/aux/obs (pitched or dense)
+  unsigned long long* red;           // HJ_REDUCE_LEN(D) ordered-uint64 slots, or nullptr
+  const unsigned long long* epsmax;  // D ordered-uint64 raw max(D1^2) (intended WENO), or nullptr
+};
+
+// ---------------------------------------------------------------- ordered encoding for fp64 atomics
+HJ_DEV unsigned long long enc_ordered(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+HJ_DEV double dec_ordered(unsigned long long e) {
+  unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  return __longlong_as_double((long long)b);
+}
+
+HJ_DEV double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+HJ_DEV double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- ghost cells
+// addGhostExtrapolate: slope = m*|edge-next|*sign(edge); ghost `dist` cells outside = edge + dist*slope.
+// Un-fused multiplies/adds so the ghost values are bit-identical to numpy's.
+HJ_DEV double ghost_extrapolate(double edge, double next, int dist, double m) {
+  double sgn = (edge > 0.0) ? 1.0 : ((edge < 0.0) ? -1.0 : 0.0);
+  double slope = __dmul_rn(__dmul_rn(m, fabs(__dsub_rn(edge, next))), sgn);
+  return __dadd_rn(edge, __dmul_rn((double)dist, slope));
+}
+
+// v[k] = phi[i + k - 3], k = 0..6, along one dim, ghosts resolved on the fly.
+// `p` points at node i; `s` is the element stride of the dim.
+HJ_DEV void load_stencil(const double* __restrict__ p, int i, int n, long long s, int bc, double m, double v[7]) {
+  if ((i >= HJ_GHOST && i < n - HJ_GHOST) || bc == HJ_BC_HALO) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = __ldg(p + (long long)(k - 3) * s);
+  } else if (bc == HJ_BC_PERIODIC) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      int j = i + k - 3;
+      j = (j < 0) ? j + n : ((j >= n) ? j - n : j);
+      v[k] = __ldg(p + (long long)(j - i) * s);
+    }
+  } else {
+    double e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+    if (i < HJ_GHOST) {
+      e0 = __ldg(p + (long long)(0 - i) * s);
+      e1 = __ldg(p + (long long)(1 - i) * s);
+    }
+    if (i >= n - HJ_GHOST) {
+      f0 = __ldg(p + (long long)(n - 1 - i) * s);
+      f1 = __ldg(p + (long long)(n - 2 - i) * s);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      int j = i + k - 3;
+      if (j < 0) v[k] = ghost_extrapolate(e0, e1, -j, m);
+      else if (j >= n) v[k] = ghost_extrapolate(f0, f1, j - (n - 1), m);
+      else v[k] = __ldg(p + (long long)(k - 3) * s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fifth-order upwind derivative pair
+// v[0..6] = phi[i-3..i+3].  Returns derivL (phi^-) and derivR (phi^+).
+//
+// AS_SHIPPED: upwind_first_weno5a.py as shipped has all three smoothness indicators == 0 (aliasing at :97),
+// so weightWENO (:189-194) reduces to the fixed weights (.1,.6,.3)/(.3,.6,.1) applied to the ENO3 candidates of
+// ENO3aHelper.py:116-189.  Written on the six first differences; agrees with the reference to a few ulp.
+HJ_DEV void upwind5_linear(const double v[7], double dxinv, double& L, double& R) {
+  const double d0 = v[1] - v[0], d1 = v[2] - v[1], d2 = v[3] - v[2];
+  const double d3 = v[4] - v[3], d4 = v[5] - v[4], d5 = v[6] - v[5];
+  const double c2 = 2.0 / 60.0, c13 = 13.0 / 60.0, c47 = 47.0 / 60.0, c27 = 27.0 / 60.0, c3 = 3.0 / 60.0;
+  L = dxinv * (c2 * d0 - c13 * d1 + c47 * d2 + c27 * d3 - c3 * d4);
+  R = dxinv * (-c3 * d1 + c27 * d2 + c47 * d3 - c13 * d4 + c2 * d5);
+}
+
+// INTENDED: Osher & Fedkiw (3.32)-(3.41) / Mitchell's upwindFirstWENO5a, i.e. what upwind_first_weno5a.py:107-172
+// computes without the aliasing bug: v_k = D1 (unstripped), smoothness S1..S3, alpha_k = w_k/(S_k+eps)^2 with
+// eps = 1e-6*max(D1^2)+1e-99.  inv_eps = 1/eps.  The weights are evaluated as w_k * prod_{j!=k} q_j with
+// q_j = (S_j/eps + 1)^2, which is alpha_k * (eps^2 * q0 q1 q2): same ratio, one division, and no under/overflow
+// when eps == 1e-99 (a field that is flat along this dim).
+HJ_DEV double weno_combine(double c0, double c1, double c2, double s0, double s1, double s2, double w0, double w1,
+                           double w2, double inv_eps) {
+  double q0 = fma(s0, inv_eps, 1.0), q1 = fma(s1, inv_eps, 1.0), q2 = fma(s2, inv_eps, 1.0);
+  q0 *= q0; q1 *= q1; q2 *= q2;
+  const double a0 = w0 * (q1 * q2), a1 = w1 * (q0 * q2), a2 = w2 * (q0 * q1);
+  return (a0 * c0 + a1 * c1 + a2 * c2) / (a0 + a1 + a2);
+}
+
+HJ_DEV void upwind5_weno(const double v[7], double dxinv, double inv_eps, double& L, double& R) {
+  const double v1 = dxinv * (v[1] - v[0]), v2 = dxinv * (v[2] - v[1]), v3 = dxinv * (v[3] - v[2]);
+  const double v4 = dxinv * (v[4] - v[3]), v5 = dxinv * (v[5] - v[4]), v6 = dxinv * (v[6] - v[5]);
+  const double k6 = 1.0 / 6.0;
+  // third-order candidates on {i-3..i}, {i-2..i+1}, {i-1..i+2}, {i..i+3}  (dL[1]==dR[0], dL[2]==dR[1])
+  const double c0 = k6 * (2.0 * v1 - 7.0 * v2 + 11.0 * v3);
+  const double c1 = k6 * (-v2 + 5.0 * v3 + 2.0 * v4);
+  const double c2 = k6 * (2.0 * v3 + 5.0 * v4 - v5);
+  const double c3 = k6 * (11.0 * v4 - 7.0 * v5 + 2.0 * v6);
+  const double k13 = 13.0 / 12.0;
+  const double t123 = v1 - 2.0 * v2 + v3, t234 = v2 - 2.0 * v3 + v4, t345 = v3 - 2.0 * v4 + v5,
+               t456 = v4 - 2.0 * v5 + v6;
+  double u;
+  // left: S1(v1,v2,v3), S2(v2,v3,v4), S3(v3,v4,v5)
+  u = v1 - 4.0 * v2 + 3.0 * v3; const double sl0 = k13 * t123 * t123 + 0.25 * u * u;
+  u = v2 - v4;                  const double sl1 = k13 * t234 * t234 + 0.25 * u * u;
+  u = 3.0 * v3 - 4.0 * v4 + v5; const double sl2 = k13 * t345 * t345 + 0.25 * u * u;
+  // right: the same three forms one position up: S1(v2,v3,v4), S2(v3,v4,v5), S3(v4,v5,v6)
+  u = v2 - 4.0 * v3 + 3.0 * v4; const double sr0 = k13 * t234 * t234 + 0.25 * u * u;
+  u = v3 - v5;                  const double sr1 = k13 * t345 * t345 + 0.25 * u * u;
+  u = 3.0 * v4 - 4.0 * v5 + v6; const double sr2 = k13 * t456 * t456 + 0.25 * u * u;
+  L = weno_combine(c0, c1, c2, sl0, sl1, sl2, 0.1, 0.6, 0.3, inv_eps);
+  R = weno_combine(c1, c2, c3, sr0, sr1, sr2, 0.3, 0.6, 0.1, inv_eps);
+}
+
+template <int WENO>
+HJ_DEV void upwind5(const double v[7], double dxinv, double inv_eps, double& L, double& R) {
+  if (WENO == HJ_WENO_AS_SHIPPED) upwind5_linear(v, dxinv, L, R);
+  else upwind5_weno(v, dxinv, inv_eps, L, R);
+}
+
+// max over the D1 entries this node is responsible for (unstripped table: node pairs (-3,-2)..(N+1,N+2)):
+// pair (i,i+1) always; node 0 adds the three pairs below it, node N-1 the two pairs above (i+1,i+2),(i+2,i+3).
+HJ_DEV double d1sq_local(const double v[7], double dxinv, int i, int n) {
+  double d = dxinv * (v[4] - v[3]);
+  double m = d * d;
+  if (i == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { d = dxinv * (v[k + 1] - v[k]); m = fmax(m, d * d); }
+  }
+  if (i == n - 1) {
+#pragma unroll
+    for (int k = 4; k < 6; ++k) { d = dxinv * (v[k + 1] - v[k]); m = fmax(m, d * d); }
+  }
+  return m;
+}
+
+HJ_DEV double inv_eps_from_max(unsigned long long enc) {
+  const double mx = dec_ordered(enc);
+  return 1.0 / (1e-6 * mx + 1e-99);   // upwind_first_weno5a.py:156
+}
+
+// ---------------------------------------------------------------- RK3 stage algebra + driver epilogue
+// ode_cfl_3.py:151 (y1), :184,:193 (y2, yHalf), :226,:241 (yThreeHalf, y); hji_solver.py:571-599, :641-644.
+HJ_DEV double stage_update(const KStage& st, double yin, double ydot, long long oidx) {
+  if (st.stage == 0) return ydot;
+  if (st.stage == 1) return yin + st.dt * ydot;
+  const double y0 = st.y0[oidx];
+  if (st.stage == 2) {
+    const double y2 = yin + st.dt * ydot;
+    return 0.25 * (3.0 * y0 + y2);
+  }
+  const double y32 = yin + st.dt * ydot;
+  double y = (1.0 / 3.0) * (y0 + 2.0 * y32);
+  switch (st.comp) {
+    case HJ_COMP_MIN_OVER_TIME: y = fmin(y, y0); break;
+    case HJ_COMP_MAX_OVER_TIME: y = fmax(y, y0); break;
+    case HJ_COMP_MIN_WITH_AUX: y = fmin(y, st.aux[oidx]); break;
+    case HJ_COMP_MAX_WITH_AUX: y = fmax(y, st.aux[oidx]); break;
+    default: break;
+  }
+  if (st.use_obs) y = fmax(y, -st.obs[oidx]);
+  return y;
+}
+
+// ---------------------------------------------------------------- per-thread reduction accumulator
+template <int D>
+struct RedAcc {
+  double amax[D], dmin[D], dmax[D];
+  int nan;
+  HJ_DEV void init() {
+#pragma unroll
+    for (int d = 0; d < D; ++d) { amax[d] = -INFINITY; dmin[d] = INFINITY; dmax[d] = -INFINITY; }
+    nan = 0;
+  }
+  // block-wide: warp shuffles, then one atomic per warp per slot (REDG on distinct addresses)
+  HJ_DEV void flush(unsigned long long* red) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double a = warp_max(amax[d]), lo = warp_min(dmin[d]), hi = warp_max(dmax[d]);
+      if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0) {
+        atomicMax(red + d, enc_ordered(a));
+        atomicMin(red + D + d, enc_ordered(lo));
+        atomicMax(red + 2 * D + d, enc_ordered(hi));
+      }
+    }
+    const int any = __any_sync(0xffffffffu, nan);
+    if (any && (threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0) atomicOr(red + 3 * D, 1ull);
+  }
+};

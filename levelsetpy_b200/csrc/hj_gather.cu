@@ -1,0 +1,352 @@
+// hj_gather.cu -- "gather" backend: one thread per grid node, neighbours fetched through L1/L2 with ghost
+// cells generated on the fly.  Works for every shape/BC/system; it is the correctness baseline on the device,
+// the backend of the per-operator entry points (hj_deriv, hj_add_ghost, hj_rhs on dense user arrays) and the
+// fallback for shapes the TMA ring kernel does not take.  It is still a single fused kernel per RK stage:
+// no padded copies, no derivative arrays, no separate reductions.
+#include "hj_internal.h"
+#include "hj_systems.cuh"
+
+namespace {
+
+constexpr int BX = 32, BY = 8;
+
+template <int D>
+HJ_DEV void decompose_outer(long long o, const KGrid& g, int* idx) {
+#pragma unroll
+  for (int d = D - 3; d >= 0; --d) {
+    idx[d] = (int)(o % g.N[d]);
+    o /= g.N[d];
+  }
+}
+
+// One fused RHS / RK-stage kernel: for every node, for every dim: 7-point stencil with on-the-fly ghosts ->
+// (derivL, derivR) -> derivC, R-L; then H(x, derivC), GLF dissipation, stage algebra, and (optionally) the
+// derivative min/max, alpha max and NaN reductions.
+template <class Sys, int WENO>
+__global__ void __launch_bounds__(BX* BY) k_stage_gather(const KGrid g, const KSys ks, const KStage st,
+                                                          const long long nouter) {
+  constexpr int D = Sys::ND;
+  const int NX = g.N[D - 1], NY = g.N[D - 2];
+  const int xt = (NX + BX - 1) / BX;
+  const int ix = (blockIdx.x % xt) * BX + threadIdx.x;
+  const int iy = (blockIdx.x / xt) * BY + threadIdx.y;
+  const bool active = ix < NX && iy < NY;
+
+  double inv_eps[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
+
+  RedAcc<D> acc;
+  acc.init();
+
+  for (long long o = blockIdx.y; o < nouter; o += gridDim.y) {
+    if (!active) continue;
+    int idx[D];
+    decompose_outer<D>(o, g, idx);
+    idx[D - 2] = iy;
+    idx[D - 1] = ix;
+    long long off = 0, ooff = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      off += (long long)idx[d] * g.stride[d];
+      ooff += (long long)idx[d] * st.out_stride[d];
+    }
+    double pc[D], dd[D];
+    double yin = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double v[7], L, R;
+      load_stencil(st.in + off, idx[d], g.N[d], g.stride[d], g.bc[d], g.slope_mult[d], v);
+      upwind5<WENO>(v, g.dxinv[d], inv_eps[d], L, R);
+      pc[d] = 0.5 * (L + R);           // term_lax_friedrich.py:108
+      dd[d] = R - L;                   // artificial_diss_glf.py:90
+      if (d == 0) yin = v[3];
+      if (st.want_reduce) {
+        acc.dmin[d] = fmin(acc.dmin[d], fmin(L, R));
+        acc.dmax[d] = fmax(acc.dmax[d], fmax(L, R));
+      }
+    }
+    const typename Sys::Pt pt = Sys::load(idx, g, ks);
+    const double ham = Sys::ham(pt, pc, ks);
+    double diss = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double a = Sys::alpha(d, pt, ks);
+      diss += (0.5 * dd[d]) * a;       // artificial_diss_glf.py:100
+      if (st.want_reduce) acc.amax[d] = fmax(acc.amax[d], a);
+    }
+    const double ydot = -(ham - diss); // term_lax_friedrich.py:124-128
+    const double y = stage_update(st, yin, ydot, ooff);
+    st.out[ooff] = y;
+    if (st.want_reduce && y != y) acc.nan = 1;
+  }
+  if (st.want_reduce) acc.flush(st.red);
+}
+
+// upwindFirstWENO5a(grid, data, dim) -> derivL, derivR (dense in, dense out)
+template <int WENO>
+__global__ void __launch_bounds__(256) k_deriv(const KGrid g, const double* __restrict__ in, const int dim,
+                                               double* __restrict__ dl, double* __restrict__ dr,
+                                               const unsigned long long* epsmax, const long long n) {
+  const double inv_eps = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(epsmax[dim]) : 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)((e / g.stride[dim]) % g.N[dim]);
+    double v[7], L, R;
+    load_stencil(in + e, i, g.N[dim], g.stride[dim], g.bc[dim], g.slope_mult[dim], v);
+    upwind5<WENO>(v, g.dxinv[dim], inv_eps, L, R);
+    dl[e] = L;
+    dr[e] = R;
+  }
+}
+
+// addGhostExtrapolate / addGhostPeriodic: dense (.., N_dim, ..) -> dense (.., N_dim + 2*width, ..)
+__global__ void __launch_bounds__(256) k_add_ghost(const KGrid g, const double* __restrict__ in, const int dim,
+                                                   const int width, double* __restrict__ out, const long long nout) {
+  const long long inner = g.stride[dim];           // dense: product of N[dim+1..]
+  const int n = g.N[dim], no = n + 2 * width;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nout; e += (long long)gridDim.x * blockDim.x) {
+    const long long in_ = e % inner;
+    const long long t = e / inner;
+    const int jo = (int)(t % no);
+    const long long outer = t / no;
+    const double* base = in + outer * (long long)n * inner + in_;
+    const int j = jo - width;
+    double val;
+    if (j >= 0 && j < n) val = base[(long long)j * inner];
+    else if (g.bc[dim] == HJ_BC_PERIODIC) val = base[(long long)((j < 0) ? j + n : j - n) * inner];
+    else if (j < 0) val = ghost_extrapolate(base[0], base[inner], -j, g.slope_mult[dim]);
+    else val = ghost_extrapolate(base[(long long)(n - 1) * inner], base[(long long)(n - 2) * inner], j - (n - 1),
+                                 g.slope_mult[dim]);
+    out[e] = val;
+  }
+}
+
+// max_x alpha_d without a field (state-only partialFunc): artificial_diss_glf.py:104 evaluated once.
+template <class Sys>
+__global__ void __launch_bounds__(BX* BY) k_alpha_max(const KGrid g, const KSys ks, unsigned long long* red,
+                                                       const long long nouter) {
+  constexpr int D = Sys::ND;
+  const int NX = g.N[D - 1], NY = g.N[D - 2];
+  const int xt = (NX + BX - 1) / BX;
+  const int ix = (blockIdx.x % xt) * BX + threadIdx.x;
+  const int iy = (blockIdx.x / xt) * BY + threadIdx.y;
+  const bool active = ix < NX && iy < NY;
+  RedAcc<D> acc;
+  acc.init();
+  for (long long o = blockIdx.y; o < nouter; o += gridDim.y) {
+    if (!active) continue;
+    int idx[D];
+    decompose_outer<D>(o, g, idx);
+    idx[D - 2] = iy;
+    idx[D - 1] = ix;
+    const typename Sys::Pt pt = Sys::load(idx, g, ks);
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc.amax[d] = fmax(acc.amax[d], Sys::alpha(d, pt, ks));
+  }
+  acc.flush(red);
+}
+
+// intended WENO: eps_d = 1e-6 * max(D1_d^2) + 1e-99 over the unstripped D1 table (upwind_first_weno5a.py:154-156).
+// This prepass produces the raw maxima; the stage kernel turns them into 1/eps.
+template <int D>
+__global__ void __launch_bounds__(BX* BY) k_maxd1sq(const KGrid g, const double* __restrict__ in,
+                                                     unsigned long long* epsmax, const long long nouter,
+                                                     const int only_dim) {
+  const int NX = g.N[D - 1], NY = g.N[D - 2];
+  const int xt = (NX + BX - 1) / BX;
+  const int ix = (blockIdx.x % xt) * BX + threadIdx.x;
+  const int iy = (blockIdx.x / xt) * BY + threadIdx.y;
+  const bool active = ix < NX && iy < NY;
+  double mx[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) mx[d] = 0.0;
+  for (long long o = blockIdx.y; o < nouter; o += gridDim.y) {
+    if (!active) continue;
+    int idx[D];
+    decompose_outer<D>(o, g, idx);
+    idx[D - 2] = iy;
+    idx[D - 1] = ix;
+    long long off = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) off += (long long)idx[d] * g.stride[d];
+    const double c = __ldg(in + off);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (only_dim >= 0 && d != only_dim) continue;
+      const int i = idx[d], n = g.N[d];
+      if ((i > 0 && i < n - 1) || (g.bc[d] == HJ_BC_HALO && i < n - 1)) {
+        const double dl = g.dxinv[d] * (__ldg(in + off + g.stride[d]) - c);
+        mx[d] = fmax(mx[d], dl * dl);
+        if (g.bc[d] == HJ_BC_HALO && i == 0) {   // pairs reaching into the lower halo planes belong to this rank's table
+          double v[7];
+          load_stencil(in + off, i, n, g.stride[d], g.bc[d], g.slope_mult[d], v);
+          mx[d] = fmax(mx[d], d1sq_local(v, g.dxinv[d], 0, n + 1));
+        }
+      } else {
+        double v[7];
+        load_stencil(in + off, i, n, g.stride[d], g.bc[d], g.slope_mult[d], v);
+        mx[d] = fmax(mx[d], d1sq_local(v, g.dxinv[d], i, n));
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double m = warp_max(mx[d]);
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && m > 0.0) atomicMax(epsmax + d, enc_ordered(m));
+  }
+}
+
+__global__ void k_init_reduce(unsigned long long* red, int D) {
+  const int i = threadIdx.x;
+  if (i < D) red[i] = enc_ordered(-INFINITY);
+  else if (i < 2 * D) red[i] = enc_ordered(INFINITY);
+  else if (i < 3 * D) red[i] = enc_ordered(-INFINITY);
+  else if (i == 3 * D) red[i] = 0ull;
+}
+__global__ void k_init_eps(unsigned long long* eps, int D) {
+  if ((int)threadIdx.x < D) eps[threadIdx.x] = enc_ordered(0.0);
+}
+
+// dense <-> pitched (rows of the innermost dim)
+__global__ void __launch_bounds__(256) k_repitch(const double* __restrict__ src, double* __restrict__ dst, const int nx,
+                                                 const long long rows, const long long src_pitch,
+                                                 const long long dst_pitch) {
+  const long long total = rows * nx;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / nx;
+    const int x = (int)(e - r * nx);
+    dst[r * dst_pitch + x] = src[r * src_pitch + x];
+  }
+}
+
+template <int D>
+long long outer_count(const KGrid& g) {
+  long long n = 1;
+  for (int d = 0; d <= D - 3; ++d) n *= g.N[d];
+  return n;
+}
+
+inline dim3 tile_grid(const KGrid& g, int D, long long nouter) {
+  const int xt = (g.N[D - 1] + BX - 1) / BX, yt = (g.N[D - 2] + BY - 1) / BY;
+  return dim3((unsigned)(xt * yt), (unsigned)(nouter < 65535 ? nouter : 65535), 1);
+}
+
+inline int flat_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = 148LL * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+struct StageLauncher {
+  int weno;
+  const KGrid& g;
+  const KSys& ks;
+  const KStage& st;
+  cudaStream_t s;
+  template <class Sys>
+  void operator()() {
+    constexpr int D = Sys::ND;
+    const long long no = outer_count<D>(g);
+    const dim3 grid = tile_grid(g, D, no), block(BX, BY);
+    if (weno == HJ_WENO_AS_SHIPPED) k_stage_gather<Sys, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, ks, st, no);
+    else k_stage_gather<Sys, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, ks, st, no);
+  }
+};
+
+struct AlphaLauncher {
+  const KGrid& g;
+  const KSys& ks;
+  unsigned long long* red;
+  cudaStream_t s;
+  template <class Sys>
+  void operator()() {
+    constexpr int D = Sys::ND;
+    const long long no = outer_count<D>(g);
+    k_alpha_max<Sys><<<tile_grid(g, D, no), dim3(BX, BY), 0, s>>>(g, ks, red, no);
+  }
+};
+
+}  // namespace
+
+cudaError_t hj_launch_stage_gather(int system_id, int weno, const KGrid& g, const KSys& ks, const KStage& st,
+                                   cudaStream_t s) {
+  StageLauncher l{weno, g, ks, st, s};
+  if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_deriv(int weno, const KGrid& g, const double* in, int dim, double* dl, double* dr,
+                            const unsigned long long* epsmax, cudaStream_t s) {
+  long long n = 1;
+  for (int d = 0; d < g.D; ++d) n *= g.N[d];
+  if (weno == HJ_WENO_AS_SHIPPED)
+    k_deriv<HJ_WENO_AS_SHIPPED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n);
+  else
+    k_deriv<HJ_WENO_INTENDED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_add_ghost(const KGrid& g, const double* in, int dim, int width, double* out, cudaStream_t s) {
+  long long n = 1;
+  for (int d = 0; d < g.D; ++d) n *= (d == dim) ? (g.N[d] + 2 * width) : g.N[d];
+  k_add_ghost<<<flat_blocks(n), 256, 0, s>>>(g, in, dim, width, out, n);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, unsigned long long* red,
+                                cudaStream_t s) {
+  AlphaLauncher l{g, ks, red, s};
+  if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long long* epsmax, int only_dim,
+                              cudaStream_t s) {
+  const dim3 block(BX, BY);
+  switch (g.D) {
+    case 2: { long long no = outer_count<2>(g); k_maxd1sq<2><<<tile_grid(g, 2, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 3: { long long no = outer_count<3>(g); k_maxd1sq<3><<<tile_grid(g, 3, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 4: { long long no = outer_count<4>(g); k_maxd1sq<4><<<tile_grid(g, 4, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 5: { long long no = outer_count<5>(g); k_maxd1sq<5><<<tile_grid(g, 5, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 6: { long long no = outer_count<6>(g); k_maxd1sq<6><<<tile_grid(g, 6, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    default: return cudaErrorInvalidValue;
+  }
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s) {
+  k_init_reduce<<<1, 32, 0, s>>>(red, D);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s) {
+  k_init_eps<<<1, 32, 0, s>>>(eps, D);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+static long long rows_of(const KGrid& g) {
+  long long r = 1;
+  for (int d = 0; d < g.D - 1; ++d) r *= g.N[d];
+  return r;
+}
+
+cudaError_t hj_launch_pack(const double* dense, double* pitched, const KGrid& gd, const KGrid& gp, cudaStream_t s) {
+  const long long rows = rows_of(gd);
+  const int nx = gd.N[gd.D - 1];
+  k_repitch<<<flat_blocks(rows * nx), 256, 0, s>>>(dense, pitched, nx, rows, gd.stride[gd.D - 2], gp.stride[gp.D - 2]);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t hj_launch_unpack(const double* pitched, double* dense, const KGrid& gd, const KGrid& gp, cudaStream_t s) {
+  const long long rows = rows_of(gd);
+  const int nx = gd.N[gd.D - 1];
+  k_repitch<<<flat_blocks(rows * nx), 256, 0, s>>>(pitched, dense, nx, rows, gp.stride[gp.D - 2], gd.stride[gd.D - 2]);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}

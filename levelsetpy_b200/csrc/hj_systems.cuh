@@ -1,0 +1,135 @@
+// hj_systems.cuh -- compiled device functors for schemeData.hamFunc / schemeData.partialFunc.
+//
+// Each functor restates one DynamicalSystems class of the reference:
+//   DubinsRelF   dubins_relative.py:63-111      H = p1(v_e - v_p cos x3) - p2 v_p sin x3 - w|p1 x2 - p2 x1 - p3| + w|p3|
+//   DoubleIntF   double_integrator.py:49-89     H = -(p1 x2 - |p2| u)
+//   FlockF       flock.py:190-258, bird.py:235-372   H = min_j {H_abs(j), H_attacked}; scalar coefficients per bird
+//   PairF<A,B>   product construction of SURVEY.md 8(d): H = H_A + H_B on disjoint dim blocks
+//
+// alpha_d (the partialFunc of artificial_diss_glf.py:98) is state-only for every one of them, so the GLF
+// stepBound does not depend on the field.  Products/sums that feed max_x alpha_d use un-fused (_rn) arithmetic and
+// host-evaluated trig tables so that the device maximum -- hence dt -- is bit-identical to numpy's.
+#pragma once
+#include "hj_common.cuh"
+
+// Parameter block layouts (doubles) ------------------------------------------------------------------------
+//  DubinsRel : [0]=v_e [1]=v_p [2]=w(1) [3]=w_e [4]=w_p ; tables TB+0 = cos(vs[2]), TB+1 = sin(vs[2])
+//  DoubleInt : [0]=u_bound
+//  Flock     : [0]=K (# un-attacked birds) [1]=has_attacked [2]=W [3]=a1 [4]=a2 [5]=x_att [6]=y_att
+//              [7..9]=alpha_0..2 (host scalars)  [10+3j..] = (c1,c2,c3)_j : H_abs_j = p1 c1 + p2 c2 + p3 c3
+#define HJ_DUBINS_NP 5
+#define HJ_DINT_NP 1
+#define HJ_FLOCK_HDR 10
+
+template <int BASE, int PB, int TB>
+struct DubinsRelF {
+  static constexpr int ND = 3;
+  struct Pt { double x1, x2, c, s; };
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+    Pt q;
+    q.x1 = __ldg(g.vs[BASE + 0] + idx[BASE + 0]);
+    q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
+    q.c = __ldg(k.tab[TB + 0] + idx[BASE + 2]);
+    q.s = __ldg(k.tab[TB + 1] + idx[BASE + 2]);
+    return q;
+  }
+  HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
+    const double ve = k.p[PB + 0], vp = k.p[PB + 1], w = k.p[PB + 2];
+    const double p1 = p[BASE + 0], p2 = p[BASE + 1], p3 = p[BASE + 2];
+    const double p1c = ve - vp * q.c;
+    const double p2c = vp * q.s;
+    return p1 * p1c - p2 * p2c - w * fabs(p1 * q.x2 - p2 * q.x1 - p3) + w * fabs(p3);
+  }
+  HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
+    const double ve = k.p[PB + 0], vp = k.p[PB + 1], w = k.p[PB + 2];
+    if (dl == 0) return __dadd_rn(fabs(__dsub_rn(ve, __dmul_rn(vp, q.c))), fabs(__dmul_rn(w, q.x2)));
+    if (dl == 1) return __dadd_rn(fabs(__dmul_rn(vp, q.s)), fabs(__dmul_rn(w, q.x1)));
+    return __dadd_rn(k.p[PB + 3], k.p[PB + 4]);
+  }
+};
+
+template <int BASE, int PB>
+struct DoubleIntF {
+  static constexpr int ND = 2;
+  struct Pt { double x2; };
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+    Pt q;
+    q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
+    return q;
+  }
+  HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
+    return -(p[BASE + 0] * q.x2 - fabs(p[BASE + 1]) * k.p[PB + 0]);
+  }
+  HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
+    return dl == 0 ? fabs(q.x2) : fabs(k.p[PB + 0]);
+  }
+};
+
+struct FlockF {
+  static constexpr int ND = 3;
+  struct Pt { int dummy; };
+  HJ_DEV static Pt load(const int*, const KGrid&, const KSys&) { return Pt{0}; }
+  HJ_DEV static double ham(const Pt&, const double* p, const KSys& k) {
+    const int K = (int)k.p[0];
+    const double p1 = p[0], p2 = p[1], p3 = p[2];
+    double h = INFINITY;
+    for (int j = 0; j < K; ++j) {
+      const double* c = k.p + HJ_FLOCK_HDR + 3 * j;
+      h = fmin(h, p1 * c[0] + p2 * c[1] + p3 * c[2]);                      // bird.py:266-273
+    }
+    if (k.p[1] != 0.0) {
+      const double W = k.p[2];
+      const double ha = (p1 * k.p[3] - p2 * k.p[4]) + W * fabs(p2 * k.p[5] - p1 * k.p[6] + p3) + W * fabs(p3);
+      h = fmin(h, ha);                                                     // bird.py:305-316, flock.py:232-233
+    }
+    return h;
+  }
+  HJ_DEV static double alpha(int dl, const Pt&, const KSys& k) { return k.p[7 + dl]; }
+};
+
+template <class A, class B>
+struct PairF {
+  static constexpr int ND = A::ND + B::ND;
+  struct Pt { typename A::Pt a; typename B::Pt b; };
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+    Pt q;
+    q.a = A::load(idx, g, k);
+    q.b = B::load(idx, g, k);
+    return q;
+  }
+  HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
+    return A::ham(q.a, p, k) + B::ham(q.b, p, k);
+  }
+  HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
+    return dl < A::ND ? A::alpha(dl, q.a, k) : B::alpha(dl - A::ND, q.b, k);
+  }
+};
+
+using SysDubinsRel = DubinsRelF<0, 0, 0>;
+using SysDoubleInt = DoubleIntF<0, 0>;
+using SysFlock = FlockF;
+using SysDubinsRelPair = PairF<DubinsRelF<0, 0, 0>, DubinsRelF<3, HJ_DUBINS_NP, 2>>;
+using SysDoubleIntPair = PairF<DoubleIntF<0, 0>, DoubleIntF<2, HJ_DINT_NP>>;
+
+// host-side dispatch helper: calls f.template operator()<Sys>() for the functor registered under `id`
+template <class F>
+inline bool hj_dispatch_system(int id, F&& f) {
+  switch (id) {
+    case HJ_SYS_DUBINS_REL: f.template operator()<SysDubinsRel>(); return true;
+    case HJ_SYS_DOUBLE_INT: f.template operator()<SysDoubleInt>(); return true;
+    case HJ_SYS_FLOCK: f.template operator()<SysFlock>(); return true;
+    case HJ_SYS_DUBINS_REL_PAIR: f.template operator()<SysDubinsRelPair>(); return true;
+    case HJ_SYS_DOUBLE_INT_PAIR: f.template operator()<SysDoubleIntPair>(); return true;
+    default: return false;
+  }
+}
+inline int hj_system_ndim(int id) {
+  switch (id) {
+    case HJ_SYS_DUBINS_REL: return 3;
+    case HJ_SYS_DOUBLE_INT: return 2;
+    case HJ_SYS_FLOCK: return 3;
+    case HJ_SYS_DUBINS_REL_PAIR: return 6;
+    case HJ_SYS_DOUBLE_INT_PAIR: return 4;
+    default: return -1;
+  }
+}

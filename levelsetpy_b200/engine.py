@@ -1,0 +1,333 @@
+"""Python face of one ``hj_ctx`` (include/hjb200.h): grid + scheme + resident fields on one GPU.
+
+Everything numerical happens in the CUDA library; this module only marshals the reference's host-side
+objects (grid Bundles, numpy / torch arrays) into the C-ABI.  PyTorch is optional here: numpy arrays are
+staged through the library's own device-memory helpers; torch CUDA tensors are passed by pointer.
+"""
+import ctypes as C
+import sys
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = ["Engine", "engine_for_grid", "DeviceBuffer", "current_stream", "weno_mode_of", "clear_engine_cache"]
+
+_WENO = {"as_shipped": L.WENO_AS_SHIPPED, "intended": L.WENO_INTENDED,
+         L.WENO_AS_SHIPPED: L.WENO_AS_SHIPPED, L.WENO_INTENDED: L.WENO_INTENDED}
+
+
+def _torch():
+    return sys.modules.get("torch")
+
+
+def is_torch_tensor(x):
+    t = _torch()
+    return t is not None and isinstance(x, t.Tensor)
+
+
+def current_stream(device=None):
+    """The CUDA stream work is enqueued on: torch's current stream if torch is loaded, else the default stream."""
+    t = _torch()
+    if t is not None and t.cuda.is_available():
+        return int(t.cuda.current_stream(device).cuda_stream)
+    return 0
+
+
+def weno_mode_of(scheme_data=None, default="as_shipped"):
+    """``schemeData.wenoMode`` ('as_shipped' | 'intended'); the reference has no such switch, so the default is
+    its shipped behaviour."""
+    mode = getattr(scheme_data, "wenoMode", default) if scheme_data is not None else default
+    if mode not in _WENO:
+        raise ValueError("wenoMode must be 'as_shipped' or 'intended', got %r" % (mode,))
+    return mode
+
+
+class DeviceBuffer:
+    """A plain cudaMalloc'ed fp64 array owned by the library (exposes ``__cuda_array_interface__``)."""
+
+    def __init__(self, n, device=0):
+        self.n, self.device = int(n), device
+        p = C.c_void_p()
+        L.check(L.load().hj_dev_alloc(device, self.n * 8, C.byref(p)))
+        self.ptr = p.value
+        self._fin = weakref.finalize(self, L.load().hj_dev_free, C.c_void_p(self.ptr))
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n,), "typestr": "<f8", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def from_host(self, a, stream=0):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        assert a.size == self.n
+        L.check(L.load().hj_memcpy(self.ptr, a.ctypes.data, self.n * 8, 1, stream, 1))
+        return self
+
+    def to_host(self, stream=0):
+        out = np.empty(self.n, dtype=np.float64)
+        L.check(L.load().hj_memcpy(out.ctypes.data, self.ptr, self.n * 8, 2, stream, 1))
+        return out
+
+    def free(self):
+        self._fin()
+
+
+def grid_signature(grid):
+    """(N, dx, bc kinds, towardZero, vs) of a reference-style grid Bundle, validated."""
+    D = int(grid.dim)
+    N = [int(x) for x in np.asarray(grid.N).reshape(-1)]
+    dx = [float(x) for x in np.asarray(grid.dx).reshape(-1)]
+    if len(N) != D or len(dx) != D:
+        raise ValueError("grid.N / grid.dx do not agree with grid.dim")
+    kinds, tz = [], []
+    for d in range(D):
+        fn = grid.bdry[d]
+        name = getattr(fn, "__name__", None)
+        if name == "addGhostPeriodic":
+            kinds.append(L.BC_PERIODIC)
+            tz.append(0)
+        elif name == "addGhostExtrapolate":
+            kinds.append(L.BC_EXTRAPOLATE)
+            gd = grid.bdryData[d] if getattr(grid, "bdryData", None) is not None else None
+            tz.append(1 if (gd is not None and getattr(gd, "towardZero", False)) else 0)
+        else:
+            raise NotImplementedError(
+                "grid.bdry[%d] = %r has no device implementation (addGhostExtrapolate / addGhostPeriodic only; "
+                "no CPU fallback)" % (d, fn))
+    vs = [np.ascontiguousarray(np.asarray(grid.vs[d], dtype=np.float64).reshape(-1)) for d in range(D)]
+    for d in range(D):
+        if vs[d].size != N[d]:
+            raise ValueError("Inconsistent grid size in dimension %d" % d)
+    return D, N, dx, kinds, tz, vs
+
+
+class Engine:
+    """One hj_ctx.  ``slab=(lo, hi)`` restricts the context to planes [lo, hi) of dim 0 with stored halos."""
+
+    def __init__(self, grid, weno="as_shipped", device=0, slab=None, backend=None):
+        self.lib = L.load()
+        D, N, dx, kinds, tz, vs = grid_signature(grid)
+        self.D, self.N_global, self.dx, self.device = D, list(N), dx, device
+        self.weno = weno
+        self.slab = slab
+        if slab is not None:
+            lo, hi = slab
+            N = [hi - lo] + N[1:]
+            kinds = [L.BC_HALO] + kinds[1:]
+            vs = [vs[0][lo:hi].copy()] + vs[1:]
+            self.bc0_global = grid_signature(grid)[3][0]
+            self.tz0_global = grid_signature(grid)[4][0]
+        self.N, self.kinds, self.tz, self.vs = N, kinds, tz, vs
+        self.shape = tuple(N)
+        self.nodes = int(np.prod([float(n) for n in N]))
+        h = C.c_void_p()
+        L.check(self.lib.hj_create(C.byref(h), device, D, (C.c_int64 * D)(*N), (C.c_double * D)(*dx),
+                                   (C.c_int * D)(*kinds), (C.c_int * D)(*tz), _WENO[weno]))
+        self.h = h
+        self._fin = weakref.finalize(self, self.lib.hj_destroy, h)
+        for d in range(D):
+            L.check(self.lib.hj_set_axis(self.h, d, vs[d].ctypes.data, vs[d].size))
+        if backend is not None:
+            L.check(self.lib.hj_set_backend(self.h, backend))
+        self.adapter = None
+        self._params = None
+        self._tables_key = None
+        self.nparams = 0
+
+    # ------------------------------------------------------------------ system
+    def set_system(self, system_id, params, tables=()):
+        params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+        key = tuple((slot, tab.tobytes()) for slot, tab in tables)
+        if key != self._tables_key:
+            for slot, tab in tables:
+                tab = np.ascontiguousarray(tab, dtype=np.float64).reshape(-1)
+                L.check(self.lib.hj_set_table(self.h, slot, tab.ctypes.data, tab.size))
+            self._tables_key = key
+        if self._params is None or self._params[0] != system_id or not np.array_equal(self._params[1], params):
+            L.check(self.lib.hj_set_system(self.h, system_id, params.ctypes.data, params.size))
+            self._params = (system_id, params.copy())
+        self.nparams = params.size
+
+    # ------------------------------------------------------------------ array marshalling
+    def _flat(self, a, n=None):
+        n = self.nodes if n is None else n
+        if is_torch_tensor(a):
+            t = _torch()
+            if not a.is_cuda:
+                raise ValueError("torch tensors must live on the GPU (pass numpy arrays for host data)")
+            a = a.detach()
+            if a.dtype != t.float64:
+                a = a.to(t.float64)
+            a = a.contiguous().reshape(-1)
+            if a.numel() != n:
+                raise ValueError("array has %d entries, grid has %d nodes" % (a.numel(), n))
+            return a, a.data_ptr(), 0
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        if a.size != n:
+            raise ValueError("array has %d entries, grid has %d nodes" % (a.size, n))
+        return a, a.ctypes.data, 1
+
+    def _like(self, like, n, shape):
+        """Output array of the same kind as ``like`` plus its pointer."""
+        if is_torch_tensor(like):
+            t = _torch()
+            out = t.empty(n, dtype=t.float64, device=like.device)
+            return out, out.data_ptr(), 0, lambda: out.reshape(shape)
+        buf = DeviceBuffer(n, self.device)
+        return buf, buf.ptr, 1, lambda: buf.to_host(self.stream()).reshape(shape)
+
+    def _to_device(self, a, n=None):
+        """Dense device copy (pointer) of a numpy array, or the tensor's own storage."""
+        flat, ptr, is_host = self._flat(a, n)
+        if not is_host:
+            return flat, ptr
+        buf = DeviceBuffer(flat.size, self.device).from_host(flat, self.stream())
+        return buf, buf.ptr
+
+    def stream(self):
+        return current_stream(self.device)
+
+    # ------------------------------------------------------------------ resident fields
+    def upload(self, a, field=L.FIELD_STATE):
+        flat, ptr, is_host = self._flat(a)
+        L.check(self.lib.hj_upload(self.h, self.stream(), field, ptr, is_host))
+        self._keep = flat
+
+    def download(self, like=None, field=L.FIELD_STATE, shape=None):
+        shape = (self.nodes, 1) if shape is None else shape
+        if is_torch_tensor(like):
+            t = _torch()
+            out = t.empty(self.nodes, dtype=t.float64, device=like.device)
+            L.check(self.lib.hj_download(self.h, self.stream(), field, out.data_ptr(), 0))
+            return out.reshape(shape)
+        out = np.empty(self.nodes, dtype=np.float64)
+        L.check(self.lib.hj_download(self.h, self.stream(), field, out.ctypes.data, 1))
+        return out.reshape(shape)
+
+    # ------------------------------------------------------------------ operators
+    def deriv(self, data, dim):
+        """upwindFirstWENO5a: (derivL, derivR), same kind/shape as ``data``."""
+        keep, pin = self._to_device(data)
+        shape = tuple(data.shape)
+        oL, pL, _, getL = self._like(data, self.nodes, shape)
+        oR, pR, _, getR = self._like(data, self.nodes, shape)
+        L.check(self.lib.hj_deriv(self.h, self.stream(), pin, int(dim), pL, pR))
+        return getL(), getR()
+
+    def add_ghost(self, data, dim, width):
+        keep, pin = self._to_device(data)
+        shape = list(self.shape)
+        shape[dim] += 2 * width
+        n = int(np.prod(shape))
+        o, po, _, get = self._like(data, n, tuple(shape))
+        L.check(self.lib.hj_add_ghost(self.h, self.stream(), pin, int(dim), int(width), po))
+        return get()
+
+    def rhs(self, t, y):
+        """termLaxFriedrichs: (ydot (n,1), stepBound, reductions dict)."""
+        keep, pin = self._to_device(y)
+        o, po, _, get = self._like(y, self.nodes, (self.nodes, 1))
+        sb = C.c_double()
+        red = (C.c_double * (3 * self.D + 1))()
+        L.check(self.lib.hj_rhs(self.h, self.stream(), float(t), pin, po, C.byref(sb), red))
+        r = np.array(red[:])
+        D = self.D
+        return get(), sb.value, dict(alphaMax=r[:D], derivMin=r[D:2 * D], derivMax=r[2 * D:3 * D], nan=bool(r[3 * D]))
+
+    def alpha_max(self, t=0.0):
+        a = (C.c_double * self.D)()
+        sb = C.c_double()
+        L.check(self.lib.hj_alpha_max(self.h, self.stream(), float(t), a, C.byref(sb)))
+        return np.array(a[:]), sb.value
+
+    def step(self, t, dt, stage_params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False):
+        p = None
+        if stage_params is not None:
+            sp = np.ascontiguousarray(stage_params, dtype=np.float64).reshape(-1)
+            assert sp.size == 3 * self.nparams
+            p = sp.ctypes.data
+            self._sp_keep = sp
+        L.check(self.lib.hj_step(self.h, self.stream(), float(t), float(dt), p, int(comp), int(bool(use_obstacle)),
+                                 int(bool(want_reduce))))
+
+    def stage(self, stage, t, dt, params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False):
+        p = None
+        if params is not None:
+            sp = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+            p = sp.ctypes.data
+            self._sp_keep = sp
+        L.check(self.lib.hj_stage(self.h, self.stream(), int(stage), float(t), float(dt), p, int(comp),
+                                  int(bool(use_obstacle)), int(bool(want_reduce))))
+
+    def step_reductions(self):
+        n = 3 * self.D + 1
+        buf = (C.c_double * (3 * n))()
+        L.check(self.lib.hj_step_reductions(self.h, self.stream(), buf))
+        r = np.array(buf[:]).reshape(3, n)
+        D = self.D
+        return [dict(alphaMax=x[:D], derivMin=x[D:2 * D], derivMax=x[2 * D:3 * D], nan=bool(x[3 * D])) for x in r]
+
+    def ode_cfl3_single(self, t, t_end, factor_cfl, max_step, y, comp=L.COMP_NONE, use_obstacle=False):
+        """hj_ode_cfl3_single on a numpy array (in place) or a torch CUDA tensor (in place)."""
+        flat, ptr, is_host = self._flat(y)
+        tn, dt = C.c_double(), C.c_double()
+        L.check(self.lib.hj_ode_cfl3_single(self.h, self.stream(), float(t), float(t_end), float(factor_cfl),
+                                            float(max_step), ptr, is_host, int(comp), int(bool(use_obstacle)),
+                                            C.byref(tn), C.byref(dt)))
+        return tn.value, flat, dt.value
+
+    def sync(self):
+        L.check(self.lib.hj_stream_sync(self.stream()))
+
+    def set_backend(self, backend):
+        L.check(self.lib.hj_set_backend(self.h, backend))
+
+    def buffer_ptr(self, which):
+        p = C.c_void_p()
+        L.check(self.lib.hj_state_ptr(self.h, which, C.byref(p)))
+        return p.value
+
+    @property
+    def plane_elems(self):
+        return int(self.lib.hj_plane_elems(self.h))
+
+    @property
+    def field_elems(self):
+        return int(self.lib.hj_field_elems(self.h))
+
+    def stage_io(self, stage):
+        a, b = C.c_int(), C.c_int()
+        L.check(self.lib.hj_stage_io(self.h, stage, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        self._fin()
+
+
+# ---------------------------------------------------------------------- engine cache
+_CACHE = {}
+_CACHE_MAX = 4
+
+
+def clear_engine_cache():
+    for e in list(_CACHE.values()):
+        e.close()
+    _CACHE.clear()
+
+
+def engine_for_grid(grid, weno="as_shipped", device=None):
+    """Engines are cached by grid *value* (N, dx, BCs, vs), so the shallow grid copies the reference makes
+    (term_lax_friedrich.py:91) land on the same context."""
+    if device is None:
+        t = _torch()
+        device = t.cuda.current_device() if (t is not None and t.cuda.is_available()) else 0
+    D, N, dx, kinds, tz, vs = grid_signature(grid)
+    key = (device, weno, tuple(N), tuple(dx), tuple(kinds), tuple(tz), tuple(v.tobytes() for v in vs))
+    eng = _CACHE.get(key)
+    if eng is None:
+        while len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE))).close()
+        eng = Engine(grid, weno, device)
+        _CACHE[key] = eng
+    return eng

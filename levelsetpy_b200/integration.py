@@ -1,0 +1,126 @@
+"""ExplicitIntegration/Integration call surface: ``odeCFLset`` and ``odeCFL3``."""
+import numpy as np
+
+from . import _lib as L
+from .engine import is_torch_tensor
+from .term import eng_grid, prepare_scheme
+from .utilities import Bundle, cputime, eps, info, isbundle, iscell, isfield, realmax, strcmp, warn
+
+__all__ = ["odeCFLset", "odeCFL3", "rk3_times"]
+
+
+def odeCFLset(kwargs=None):
+    """options = odeCFLset(Bundle(...)) -- ExplicitIntegration/Integration/ode_cfl_set.py:5-133 (same defaults,
+    same error behaviour)."""
+    if not kwargs:
+        raise ValueError("kwargs cannot be None")                      # ode_cfl_set.py:81-89
+    assert isbundle(kwargs), "kwargs must be a bundle type."
+    d = kwargs.__dict__
+    options = Bundle({})
+    options.factorCFL = d.get("factorCFL", 0.5)
+    options.maxStep = d.get("realmax", realmax)                        # sic: key is 'realmax', :96
+    options.postTimeStep = d.get("postTimeStep", None)
+    options.singleStep = d.get("singleStep", "off")
+    options.stats = d.get("stats", "off")
+    options.terminalEvent = d.get("terminalEvent", None)
+    if options.factorCFL < 0.0:
+        raise ValueError("FactorCFL must be a positive scalar double value")
+    if options.maxStep < 0.0:
+        raise ValueError("MaxStep must be a positive scalar double value")
+    if options.postTimeStep is not None:
+        if isinstance(options.postTimeStep, list):
+            for f in options.postTimeStep:
+                if not callable(f):
+                    raise ValueError("Each element in a postTimeStep cell vector must be a function handle.")
+        else:
+            raise ValueError("PostTimeStep parameter must be a function handle or a list of function handles.")
+    if options.terminalEvent is not None and not callable(options.terminalEvent):
+        raise ValueError("PostTimeStep parameter must be a function handle.")
+    return options
+
+
+def rk3_times(t, dt):
+    """Stage times and the new time, arithmetic verbatim from ode_cfl_3.py:145,178,187,220,236."""
+    t1 = t + dt
+    t2 = t1 + dt
+    tHalf = 0.25 * (3 * t + t2)
+    tThreeHalf = tHalf + dt
+    tNew = (1 / 3) * (t + 2 * tThreeHalf)
+    return t1, tHalf, tNew
+
+
+def _step_bound(eng, ad, block):
+    """stepBound for one RHS: host scalars when the functor carries its alphas (Flock), else the cached device
+    maximum of the state-only alpha (artificial_diss_glf.py:104-109)."""
+    al = ad.alphas(block)
+    if al is None:
+        return eng.alpha_max()[1]
+    inv = 0
+    for d in range(eng.D):
+        inv = inv + (al[d] / eng.dx[d])
+    return 1 / inv
+
+
+def rk3_step_resident(eng, ad, grid, t, t_end, factorCFL, maxStep, comp=L.COMP_NONE, use_obstacle=False):
+    """One CFL-limited TVD-RK3 step on the engine's resident state.  Returns (t_new, dt)."""
+    safetyFactorCFL = min(1.0, 1.2 * factorCFL)                         # ode_cfl_3.py:95
+    tables = list(enumerate(ad.tables(grid)))
+    blocks = [ad.block()]
+    eng.set_system(ad.system_id, blocks[0], tables)
+    stepBound = _step_bound(eng, ad, blocks[0])
+    deltaT = float(np.min(np.hstack((factorCFL * stepBound, t_end - t, maxStep))))   # ode_cfl_3.py:142-143
+    if ad.time_varying:
+        # the reference's hamFunc mutates the system on each of the three RHS evaluations (flock.py:213)
+        bounds = [stepBound]
+        for _ in range(2):
+            b = ad.block()
+            blocks.append(b)
+            bounds.append(_step_bound(eng, ad, b))
+        for k, name in ((1, "Second"), (2, "Third")):
+            if deltaT > safetyFactorCFL * bounds[k]:                    # ode_cfl_3.py:173-175, :215-217
+                warn("%s substep violated CFL effective number %s" % (name, deltaT / bounds[k]))
+        eng.step(t, deltaT, np.concatenate(blocks), comp, use_obstacle)
+    else:
+        # state-only alpha: the stage-2/3 bounds equal the stage-1 bound, the CFL check cannot fire
+        eng.step(t, deltaT, None, comp, use_obstacle)
+    return rk3_times(t, deltaT)[2], deltaT
+
+
+def odeCFL3(schemeFunc, tspan, y0, options=None, schemeData=None):
+    """[t, y, schemeData] = odeCFL3(schemeFunc, tspan, y0, options, schemeData)
+    -- ExplicitIntegration/Integration/ode_cfl_3.py:11-277: third-order TVD Runge-Kutta with a CFL-limited step.
+
+    Each step is three fused sm_100a stage kernels on a field that stays resident in HBM; ``y0`` is uploaded once
+    and ``y`` downloaded once per call (numpy in -> numpy out; torch CUDA tensor in -> tensor out, no host copy).
+    ``schemeFunc`` must be ``termLaxFriedrichs`` (this package's or the reference's own object)."""
+    small = 100 * eps                                                   # ode_cfl_3.py:81
+    if not options:
+        options = odeCFLset()                                           # raises, like the reference (:85-86)
+    if getattr(schemeFunc, "__name__", None) != "termLaxFriedrichs":
+        raise NotImplementedError("schemeFunc=%r: only termLaxFriedrichs is compiled for the device" % (schemeFunc,))
+    if iscell(y0):
+        raise NotImplementedError("vector level sets (cell y0) are outside the hot path")
+    if isfield(options, "postTimeStep") and options.postTimeStep:
+        raise NotImplementedError("postTimeStep hooks would need the field on the host every step")
+    if isfield(options, "terminalEvent") and options.terminalEvent:
+        raise NotImplementedError("terminalEvent hooks would need the field on the host every step")
+    numT = len(tspan)
+    if numT != 2:
+        raise NotImplementedError("tspan must have exactly two entries (odeCFLmultipleSteps is outside the hot path)")
+    eng, ad = prepare_scheme(schemeData)
+    grid = eng_grid(schemeData)
+    t = tspan[0]
+    steps = 0
+    startTime = cputime()
+    eng.upload(y0)
+    while tspan[1] - t >= small * np.abs(tspan[1]):                     # ode_cfl_3.py:125
+        t, _ = rk3_step_resident(eng, ad, grid, t, tspan[1], options.factorCFL, options.maxStep)
+        steps += 1
+        if isfield(options, "singleStep") and strcmp(options.singleStep, "on"):
+            break                                                       # :250-251
+    shape = tuple(y0.shape)
+    y = eng.download(like=y0, shape=shape)
+    endTime = cputime()
+    if isfield(options, "stats") and strcmp(options.stats, "on"):
+        info("%d steps in %.2g seconds from  %.2f to %.2f." % (steps, endTime - startTime, tspan[0], t))
+    return t, y, schemeData

@@ -1,0 +1,116 @@
+"""ValueFuncs call surface: ``HJIPDE_solve`` -- the driver loop of ValueFuncs/hji_solver.py:24-868 around the hot
+path, with the field resident in HBM for the whole solve (one upload, one download per requested time)."""
+import numpy as np
+
+from . import _lib as L
+from .dissipation import artificialDissipationGLF
+from .integration import rk3_step_resident
+from .spatial import upwindFirstWENO5
+from .term import eng_grid, prepare_scheme
+from .utilities import Bundle, error, info, isfield
+
+__all__ = ["HJIPDE_solve"]
+
+_COMP = {
+    None: L.COMP_NONE, "none": L.COMP_NONE, "set": L.COMP_NONE,
+    "minVOverTime": L.COMP_MIN_OVER_TIME, "maxVOverTime": L.COMP_MAX_OVER_TIME,
+    "minVWithV0": L.COMP_MIN_WITH_AUX, "maxVWithV0": L.COMP_MAX_WITH_AUX,
+    "minVWithL": L.COMP_MIN_WITH_AUX, "minVwithL": L.COMP_MIN_WITH_AUX, "minVWithTarget": L.COMP_MIN_WITH_AUX,
+    "maxVWithL": L.COMP_MAX_WITH_AUX, "maxVwithL": L.COMP_MAX_WITH_AUX, "maxVWithTarget": L.COMP_MAX_WITH_AUX,
+}
+
+
+def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
+    """[data, tau, extraOuts] = HJIPDE_solve(data0, tau, schemeData, compMethod, extraArgs)
+
+    Solves D_t V = -H(x, D_x V) from ``data0`` over the time vector ``tau`` with WENO5 + global Lax-Friedrichs +
+    TVD-RK3 at factorCFL 0.8, single-stepping until ``tau[i] - 1e-4`` (hji_solver.py:185,445,536-542).
+
+    compMethod: None/'set'/'none', 'minVOverTime', 'maxVOverTime', 'minVWithV0', 'maxVWithV0',
+                'minVWithTarget'/'minVWithL', 'maxVWithTarget'/'maxVWithL'  (:566-599), fused into RK stage 3.
+    extraArgs : Bundle with optional ``quiet``, ``keepLast``, ``obstacleFunction`` (pointwise max(V, -obstacle),
+                the intended semantics of :641-644), ``targetFunction``, ``stopConverge`` + ``convergeThreshold``.
+                Time-varying obstacles/targets, discounting, SDModFunc, visualisation: NotImplementedError.
+    Returns ``data`` of shape grid.shape (keepLast) or (len(tau),) + grid.shape (time on axis 0, as :483-484
+    indexes it), ``tau`` (truncated if converged) and an ``extraOuts`` Bundle."""
+    if extraArgs is None:
+        extraArgs = Bundle({})
+    if not isfield(schemeData, "grid"):
+        error("grid not in bundle schemeData")
+    for bad in ("SDModFunc", "discountFactor", "discountMode", "addGaussianNoiseStandardDeviation", "visualize",
+                "ignoreBoundary", "stopInit", "stopSetInclude", "stopSetIntersect", "saveFilename"):
+        if isfield(extraArgs, bad) and getattr(extraArgs, bad):
+            raise NotImplementedError("extraArgs.%s is outside the accelerated hot path" % bad)
+    if compMethod in ("zero", "minWithZero"):
+        raise NotImplementedError("compMethod %r needs termRestrictUpdate (SURVEY.md 8f, not built yet)" % compMethod)
+    if compMethod not in _COMP:
+        error("Check which compMethod you are using")                   # hji_solver.py:599
+    comp = _COMP[compMethod]
+    quiet = bool(getattr(extraArgs, "quiet", False))
+    keepLast = bool(getattr(extraArgs, "keepLast", False))
+    small = 1e-4                                                        # hji_solver.py:185
+    g = schemeData.grid
+    data0 = np.asarray(data0, dtype=np.float64)
+    if data0.shape != tuple(g.shape):
+        error("Inconsistent initial condition dimension!")              # hji_solver.py:503
+    # numerical approximation functions (hji_solver.py:434); the reference sets `derivFunc` although
+    # termLaxFriedrichs reads `CoStateCalc` -- set both so either spelling works
+    schemeData.dissFunc = artificialDissipationGLF
+    schemeData.derivFunc = upwindFirstWENO5
+    if not isfield(schemeData, "CoStateCalc"):
+        schemeData.CoStateCalc = upwindFirstWENO5
+    eng, ad = prepare_scheme(schemeData)
+    grid = eng_grid(schemeData)
+
+    use_obs = False
+    if isfield(extraArgs, "obstacleFunction") and extraArgs.obstacleFunction is not None:
+        obs = np.asarray(extraArgs.obstacleFunction, dtype=np.float64)
+        if obs.shape != tuple(g.shape):
+            raise NotImplementedError("time-varying obstacleFunction is outside the accelerated hot path")
+        eng.upload(obs, L.FIELD_OBSTACLE)
+        use_obs = True
+    if comp in (L.COMP_MIN_WITH_AUX, L.COMP_MAX_WITH_AUX):
+        if compMethod in ("minVWithV0", "maxVWithV0"):
+            aux = data0
+        else:
+            if not isfield(extraArgs, "targetFunction"):
+                error("Need to define target function l(x)!")           # hji_solver.py:584
+            aux = np.asarray(extraArgs.targetFunction, dtype=np.float64)
+            if aux.shape != tuple(g.shape):
+                raise NotImplementedError("time-varying targetFunction is outside the accelerated hot path")
+        eng.upload(aux, L.FIELD_AUX)
+    stopConverge = bool(getattr(extraArgs, "stopConverge", False))
+    convergeThreshold = getattr(extraArgs, "convergeThreshold", 1e-5)
+
+    tau = np.asarray(tau, dtype=np.float64)
+    eng.upload(data0)
+    frames = None if keepLast else [data0.copy()]
+    last = data0
+    extraOuts = Bundle(dict(dts=[], steps=0))
+    i_end = len(tau) - 1
+    for i in range(1, len(tau)):
+        if not quiet:
+            info("Computing value function at time tau[%d]: %.4f" % (i, tau[i]))
+        tNow = float(tau[i - 1])
+        while tNow < tau[i] - small:                                    # hji_solver.py:536
+            tNow, dt = rk3_step_resident(eng, ad, grid, tNow, float(tau[i]), 0.8, np.finfo(np.float64).max,
+                                         comp, use_obs)
+            extraOuts.dts.append(dt)
+            extraOuts.steps += 1
+        if not keepLast or stopConverge or i == len(tau) - 1:
+            cur = eng.download(shape=tuple(g.shape))
+            if np.any(np.isnan(cur)):
+                error("Nans encountered in the integrated result of HJI PDE data")   # hji_solver.py:544
+            if frames is not None:
+                frames.append(cur)
+            if stopConverge:
+                change = float(np.max(np.abs(cur - last)))              # hji_solver.py:661-672
+                if not quiet:
+                    info("Max change since last iteration: %g" % change)
+                if change < convergeThreshold:
+                    last = cur
+                    i_end = i
+                    break
+            last = cur
+    data = last if keepLast else np.stack(frames, axis=0)
+    return data, tau[: i_end + 1], extraOuts

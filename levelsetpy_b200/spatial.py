@@ -1,0 +1,21 @@
+"""SpatialDerivative call surface: ``schemeData.CoStateCalc`` tokens + standalone GPU operators."""
+from .engine import engine_for_grid
+
+__all__ = ["upwindFirstWENO5a", "upwindFirstWENO5"]
+
+
+def upwindFirstWENO5a(grid, data, dim, generateAll=False, wenoMode="as_shipped"):
+    """[derivL, derivR] = upwindFirstWENO5a(grid, data, dim) -- SpatialDerivative/upwind_first_weno5a.py:13.
+
+    ``data``: numpy array or torch CUDA tensor of shape grid.shape; result has the same kind and shape.
+    ``wenoMode``: 'as_shipped' (the reference's behaviour) or 'intended' (true WENO5 weights)."""
+    if dim < 0 or dim > grid.dim:
+        raise ValueError("Illegal dim parameter")           # upwind_first_weno5a.py:59-60
+    if generateAll:
+        raise NotImplementedError("generateAll=True (the three raw ENO candidates) is outside the hot path")
+    return engine_for_grid(grid, wenoMode).deriv(data, dim)
+
+
+def upwindFirstWENO5(grid, data, dim, generateAll=False, wenoMode="as_shipped"):
+    """Alias of upwindFirstWENO5a -- SpatialDerivative/upwind_first_weno5.py:11-48."""
+    return upwindFirstWENO5a(grid, data, dim, generateAll, wenoMode)

@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 WENO5 + Lax-Friedrichs + TVD-RK3 grid-point updates/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload air3d512|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one full TVD-RK3 step (3 fused RHS+stage kernels) of the hot path over the whole grid.
+1 point-step = one grid node advanced by one RK3 step.  N=1 workload: air3D 512^3 (configs[1]).
+N>1: the same 512^2 cross-section with 512 planes per GPU, slab-decomposed along dim 0 with a 3-plane halo
+exchange per RK stage (weak scaling).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64 WENO5+LF grid-point updates/s (1 point-step = one node advanced one TVD-RK3 step)"
+UNIT = "point-steps/s"
+ALG_BYTES_PER_POINT_STEP = 64.0   # 16 + 24 + 24 B over the three fused stages
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- workloads
+def air3d_setup(lsp, N0, N1, N2):
+    """air3D (Dubins relative, reach-avoid cylinder): SURVEY.md 8d configs 1/2."""
+    g = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / N2)]),
+                       np.array([N0, N1, N2]), pdDims=2, low_mem=True)
+    data0 = np.ascontiguousarray(np.broadcast_to(np.sqrt(g.xs[0] ** 2 + g.xs[1] ** 2) - 5.0, g.shape))
+    return g, data0
+
+
+def scheme_for(lsp, g, weno):
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    return lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation, wenoMode=weno,
+                           dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_port_step_rate(sample_n, steps, warmup=0):
+    """The numpy oracle (restating the reference's CPU path) on an air3D sample; returns (point-steps/s, secs)."""
+    from oracle import hj_oracle as orc
+    from oracle import systems as osys
+    import levelsetpy_b200.grids as grids
+    g = grids.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / sample_n)]),
+                         np.array([sample_n] * 3), pdDims=2)
+    data0 = np.sqrt(g.xs[0] ** 2 + g.xs[1] ** 2) - 5.0
+    o = osys.DubinsVehicleRel(g, 5, 1)
+    sd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    y = data0.reshape(-1, 1)
+    t = 0.0
+    for _ in range(warmup):
+        t, y, _ = orc.ode_cfl3([t, 1e9], y, sd, factor_cfl=0.8, single_step=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y_last = y
+        t, y, _ = orc.ode_cfl3([t, 1e9], y, sd, factor_cfl=0.8, single_step=True)
+        y = np.minimum(y, y_last)
+    dt = time.perf_counter() - t0
+    return sample_n ** 3 * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_sample
+    rate, secs = cpu_port_step_rate(n, args.steps, args.warmup)
+    sample = "air3D %d^3 (same box/ICs/system as the GPU arm), one TVD-RK3 step per bench step, numpy oracle port" % n
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cpu_sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    n = args.n
+    if args.gpus == 1:
+        return "air3D %d^3 fp64 (Dubins relative, GLF, WENO5a, odeCFL3, minVOverTime), 1xB200" % n
+    return ("air3D %dx%dx%d fp64 slab-decomposed along dim 0 over %d GPUs (%d planes/GPU, 3-plane halo exchange "
+            "per RK stage)" % (n * args.gpus, n, n, args.gpus, n))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import levelsetpy_b200 as lsp
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.integration import rk3_step_resident
+    from levelsetpy_b200.term import prepare_scheme
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    lib = L.load()
+    n = args.n
+    hbm_peak, peak_src = peaks()
+    comp = L.COMP_MIN_OVER_TIME
+    backend = {"auto": L.BACKEND_AUTO, "gather": L.BACKEND_GATHER, "tma": L.BACKEND_TMA}[args.backend]
+
+    if world > 1:
+        import torch.distributed as dist
+        from levelsetpy_b200.slab import SlabSolver
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        g, _ = air3d_setup(lsp, n * world, n, n) if False else (None, None)
+        # global grid: world*n planes along dim 0; each rank builds only its slab of the initial data
+        gg = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / n)]),
+                            np.array([n * world, n, n]), pdDims=2, low_mem=True)
+        solver = SlabSolver(scheme_for(lsp, gg, args.weno), device=local, backend=backend)
+        lo, hi = solver.lo, solver.hi
+        x0 = gg.vs[0].reshape(-1)[lo:hi].reshape(-1, 1, 1)
+        slab0 = np.ascontiguousarray(np.broadcast_to(np.sqrt(x0 ** 2 + gg.xs[1] ** 2) - 5.0, (hi - lo, n, n)))
+        solver.upload(slab0)
+        step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
+        points = float(n) ** 3 * world
+        barrier = lambda: dist.barrier()
+    else:
+        g, data0 = air3d_setup(lsp, n, n, n)
+        sd = scheme_for(lsp, g, args.weno)
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(backend)
+        eng.upload(data0)
+        step = lambda t: rk3_step_resident(eng, ad, g, t, 1e9, 0.8, np.finfo(np.float64).max, comp)[0]
+        points = float(n) ** 3
+        barrier = lambda: None
+
+    t = 0.0
+    for _ in range(args.warmup):
+        t = step(t)
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.hj_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        t = step(t)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.hj_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    secs = ms * 1e-3
+    value = points * args.steps / secs
+
+    # ---- e2e: the reference-facing call with HOST buffers: H2D of y, one RK3 step, D2H of y, per step
+    e2e = None
+    if world == 1:
+        y_host = torch.from_numpy(data0.reshape(-1)).pin_memory()
+        y_np = y_host.numpy()
+        te = 0.0
+        for _ in range(1):
+            te, _, _ = eng.ode_cfl3_single(te, 1e9, 0.8, np.finfo(np.float64).max, y_np, comp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            te, _, _ = eng.ode_cfl3_single(te, 1e9, 0.8, np.finfo(np.float64).max, y_np, comp)
+        torch.cuda.synchronize()
+        es = time.perf_counter() - t0
+        e2e = {"value": points * args.e2e_steps / es, "unit": UNIT, "h2d_bytes_per_step": int(points * 8),
+               "d2h_bytes_per_step": int(points * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * es / args.e2e_steps,
+               "api": "hj_ode_cfl3_single (odeCFL3 drop-in, pinned host y in/out)"}
+    else:
+        import torch.distributed as dist
+        # slab job: every rank uploads its slab from pinned host memory, steps once, downloads it
+        y_host = torch.from_numpy(slab0.reshape(-1)).pin_memory()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        te = 0.0
+        for _ in range(args.e2e_steps):
+            solver.upload(y_host.numpy())
+            te = solver.step(te, 1e9, 0.8, comp)[0]
+            solver.download(out=y_host.numpy())
+        torch.cuda.synchronize()
+        dist.barrier()
+        es = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(es, op=dist.ReduceOp.MAX)
+        es = float(es.item())
+        e2e = {"value": points * args.e2e_steps / es, "unit": UNIT, "h2d_bytes_per_step": int(points * 8),
+               "d2h_bytes_per_step": int(points * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * es / args.e2e_steps,
+               "api": "SlabSolver.upload/step/download (pinned host slabs)"}
+
+    if rank != 0:
+        return
+    stage_launches = 3 * args.steps
+    avg_launch_s = secs / stage_launches                 # the three stage kernels are the whole step on this path
+    achieved = (points / world) * (ALG_BYTES_PER_POINT_STEP / 3.0) / avg_launch_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "weno": args.weno, "backend": args.backend,
+                   "factorCFL": 0.8, "compMethod": "minVOverTime",
+                   "l2": "inputs larger than L2 (3 x %.2f GB fields per GPU)" % (float(n) ** 3 * 8e-9),
+                   "point_stage_updates_per_s": 3 * value},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": args.traffic, "peak_source": peak_src, "kernel": "k_stage_* (fused RHS + RK stage)",
+                     "algorithmic_bytes_per_launch": (points / world) * ALG_BYTES_PER_POINT_STEP / 3.0,
+                     "avg_launch_ms": 1e3 * avg_launch_s},
+    }
+    if world == 1 and not args.no_cpu:
+        rate, csecs = cpu_port_step_rate(args.cpu_sample, args.cpu_steps)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                                "sample": "air3D %d^3, %d TVD-RK3 steps of the numpy oracle port (%.1f s)" % (
+                                    args.cpu_sample, args.cpu_steps, csecs)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="nodes per dim (per GPU along dim 0)")
+    ap.add_argument("--weno", default="as_shipped", choices=["as_shipped", "intended"])
+    ap.add_argument("--backend", default="auto", choices=["auto", "gather", "tma"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from an ncu --set full capture")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

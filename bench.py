@@ -222,7 +222,9 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call with HOST buffers: H2D of y, one RK3 step, D2H of y, per step
     e2e = None
-    if world == 1:
+    if args.e2e_steps <= 0:
+        pass
+    elif world == 1:
         y_host = torch.from_numpy(data0.reshape(-1)).pin_memory()
         y_np = y_host.numpy()
         te = 0.0

@@ -179,3 +179,67 @@ def test_product_systems_vs_oracle(lsp):
             to, yo, _ = orc.ode_cfl3([0.0, 1.0], y0, osd, factor_cfl=0.8, single_step=True, weno=weno)
             assert t == to
             assert_close(y, yo, FIELD_TOL, "%d-D step %s" % (g.dim, weno))
+
+
+def _air_case(lsp, N, pd, seed=11, tz=False):
+    rng = np.random.default_rng(seed)
+    gmax = [20.0, 10.0, 2 * np.pi]
+    gmin = [-6.0, -10.0, 0.0]
+    for d in pd:
+        gmax[d] = gmin[d] + (gmax[d] - gmin[d]) * (1 - 1 / N[d])
+    g = lsp.createGrid(np.array(gmin), np.array(gmax), np.array(N), pdDims=pd if pd else None)
+    if tz:
+        g.bdryData = [lsp.Bundle(dict(towardZero=True)) for _ in range(3)]
+    x = np.meshgrid(*[v.reshape(-1) for v in g.vs], indexing="ij")
+    d0 = np.sqrt(x[0] ** 2 + x[1] ** 2) - 5 + 0.4 * np.sin(x[2] + 0.2 * x[0]) + 0.05 * rng.standard_normal(g.shape)
+    return g, np.ascontiguousarray(d0)
+
+
+@pytest.mark.parametrize("N,pd,tz", [([70, 40, 50], [2], False), ([37, 45, 34], [], True), ([40, 33, 66], [0, 1, 2], False),
+                                      ([36, 70, 31], [1], False)])
+@pytest.mark.parametrize("weno", ["as_shipped", "intended"])
+def test_tma_ring_kernel_vs_oracle_and_gather(lsp, N, pd, tz, weno):
+    """Multi-chunk, partial-tile, every-BC-combination check of the TMA plane-ring kernel against the oracle and
+    against the gather backend (both through hj_step)."""
+    from levelsetpy_b200 import _lib as L
+    g, d0 = _air_case(lsp, N, pd, tz=tz)
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    sd = scheme(lsp, g, s, weno)
+    o = osys.DubinsVehicleRel(g, 5, 1)
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
+    y0 = d0.reshape(-1, 1)
+    to, yo, _ = orc.ode_cfl3([0.0, 1.0], y0, osd, factor_cfl=0.8, single_step=True, weno=weno)
+    out = {}
+    for name, be in (("gather", L.BACKEND_GATHER), ("tma", L.BACKEND_TMA)):
+        lsp.engine_for_grid(g, weno).set_backend(be)
+        t, y, _ = lsp.odeCFL3(lsp.termLaxFriedrichs, [0.0, 1.0], y0, opts, sd)
+        assert t == to
+        assert_close(y, yo, FIELD_TOL, "%s vs oracle" % name)
+        out[name] = y
+    lsp.engine_for_grid(g, weno).set_backend(L.BACKEND_AUTO)
+    assert_close(out["tma"], out["gather"], 1e-12, "tma vs gather")
+
+
+def test_step_reductions_match_oracle(lsp):
+    """derivMin/derivMax/alphaMax/NaN record of the fused stage kernels (artificial_diss_glf.py:82-88,104)."""
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.term import prepare_scheme
+    g, d0 = _air_case(lsp, [40, 36, 34], [2])
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    sd = scheme(lsp, g, s)
+    o = osys.DubinsVehicleRel(g, 5, 1)
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    _, _, info = orc.term_lax_friedrichs(0.0, d0.reshape(-1, 1), osd, "as_shipped", full=True)
+    for be in (L.BACKEND_GATHER, L.BACKEND_TMA):
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(be)
+        eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g))))
+        eng.upload(d0)
+        eng.step(0.0, 1e-3, None, L.COMP_NONE, False, want_reduce=True)
+        rec = eng.step_reductions()[0]            # stage 1 sees y0
+        assert np.array_equal(rec["alphaMax"], np.array(info["alphaMax"]))
+        assert np.allclose(rec["derivMin"], info["derivMin"], rtol=1e-11, atol=1e-12)
+        assert np.allclose(rec["derivMax"], info["derivMax"], rtol=1e-11, atol=1e-12)
+        assert not rec["nan"]
+        eng.set_backend(L.BACKEND_AUTO)

@@ -103,6 +103,10 @@ int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double
     gp.dxinv[d] = gd.dxinv[d] = 1 / dx[d];
     gp.bc[d] = gd.bc[d] = bc_kind[d];
     gp.slope_mult[d] = gd.slope_mult[d] = (bc_toward_zero && bc_toward_zero[d]) ? -1.0 : 1.0;
+    gp.ca1[d] = gd.ca1[d] = gp.dxinv[d] * (45.0 / 60.0);
+    gp.ca2[d] = gd.ca2[d] = gp.dxinv[d] * (-9.0 / 60.0);
+    gp.ca3[d] = gd.ca3[d] = gp.dxinv[d] * (1.0 / 60.0);
+    gp.cb[d] = gd.cb[d] = gp.dxinv[d] * (1.0 / 60.0);
     gp.stride[d] = sp;
     gd.stride[d] = sd;
     sp *= (d == D - 1) ? c->pitch : N[d];

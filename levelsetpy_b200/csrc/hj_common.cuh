@@ -24,6 +24,9 @@ struct KGrid {
   int bc[HJ_MAX_DIM];           // hj_bc
   double slope_mult[HJ_MAX_DIM];// +1 / -1 (towardZero), add_ghost_extrapolate.py:61-64
   const double* vs[HJ_MAX_DIM]; // grid.vs[d] on the device
+  // host-precomputed coefficients of the fixed-weight scheme (constant-bank operands in the TMA kernel):
+  //   derivC = ca1 (v4-v2) + ca2 (v5-v1) + ca3 (v6-v0);  0.5 (R-L) = cb (v0+v6 - 6 (v1+v5) + 15 (v2+v4) - 20 v3)
+  double ca1[HJ_MAX_DIM], ca2[HJ_MAX_DIM], ca3[HJ_MAX_DIM], cb[HJ_MAX_DIM];
 };
 
 struct KSys {

@@ -24,26 +24,35 @@
 template <int BASE, int PB, int TB>
 struct DubinsRelF {
   static constexpr int ND = 3;
-  struct Pt { double x1, x2, c, s; };
+  // x1, x2 and the two x3-only coefficients of dubins_relative.py:81-82, evaluated un-fused like numpy does
+  struct Pt { double x1, x2, p1c, p2c; };
+  HJ_DEV static void set3(Pt& q, int i3, const KSys& k) {
+    q.p1c = __dsub_rn(k.p[PB + 0], __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 0] + i3)));   // v_e - v_p cos x3
+    q.p2c = __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 1] + i3));                          // v_p sin x3
+  }
   HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
     Pt q;
     q.x1 = __ldg(g.vs[BASE + 0] + idx[BASE + 0]);
     q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
-    q.c = __ldg(k.tab[TB + 0] + idx[BASE + 2]);
-    q.s = __ldg(k.tab[TB + 1] + idx[BASE + 2]);
+    set3(q, idx[BASE + 2], k);
     return q;
   }
+  // refresh only what depends on global dim GD (the marching dim of the plane-ring kernel)
+  template <int GD>
+  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
+    if (GD == BASE + 0) q.x1 = __ldg(g.vs[BASE + 0] + i);
+    if (GD == BASE + 1) q.x2 = __ldg(g.vs[BASE + 1] + i);
+    if (GD == BASE + 2) set3(q, i, k);
+  }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
-    const double ve = k.p[PB + 0], vp = k.p[PB + 1], w = k.p[PB + 2];
+    const double w = k.p[PB + 2];
     const double p1 = p[BASE + 0], p2 = p[BASE + 1], p3 = p[BASE + 2];
-    const double p1c = ve - vp * q.c;
-    const double p2c = vp * q.s;
-    return p1 * p1c - p2 * p2c - w * fabs(p1 * q.x2 - p2 * q.x1 - p3) + w * fabs(p3);
+    return p1 * q.p1c - p2 * q.p2c - w * fabs(p1 * q.x2 - p2 * q.x1 - p3) + w * fabs(p3);
   }
   HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
-    const double ve = k.p[PB + 0], vp = k.p[PB + 1], w = k.p[PB + 2];
-    if (dl == 0) return __dadd_rn(fabs(__dsub_rn(ve, __dmul_rn(vp, q.c))), fabs(__dmul_rn(w, q.x2)));
-    if (dl == 1) return __dadd_rn(fabs(__dmul_rn(vp, q.s)), fabs(__dmul_rn(w, q.x1)));
+    const double w = k.p[PB + 2];
+    if (dl == 0) return __dadd_rn(fabs(q.p1c), fabs(__dmul_rn(w, q.x2)));
+    if (dl == 1) return __dadd_rn(fabs(q.p2c), fabs(__dmul_rn(w, q.x1)));
     return __dadd_rn(k.p[PB + 3], k.p[PB + 4]);
   }
 };
@@ -57,6 +66,10 @@ struct DoubleIntF {
     q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
     return q;
   }
+  template <int GD>
+  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
+    if (GD == BASE + 1) q.x2 = __ldg(g.vs[BASE + 1] + i);
+  }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
     return -(p[BASE + 0] * q.x2 - fabs(p[BASE + 1]) * k.p[PB + 0]);
   }
@@ -69,6 +82,8 @@ struct FlockF {
   static constexpr int ND = 3;
   struct Pt { int dummy; };
   HJ_DEV static Pt load(const int*, const KGrid&, const KSys&) { return Pt{0}; }
+  template <int GD>
+  HJ_DEV static void reload(Pt&, int, const KGrid&, const KSys&) {}
   HJ_DEV static double ham(const Pt&, const double* p, const KSys& k) {
     const int K = (int)k.p[0];
     const double p1 = p[0], p2 = p[1], p3 = p[2];
@@ -96,6 +111,11 @@ struct PairF {
     q.a = A::load(idx, g, k);
     q.b = B::load(idx, g, k);
     return q;
+  }
+  template <int GD>
+  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
+    A::template reload<GD>(q.a, i, g, k);
+    B::template reload<GD>(q.b, i, g, k);
   }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
     return A::ham(q.a, p, k) + B::ham(q.b, p, k);

@@ -68,36 +68,25 @@ HJ_DEV void tma_load_3d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c
 HJ_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // ------------------------------------------------------------------------------------------ stencil math on pairs
-// derivC and 0.5*(derivR - derivL) of the as-shipped (fixed-weight) scheme straight from the 7 nodes:
-//   derivC = dxinv * (45 (v4-v2) - 9 (v5-v1) + (v6-v0)) / 60                      (= 0.5*(L+R))
-//   0.5*(R-L) = dxinv * ((d5-d0) + 5 (d1-d4) + 10 (d3-d2)) / 60,  d_k = v[k+1]-v[k]
-// First differences of neighbouring nodes are (near-)exact, so the small R-L term keeps full relative accuracy.
-struct LinCoef { double a1, a2, a3, b; };
-HJ_DEV LinCoef lin_coef(double dxinv) {
-  LinCoef c;
-  c.a1 = dxinv * (45.0 / 60.0);
-  c.a2 = dxinv * (-9.0 / 60.0);
-  c.a3 = dxinv * (1.0 / 60.0);
-  c.b = dxinv * (1.0 / 60.0);
-  return c;
-}
-HJ_DEV void lin_pc_hd(const double v0, const double v1, const double v2, const double v3, const double v4,
-                      const double v5, const double v6, const LinCoef& c, double& pc, double& hd) {
-  pc = c.a1 * (v4 - v2) + c.a2 * (v5 - v1) + c.a3 * (v6 - v0);
-  const double d0 = v1 - v0, d1 = v2 - v1, d2 = v3 - v2, d3 = v4 - v3, d4 = v5 - v4, d5 = v6 - v5;
-  hd = c.b * ((d5 - d0) + 5.0 * (d1 - d4) + 10.0 * (d3 - d2));
-}
-
+// derivC and 0.5*(derivR - derivL) of the as-shipped (fixed-weight) scheme straight from the 7 nodes; the
+// coefficients are host-precomputed (KGrid::ca1..cb) and used as constant-bank operands:
+//   derivC    = ca1 (v4-v2) + ca2 (v5-v1) + ca3 (v6-v0)                       (= 0.5*(L+R), 6 flops)
+//   0.5*(R-L) = cb (v0+v6 - 6 (v1+v5) + 15 (v2+v4) - 20 v3)                   (sixth difference, 7 flops)
+// i.e. 13 fp64 instructions per node per dim instead of ~60 for the divided-difference tables + weightWENO.
 template <int WENO>
 HJ_DEV void pc_hd(const double v0, const double v1, const double v2, const double v3, const double v4, const double v5,
-                  const double v6, const LinCoef& c, double dxinv, double inv_eps, double& pc, double& hd, double& L,
-                  double& Rr, bool need_lr) {
+                  const double v6, const KGrid& g, const int d, double inv_eps, double& pc, double& hd, double& L,
+                  double& Rr, const bool need_lr) {
   if (WENO == HJ_WENO_AS_SHIPPED) {
-    lin_pc_hd(v0, v1, v2, v3, v4, v5, v6, c, pc, hd);
+    pc = g.ca1[d] * (v4 - v2) + g.ca2[d] * (v5 - v1) + g.ca3[d] * (v6 - v0);
+    double t = fma(-6.0, v1 + v5, v0 + v6);
+    t = fma(15.0, v2 + v4, t);
+    t = fma(-20.0, v3, t);
+    hd = g.cb[d] * t;
     if (need_lr) { L = pc - hd; Rr = pc + hd; }
   } else {
     const double v[7] = {v0, v1, v2, v3, v4, v5, v6};
-    upwind5_weno(v, dxinv, inv_eps, L, Rr);
+    upwind5_weno(v, g.dxinv[d], inv_eps, L, Rr);
     pc = 0.5 * (L + Rr);
     hd = 0.5 * (Rr - L);
   }
@@ -114,7 +103,7 @@ HJ_DEV double2 slow_neighbor(const double* p, int i, int k, int n, long long s, 
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <class Sys, int WENO, int TX, int TY>
+template <class Sys, int WENO, int TX, int TY, bool RED>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys ks, const KStage st, const TmaGeom geo) {
   constexpr int D = Sys::ND;
@@ -188,12 +177,15 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
   // ---- per-thread constants
   double inv_eps[D];
-  LinCoef lc[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
-    lc[d] = lin_coef(g.dxinv[d]);
-  }
+  for (int d = 0; d < D; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
+  // system state of my two nodes: everything that does not depend on the marching dim is loaded once
+  idx[DZ] = z0;
+  idx[DY] = min(iy, NY - 1);                                 // clamp: masked threads must not read past the axis tables
+  idx[DX] = min(ix, NX - 1);
+  typename Sys::Pt ptA = Sys::load(idx, g, ks);
+  idx[DX] = min(ix + 1, NX - 1);
+  typename Sys::Pt ptB = Sys::load(idx, g, ks);
   const int myoff = (ty + 3) * BW + 4 + 2 * tp;              // my pair inside a slot (doubles); 16-byte aligned
   const bool need_patch_x = (bcx != HJ_BC_HALO) && (x0 - 3 < 0 || x0 + TX + 2 >= NX);
   const bool need_patch_y = (bcy != HJ_BC_HALO) && (y0 - 3 < 0 || y0 + TY + 2 >= NY);
@@ -225,7 +217,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   for (int z = z0; z < z1; ++z) {
     const int kc = z - z0 + 3;                               // ring position of the current plane
     const long long off = off_xy + (long long)z * zstride;
-    idx[DZ] = z;
+    Sys::template reload<DZ>(ptA, z, g, ks);
+    Sys::template reload<DZ>(ptB, z, g, ks);
 
     // early global loads: y0 / aux / obstacle pairs, slow-dim neighbours
     double2 y0v = make_double2(0.0, 0.0), auxv = y0v, obsv = y0v;
@@ -313,43 +306,38 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
     double pcA[D], hdA[D], pcB[D], hdB[D];
     double L, Rr;
-    const bool red = st.want_reduce != 0;
+    constexpr bool red = RED;
 #define HJ_RED(d, ok)                                              \
   if (red && (ok)) {                                               \
     acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));                  \
     acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));                  \
   }
     // X: node A uses columns c-3..c+3 = (w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y); node B is shifted by one
-    pc_hd<WENO>(w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, lc[DX], g.dxinv[DX], inv_eps[DX], pcA[DX], hdA[DX], L, Rr, red);
+    pc_hd<WENO>(w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, g, DX, inv_eps[DX], pcA[DX], hdA[DX], L, Rr, red);
     HJ_RED(DX, ok0)
-    pc_hd<WENO>(w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, w4.x, lc[DX], g.dxinv[DX], inv_eps[DX], pcB[DX], hdB[DX], L, Rr, red);
+    pc_hd<WENO>(w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, w4.x, g, DX, inv_eps[DX], pcB[DX], hdB[DX], L, Rr, red);
     HJ_RED(DX, ok1)
     // Y
-    pc_hd<WENO>(ym3.x, ym2.x, ym1.x, ctr.x, yp1.x, yp2.x, yp3.x, lc[DY], g.dxinv[DY], inv_eps[DY], pcA[DY], hdA[DY], L, Rr, red);
+    pc_hd<WENO>(ym3.x, ym2.x, ym1.x, ctr.x, yp1.x, yp2.x, yp3.x, g, DY, inv_eps[DY], pcA[DY], hdA[DY], L, Rr, red);
     HJ_RED(DY, ok0)
-    pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, lc[DY], g.dxinv[DY], inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
+    pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, g, DY, inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
     HJ_RED(DY, ok1)
     // Z (register queue)
-    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, q[5].x, q[6].x, lc[DZ], g.dxinv[DZ], inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
+    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, q[3].x, q[4].x, q[5].x, q[6].x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
     HJ_RED(DZ, ok0)
-    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, q[5].y, q[6].y, lc[DZ], g.dxinv[DZ], inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
+    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, q[3].y, q[4].y, q[5].y, q[6].y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
     HJ_RED(DZ, ok1)
     // slow dims
 #pragma unroll
     for (int d = 0; d < NSLOW; ++d) {
-      pc_hd<WENO>(sn[d][0].x, sn[d][1].x, sn[d][2].x, ctr.x, sn[d][3].x, sn[d][4].x, sn[d][5].x, lc[d], g.dxinv[d], inv_eps[d], pcA[d], hdA[d], L, Rr, red);
+      pc_hd<WENO>(sn[d][0].x, sn[d][1].x, sn[d][2].x, ctr.x, sn[d][3].x, sn[d][4].x, sn[d][5].x, g, d, inv_eps[d], pcA[d], hdA[d], L, Rr, red);
       HJ_RED(d, ok0)
-      pc_hd<WENO>(sn[d][0].y, sn[d][1].y, sn[d][2].y, ctr.y, sn[d][3].y, sn[d][4].y, sn[d][5].y, lc[d], g.dxinv[d], inv_eps[d], pcB[d], hdB[d], L, Rr, red);
+      pc_hd<WENO>(sn[d][0].y, sn[d][1].y, sn[d][2].y, ctr.y, sn[d][3].y, sn[d][4].y, sn[d][5].y, g, d, inv_eps[d], pcB[d], hdB[d], L, Rr, red);
       HJ_RED(d, ok1)
     }
 #undef HJ_RED
 
     // Hamiltonian + GLF dissipation (artificial_diss_glf.py:100: diss += 0.5*(R-L)*alpha)
-    idx[DY] = min(iy, NY - 1);                              // clamp: masked threads must not read past the axis tables
-    idx[DX] = min(ix, NX - 1);
-    const typename Sys::Pt ptA = Sys::load(idx, g, ks);
-    idx[DX] = min(ix + 1, NX - 1);
-    const typename Sys::Pt ptB = Sys::load(idx, g, ks);
     const double hamA = Sys::ham(ptA, pcA, ks), hamB = Sys::ham(ptB, pcB, ks);
     double dissA = 0.0, dissB = 0.0;
 #pragma unroll
@@ -396,7 +384,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
       issue(kc + R);
     }
   }
-  if (st.want_reduce) acc.flush(st.red);
+  if (RED) acc.flush(st.red);
 }
 
 }  // namespace
@@ -426,10 +414,10 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-template <class Sys, int WENO, int TX, int TY>
+template <class Sys, int WENO, int TX, int TY, bool RED>
 static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const KGrid& g, const KSys& ks,
                               const KStage& st, cudaStream_t s) {
-  auto kern = k_stage_tma<Sys, WENO, TX, TY>;
+  auto kern = k_stage_tma<Sys, WENO, TX, TY, RED>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
@@ -452,8 +440,14 @@ struct TmaLauncher {
   template <class Sys>
   void operator()() {
     if constexpr (Sys::ND >= 3) {
-      if (weno == HJ_WENO_AS_SHIPPED) err = launch_one<Sys, HJ_WENO_AS_SHIPPED, 32, 16>(p, tm, g, ks, st, s);
-      else err = launch_one<Sys, HJ_WENO_INTENDED, 32, 16>(p, tm, g, ks, st, s);
+      const bool red = st.want_reduce != 0;
+      if (weno == HJ_WENO_AS_SHIPPED) {
+        err = red ? launch_one<Sys, HJ_WENO_AS_SHIPPED, 32, 16, true>(p, tm, g, ks, st, s)
+                  : launch_one<Sys, HJ_WENO_AS_SHIPPED, 32, 16, false>(p, tm, g, ks, st, s);
+      } else {
+        err = red ? launch_one<Sys, HJ_WENO_INTENDED, 32, 16, true>(p, tm, g, ks, st, s)
+                  : launch_one<Sys, HJ_WENO_INTENDED, 32, 16, false>(p, tm, g, ks, st, s);
+      }
     } else {
       err = cudaErrorNotSupported;
     }

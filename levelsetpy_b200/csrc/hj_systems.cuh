@@ -37,12 +37,23 @@ struct DubinsRelF {
     set3(q, idx[BASE + 2], k);
     return q;
   }
-  // refresh only what depends on global dim GD (the marching dim of the plane-ring kernel)
+  // refresh only what depends on global dim GD (the marching dim of the plane-ring kernel), in two phases so the
+  // table reads for plane z+1 can be in flight while plane z is computed
   template <int GD>
-  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
-    if (GD == BASE + 0) q.x1 = __ldg(g.vs[BASE + 0] + i);
-    if (GD == BASE + 1) q.x2 = __ldg(g.vs[BASE + 1] + i);
-    if (GD == BASE + 2) set3(q, i, k);
+  HJ_DEV static double2 fetch(int i, const KGrid& g, const KSys& k) {
+    if (GD == BASE + 0) return make_double2(__ldg(g.vs[BASE + 0] + i), 0.0);
+    if (GD == BASE + 1) return make_double2(__ldg(g.vs[BASE + 1] + i), 0.0);
+    if (GD == BASE + 2) return make_double2(__ldg(k.tab[TB + 0] + i), __ldg(k.tab[TB + 1] + i));
+    return make_double2(0.0, 0.0);
+  }
+  template <int GD>
+  HJ_DEV static void apply(Pt& q, const double2 r, const KSys& k) {
+    if (GD == BASE + 0) q.x1 = r.x;
+    if (GD == BASE + 1) q.x2 = r.x;
+    if (GD == BASE + 2) {
+      q.p1c = __dsub_rn(k.p[PB + 0], __dmul_rn(k.p[PB + 1], r.x));
+      q.p2c = __dmul_rn(k.p[PB + 1], r.y);
+    }
   }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
     const double w = k.p[PB + 2];
@@ -67,8 +78,13 @@ struct DoubleIntF {
     return q;
   }
   template <int GD>
-  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
-    if (GD == BASE + 1) q.x2 = __ldg(g.vs[BASE + 1] + i);
+  HJ_DEV static double2 fetch(int i, const KGrid& g, const KSys& k) {
+    if (GD == BASE + 1) return make_double2(__ldg(g.vs[BASE + 1] + i), 0.0);
+    return make_double2(0.0, 0.0);
+  }
+  template <int GD>
+  HJ_DEV static void apply(Pt& q, const double2 r, const KSys& k) {
+    if (GD == BASE + 1) q.x2 = r.x;
   }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
     return -(p[BASE + 0] * q.x2 - fabs(p[BASE + 1]) * k.p[PB + 0]);
@@ -83,7 +99,9 @@ struct FlockF {
   struct Pt { int dummy; };
   HJ_DEV static Pt load(const int*, const KGrid&, const KSys&) { return Pt{0}; }
   template <int GD>
-  HJ_DEV static void reload(Pt&, int, const KGrid&, const KSys&) {}
+  HJ_DEV static double2 fetch(int, const KGrid&, const KSys&) { return make_double2(0.0, 0.0); }
+  template <int GD>
+  HJ_DEV static void apply(Pt&, const double2, const KSys&) {}
   HJ_DEV static double ham(const Pt&, const double* p, const KSys& k) {
     const int K = (int)k.p[0];
     const double p1 = p[0], p2 = p[1], p3 = p[2];
@@ -112,10 +130,16 @@ struct PairF {
     q.b = B::load(idx, g, k);
     return q;
   }
+  // a global dim belongs to exactly one of the two blocks, so one double2 carries either block's fetch
   template <int GD>
-  HJ_DEV static void reload(Pt& q, int i, const KGrid& g, const KSys& k) {
-    A::template reload<GD>(q.a, i, g, k);
-    B::template reload<GD>(q.b, i, g, k);
+  HJ_DEV static double2 fetch(int i, const KGrid& g, const KSys& k) {
+    if (GD < A::ND) return A::template fetch<GD>(i, g, k);
+    return B::template fetch<GD>(i, g, k);
+  }
+  template <int GD>
+  HJ_DEV static void apply(Pt& q, const double2 r, const KSys& k) {
+    if (GD < A::ND) A::template apply<GD>(q.a, r, k);
+    else B::template apply<GD>(q.b, r, k);
   }
   HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
     return A::ham(q.a, p, k) + B::ham(q.b, p, k);

@@ -28,7 +28,6 @@
 namespace {
 
 constexpr int R = 8;          // ring slots
-constexpr int NTHREADS = 256;
 
 struct TmaGeom {
   int nxt, nyt, nzc, cz;      // tiles in X, Y; Z chunks; planes per chunk
@@ -103,23 +102,41 @@ HJ_DEV double2 slow_neighbor(const double* p, int i, int k, int n, long long s, 
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <class Sys, int WENO, int TX, int TY, bool RED>
-__global__ void __launch_bounds__(NTHREADS, 2)
-k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys ks, const KStage st, const TmaGeom geo) {
+// Producer/consumer ring without a CTA-wide barrier in the steady state:
+//   full[s]  : armed by the producer thread (expect_tx), completed by the TMA unit when plane box s has landed
+//   empty[s] : one arrival per warp when that warp no longer needs the plane in slot s
+// All 8 warps are consumers (one node pair per thread); lane 0 of warp 0 doubles as the producer: at the top of
+// step z it waits until every warp has released plane z-1 (normally already true: the ring runs R-4 = 4 planes
+// ahead of need) and re-arms that slot with plane z+R-1.  Consumer warps therefore never wait for each other in
+// interior tiles; only tiles that touch the domain boundary pay a 256-thread named barrier per plane for the
+// ghost-cell patch.
+constexpr int NCONS_WARPS = 8;
+constexpr int NCONS = NCONS_WARPS * 32;          // 256 threads
+constexpr int NTHREADS_WS = NCONS;
+
+template <class Sys, int WENO, int TX, int TY, bool RED, int STAGE>
+__global__ void __launch_bounds__(NTHREADS_WS, 2)
+k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y0, const KGrid g,
+            const KSys ks, const KStage st, const TmaGeom geo) {
   constexpr int D = Sys::ND;
   static_assert(D >= 3, "the plane-ring kernel needs a Z dim");
   constexpr int DX = D - 1, DY = D - 2, DZ = D - 3, NSLOW = D - 3;
   constexpr int PAIRS = TX / 2;
-  static_assert(PAIRS * TY == NTHREADS, "tile must give every thread one node pair");
+  static_assert(PAIRS * TY == NCONS, "tile must give every consumer thread one node pair");
   constexpr int BW = TX + 8, BH = TY + 6, SLOT = BW * BH;        // doubles
   static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
+  static_assert((R & (R - 1)) == 0, "R must be a power of two");
+  // stages 2/3 also stream the un-haloed y0 tile (TY x TX) of each plane through the ring, on the same barrier
+  constexpr int YSLOT = (STAGE >= 2) ? TX * TY : 0;
+  static_assert((YSLOT * 8) % 128 == 0, "y0 slot must keep 128-byte alignment");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)R * SLOT * 8);
+  double* yring = ring + (size_t)R * SLOT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)R * (SLOT + YSLOT) * 8);
+  uint64_t* empty = full + R;
 
   const int tid = threadIdx.x;
-  const int tp = tid % PAIRS, ty = tid / PAIRS;
   long long b = blockIdx.x;
   const int xt = (int)(b % geo.nxt); b /= geo.nxt;
   const int yt = (int)(b % geo.nyt); b /= geo.nyt;
@@ -129,7 +146,43 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   const int x0 = xt * TX, y0 = yt * TY, z0 = zc * geo.cz;
   const int z1 = min(z0 + geo.cz, NZ);
   const int bcx = g.bc[DX], bcy = g.bc[DY], bcz = g.bc[DZ];
+  const unsigned klast = (unsigned)((z1 - 1 + 3) - (z0 - 3));   // ring position of the last plane this chunk needs
+  const int zcoord_base = (int)(geo.zcoord0 + slow_flat * NZ);
 
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // plane with ring position k -> slot k & (R-1): TMA load, or a bare arrival for a computed ghost plane
+  auto issue = [&](unsigned k) {
+    const unsigned s = k & (R - 1);
+    const int zp = z0 - 3 + (int)k;
+    int zsrc = zp;
+    bool load = true;
+    if (zp < 0 || zp >= NZ) {
+      if (bcz == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NZ : zp - NZ;
+      else if (bcz == HJ_BC_EXTRAPOLATE) load = false;          // ghost plane: computed from the register queue
+    }
+    // the y0 tile rides along for planes that will be "current" (ring positions 3 .. klast-3)
+    const bool ytile = STAGE >= 2 && k >= 3 && k + 3 <= klast;
+    if (load) {
+      mbar_expect_tx(&full[s], (SLOT + (ytile ? YSLOT : 0)) * 8);
+      tma_load_3d(ring + (size_t)s * SLOT, &tmap, &full[s], x0 - 4, y0 - 3, zcoord_base + zsrc);
+      if (ytile) tma_load_3d(yring + (size_t)s * YSLOT, &tmap_y0, &full[s], x0, y0, zcoord_base + zp);
+    } else {
+      mbar_arrive(&full[s]);
+    }
+  };
+  if (tid == 0) {
+    for (unsigned k = 0; k < R && k <= klast; ++k) issue(k);
+  }
+
+  // ================================================================== consumer warps
+  const int lane = tid & 31;
+  const int tp = tid % PAIRS, ty = tid / PAIRS;
   int idx[D];
   {
     long long r = slow_flat;
@@ -137,45 +190,12 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     for (int d = NSLOW - 1; d >= 0; --d) { idx[d] = (int)(r % g.N[d]); r /= g.N[d]; }
   }
   const int ix = x0 + 2 * tp, iy = y0 + ty;
-  idx[DX] = ix; idx[DY] = iy;
   const bool ok0 = ix < NX && iy < NY, ok1 = ix + 1 < NX && iy < NY;
-  long long off_xy = (long long)iy * g.stride[DY] + ix;          // stride[DX] == 1
+  long long off = (long long)iy * g.stride[DY] + ix + (long long)z0 * g.stride[DZ];   // stride[DX] == 1
 #pragma unroll
-  for (int d = 0; d < NSLOW; ++d) off_xy += (long long)idx[d] * g.stride[d];
+  for (int d = 0; d < NSLOW; ++d) off += (long long)idx[d] * g.stride[d];
   const long long zstride = g.stride[DZ];
-  const int zcoord_base = (int)(geo.zcoord0 + slow_flat * NZ);
 
-  // ---- barriers
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < R; ++s) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // plane with ring position k (k = plane - (z0-3)) -> slot k % R, parity (k / R) & 1
-  auto issue = [&](int k) {
-    const int zp = z0 - 3 + k;
-    int zsrc = zp;
-    bool load = true;
-    if (zp < 0 || zp >= NZ) {
-      if (bcz == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NZ : zp - NZ;
-      else if (bcz == HJ_BC_EXTRAPOLATE) load = false;      // ghost plane: computed from the register queue
-    }
-    uint64_t* bar = &bars[k % R];
-    if (load) {
-      mbar_expect_tx(bar, SLOT * 8);
-      tma_load_3d(ring + (size_t)(k % R) * SLOT, &tmap, bar, x0 - 4, y0 - 3, zcoord_base + zsrc);
-    } else {
-      mbar_arrive(bar);
-    }
-  };
-  const int klast = (z1 - 1 + 3) - (z0 - 3);                 // ring position of the last plane this chunk needs
-  if (tid == 0) {
-    for (int k = 0; k < R && k <= klast; ++k) issue(k);
-  }
-
-  // ---- per-thread constants
   double inv_eps[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
@@ -186,6 +206,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   typename Sys::Pt ptA = Sys::load(idx, g, ks);
   idx[DX] = min(ix + 1, NX - 1);
   typename Sys::Pt ptB = Sys::load(idx, g, ks);
+
   const int myoff = (ty + 3) * BW + 4 + 2 * tp;              // my pair inside a slot (doubles); 16-byte aligned
   const bool need_patch_x = (bcx != HJ_BC_HALO) && (x0 - 3 < 0 || x0 + TX + 2 >= NX);
   const bool need_patch_y = (bcy != HJ_BC_HALO) && (y0 - 3 < 0 || y0 + TY + 2 >= NY);
@@ -193,11 +214,11 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   RedAcc<D> acc;
   acc.init();
 
-  // ---- prologue: fill the Z register queue with planes z0-3 .. z0+2
+  // ---- prologue: fill the Z register queue with planes z0-3 .. z0+2, then hand slots 0..2 back
   double2 q[7];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    mbar_wait(&bars[k], 0);
+    mbar_wait(&full[k], 0);
     q[k] = *reinterpret_cast<const double2*>(ring + (size_t)k * SLOT + myoff);
   }
   if (bcz == HJ_BC_EXTRAPOLATE && z0 == 0) {
@@ -207,23 +228,31 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
       q[k].y = ghost_extrapolate(q[3].y, q[4].y, 3 - k, g.slope_mult[DZ]);
     }
   }
-  __syncthreads();                                           // slots 0..2 (planes below z0) are dead now
+  __syncwarp();
+  if (lane == 0) { mbar_arrive(&empty[0]); mbar_arrive(&empty[1]); mbar_arrive(&empty[2]); }
   if (tid == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int k = R; k < R + 3 && k <= klast; ++k) issue(k);
+    for (unsigned k = R; k < R + 3 && k <= klast; ++k) {     // planes z0+5..z0+7 into the slots of z0-3..z0-1
+      mbar_wait(&empty[k & (R - 1)], 0);
+      issue(k);
+    }
   }
 
   // ---- march
-  for (int z = z0; z < z1; ++z) {
-    const int kc = z - z0 + 3;                               // ring position of the current plane
-    const long long off = off_xy + (long long)z * zstride;
-    Sys::template reload<DZ>(ptA, z, g, ks);
-    Sys::template reload<DZ>(ptB, z, g, ks);
+  unsigned kc = 3;                                           // ring position of the current plane
+  double2 raw_next = Sys::template fetch<DZ>(z0, g, ks);
+  for (int z = z0; z < z1; ++z, ++kc, off += zstride) {
+    if (tid == 0 && kc >= 4 && kc - 1 + R <= klast) {       // producer duty: recycle the slot of plane z-1
+      const unsigned kp = kc - 1;
+      mbar_wait(&empty[kp & (R - 1)], (kp / R) & 1);
+      issue(kp + R);
+    }
+    Sys::template apply<DZ>(ptA, raw_next, ks);              // the marching dim is shared by my two nodes
+    Sys::template apply<DZ>(ptB, raw_next, ks);
+    raw_next = Sys::template fetch<DZ>(min(z + 1, NZ - 1), g, ks);
 
-    // early global loads: y0 / aux / obstacle pairs, slow-dim neighbours
+    // early global loads: aux / obstacle pairs, slow-dim neighbours
     double2 y0v = make_double2(0.0, 0.0), auxv = y0v, obsv = y0v;
-    if (st.stage >= 2 && ok0) y0v = *reinterpret_cast<const double2*>(st.y0 + off);
-    if (st.stage == 3 && ok0) {
+    if (STAGE == 3 && ok0) {
       if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
       if (st.use_obs) obsv = ldg2(st.obs + off);
     }
@@ -239,8 +268,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
     // newest plane (z+3): into the queue, or a computed ghost plane
     {
-      const int k = kc + 3;
-      mbar_wait(&bars[k % R], (k / R) & 1);
+      const unsigned k = kc + 3, s = k & (R - 1);
+      mbar_wait(&full[s], (k / R) & 1);
       if (bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {
         const int dist = z + 3 - (NZ - 1);                   // 1..3 ; edge plane NZ-1 sits at queue index 6-dist
         const double2 ed = dist == 1 ? q[5] : (dist == 2 ? q[4] : q[3]);
@@ -248,15 +277,17 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
         q[6].x = ghost_extrapolate(ed.x, nx.x, dist, g.slope_mult[DZ]);
         q[6].y = ghost_extrapolate(ed.y, nx.y, dist, g.slope_mult[DZ]);
       } else {
-        q[6] = *reinterpret_cast<const double2*>(ring + (size_t)(k % R) * SLOT + myoff);
+        q[6] = *reinterpret_cast<const double2*>(ring + (size_t)s * SLOT + myoff);
       }
     }
-    double* cur = ring + (size_t)(kc % R) * SLOT;
+    const unsigned scur = kc & (R - 1);
+    double* cur = ring + (size_t)scur * SLOT;
+    if (STAGE >= 2) y0v = *reinterpret_cast<const double2*>(yring + (size_t)scur * YSLOT + ty * TX + 2 * tp);
 
     // ghost cells of the current plane in X / Y (tiles touching the domain boundary only)
     if (need_patch_x || need_patch_y) {
       if (need_patch_x) {
-        for (int e = tid; e < 6 * TY; e += NTHREADS) {
+        for (int e = tid; e < 6 * TY; e += NCONS) {
           const int r = e / 6 + 3, j = e % 6;
           const int x = j < 3 ? j - 3 : NX + (j - 3);        // ghost node index
           const int c = x - x0 + 4;
@@ -273,7 +304,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
         }
       }
       if (need_patch_y) {
-        for (int e = tid; e < 6 * TX; e += NTHREADS) {
+        for (int e = tid; e < 6 * TX; e += NCONS) {
           const int cc = e % TX + 4, j = e / TX;
           const int y = j < 3 ? j - 3 : NY + (j - 3);
           const int r = y - y0 + 3;
@@ -289,7 +320,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
           cur[r * BW + cc] = val;
         }
       }
-      __syncthreads();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // patched cells will later be overwritten by TMA
+      asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
     }
 
     // X window: columns c-4 .. c+5 of my row (c = my pair's first column)
@@ -303,6 +335,9 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     const double2 yp2 = *reinterpret_cast<const double2*>(cur + myoff + 2 * BW);
     const double2 yp3 = *reinterpret_cast<const double2*>(cur + myoff + 3 * BW);
     const double2 ctr = q[3];
+    // this warp is done with the current plane's slot
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[scur]);
 
     double pcA[D], hdA[D], pcB[D], hdB[D];
     double L, Rr;
@@ -339,24 +374,23 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
     // Hamiltonian + GLF dissipation (artificial_diss_glf.py:100: diss += 0.5*(R-L)*alpha)
     const double hamA = Sys::ham(ptA, pcA, ks), hamB = Sys::ham(ptB, pcB, ks);
-    double dissA = 0.0, dissB = 0.0;
+    double ydA = -hamA, ydB = -hamB;                         // ydot = -(ham - diss)
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const double aA = Sys::alpha(d, ptA, ks), aB = Sys::alpha(d, ptB, ks);
-      dissA += hdA[d] * aA;
-      dissB += hdB[d] * aB;
+      ydA = fma(hdA[d], aA, ydA);
+      ydB = fma(hdB[d], aB, ydB);
       if (red) {
         if (ok0) acc.amax[d] = fmax(acc.amax[d], aA);
         if (ok1) acc.amax[d] = fmax(acc.amax[d], aB);
       }
     }
-    const double ydA = dissA - hamA, ydB = dissB - hamB;      // ydot = -(ham - diss)
 
     // RK stage algebra + driver epilogue (see stage_update in hj_common.cuh), on the pair
     double oA, oB;
-    if (st.stage == 0) { oA = ydA; oB = ydB; }
-    else if (st.stage == 1) { oA = ctr.x + st.dt * ydA; oB = ctr.y + st.dt * ydB; }
-    else if (st.stage == 2) {
+    if (STAGE == 0) { oA = ydA; oB = ydB; }
+    else if (STAGE == 1) { oA = ctr.x + st.dt * ydA; oB = ctr.y + st.dt * ydB; }
+    else if (STAGE == 2) {
       oA = 0.25 * (3.0 * y0v.x + (ctr.x + st.dt * ydA));
       oB = 0.25 * (3.0 * y0v.y + (ctr.y + st.dt * ydB));
     } else {
@@ -375,14 +409,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     else if (ok0) st.out[off] = oA;
     if (red && ((ok0 && oA != oA) || (ok1 && oB != oB))) acc.nan = 1;
 
-    // rotate the queue, recycle the current plane's slot
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = q[k + 1];
-    __syncthreads();
-    if (tid == 0 && kc + R <= klast) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(kc + R);
-    }
   }
   if (RED) acc.flush(st.red);
 }
@@ -396,6 +424,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct HjTmaPlan {
   CUtensorMap tmap[3];
+  CUtensorMap tmap_y0;     // un-haloed TY x TX box on buffer 0 (y at the start of the step)
   TmaGeom geo;
   int tx, ty;
   size_t smem;
@@ -414,17 +443,18 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-template <class Sys, int WENO, int TX, int TY, bool RED>
+template <class Sys, int WENO, int TX, int TY, bool RED, int STAGE>
 static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const KGrid& g, const KSys& ks,
                               const KStage& st, cudaStream_t s) {
-  auto kern = k_stage_tma<Sys, WENO, TX, TY, RED>;
+  auto kern = k_stage_tma<Sys, WENO, TX, TY, RED, STAGE>;
+  const size_t smem = (size_t)R * ((TX + 8) * (TY + 6) + (STAGE >= 2 ? TX * TY : 0)) * 8 + 2 * R * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<(unsigned)p->nblocks, NTHREADS, p->smem, s>>>(tm, g, ks, st, p->geo);
+  kern<<<(unsigned)p->nblocks, NTHREADS_WS, smem, s>>>(tm, p->tmap_y0, g, ks, st, p->geo);
   return cudaGetLastError();
 }
 
@@ -437,17 +467,21 @@ struct TmaLauncher {
   const KStage& st;
   cudaStream_t s;
   cudaError_t err = cudaSuccess;
+  template <class Sys, int WENO>
+  cudaError_t by_stage(bool red) {
+    switch (st.stage) {
+      case 1: return red ? launch_one<Sys, WENO, 32, 16, true, 1>(p, tm, g, ks, st, s) : launch_one<Sys, WENO, 32, 16, false, 1>(p, tm, g, ks, st, s);
+      case 2: return red ? launch_one<Sys, WENO, 32, 16, true, 2>(p, tm, g, ks, st, s) : launch_one<Sys, WENO, 32, 16, false, 2>(p, tm, g, ks, st, s);
+      case 3: return red ? launch_one<Sys, WENO, 32, 16, true, 3>(p, tm, g, ks, st, s) : launch_one<Sys, WENO, 32, 16, false, 3>(p, tm, g, ks, st, s);
+      default: return cudaErrorNotSupported;
+    }
+  }
   template <class Sys>
   void operator()() {
     if constexpr (Sys::ND >= 3) {
       const bool red = st.want_reduce != 0;
-      if (weno == HJ_WENO_AS_SHIPPED) {
-        err = red ? launch_one<Sys, HJ_WENO_AS_SHIPPED, 32, 16, true>(p, tm, g, ks, st, s)
-                  : launch_one<Sys, HJ_WENO_AS_SHIPPED, 32, 16, false>(p, tm, g, ks, st, s);
-      } else {
-        err = red ? launch_one<Sys, HJ_WENO_INTENDED, 32, 16, true>(p, tm, g, ks, st, s)
-                  : launch_one<Sys, HJ_WENO_INTENDED, 32, 16, false>(p, tm, g, ks, st, s);
-      }
+      if (weno == HJ_WENO_AS_SHIPPED) err = by_stage<Sys, HJ_WENO_AS_SHIPPED>(red);
+      else err = by_stage<Sys, HJ_WENO_INTENDED>(red);
     } else {
       err = cudaErrorNotSupported;
     }
@@ -493,14 +527,15 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   p->geo.zcoord0 = zcoord0;
   p->geo.NZ = NZ;
   p->nblocks = tiles * p->geo.nzc;
-  p->smem = (size_t)R * (TX + 8) * (TY + 6) * 8 + R * 8;
+  p->smem = (size_t)R * (TX + 8) * (TY + 6) * 8 + 2 * R * 8;
   if (p->nblocks > 0x7fffffffLL) { delete p; snprintf(err, errlen, "grid too large"); return nullptr; }
-  for (int bidx = 0; bidx < 3; ++bidx) {
+  for (int bidx = 0; bidx < 4; ++bidx) {                    // 0..2: haloed boxes on the RK buffers; 3: y0 tile on buffer 0
     cuuint64_t dims[3] = {(cuuint64_t)NX, (cuuint64_t)NY, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 8, (cuuint64_t)pitch * NY * 8};
-    cuuint32_t box[3] = {(cuuint32_t)(TX + 8), (cuuint32_t)(TY + 6), 1};
+    cuuint32_t box[3] = {(cuuint32_t)(bidx < 3 ? TX + 8 : TX), (cuuint32_t)(bidx < 3 ? TY + 6 : TY), 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&p->tmap[bidx], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)bufs[bidx], dims, strides, box, es,
+    CUresult r = enc(bidx < 3 ? &p->tmap[bidx] : &p->tmap_y0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                     (void*)bufs[bidx < 3 ? bidx : 0], dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

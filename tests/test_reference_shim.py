@@ -1,0 +1,61 @@
+"""CPU, build container only: the numpy oracle against the LITERAL reference (imported from /root/reference through
+oracle/ref_shim.py) on fresh seeded inputs that are NOT among the committed fixtures.  Skipped where the reference
+tree is absent (the GPU box)."""
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_shim.install()
+    import LevelSetPy.BoundaryCondition as BC
+    import LevelSetPy.DynamicalSystems as DS
+    import LevelSetPy.ExplicitIntegration as EI
+    import LevelSetPy.Grids as G
+    import LevelSetPy.SpatialDerivative as SD
+    import LevelSetPy.Utilities as U
+    return dict(BC=BC, DS=DS, EI=EI, G=G, SD=SD, U=U)
+
+
+def col(x, dt=np.float64):
+    return np.asarray(x, dtype=dt).reshape(-1, 1)
+
+
+def test_oracle_matches_reference_on_fresh_inputs(ref):
+    from oracle import hj_oracle as orc
+    from oracle import systems as osys
+    N = [14, 19, 11]
+    g = ref["G"].createGrid(col([-4, -7, 0]), col([9, 6, 2 * np.pi * (1 - 1 / N[2])]), col(N, np.int64), pdDims=2)
+    rng = np.random.default_rng(2024)
+    data = np.ascontiguousarray(np.sqrt(g.xs[0] ** 2 + g.xs[1] ** 2) - 3 + 0.3 * np.cos(g.xs[2]) + 0.1 * rng.standard_normal(g.shape))
+    for d in range(3):
+        L, R = ref["SD"].upwindFirstWENO5a(g, data, d)
+        oL, oR = orc.upwind_first_weno5a(g, data, d, "as_shipped")
+        assert np.array_equal(np.asarray(L), oL) and np.array_equal(np.asarray(R), oR)
+    B = ref["U"].Bundle
+    rs = ref["DS"].DubinsVehicleRel(g, 3, 1.5)
+    sd = B(dict(grid=g, hamFunc=rs.hamiltonian, partialFunc=rs.dissipation,
+                dissFunc=ref["EI"].artificialDissipationGLF, CoStateCalc=ref["SD"].upwindFirstWENO5a))
+    os_ = osys.DubinsVehicleRel(g, 3, 1.5)
+    osd = orc.OracleSchemeData(grid=g, hamFunc=os_.hamiltonian, partialFunc=os_.dissipation)
+    opts = ref["EI"].odeCFLset(B({"factorCFL": 0.8, "singleStep": "on"}))
+    y0 = data.reshape(-1, 1)
+    t, y, _ = ref["EI"].odeCFL3(ref["EI"].termLaxFriedrichs, [0.0, 1.0], y0, opts, sd)
+    to, yo, _ = orc.ode_cfl3([0.0, 1.0], y0, osd, factor_cfl=0.8, single_step=True)
+    assert t == to and np.array_equal(np.asarray(y), yo)
+
+
+def test_reference_weno5a_is_fixed_weight_as_shipped(ref):
+    """SURVEY.md fact 4, checked on the literal reference: max |WENO5a - (.1 d0 + .6 d1 + .3 d2)| is at ulp level."""
+    g = ref["G"].createGrid(col([0, 0]), col([1, 2]), col([25, 31], np.int64))
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal(g.shape)
+    for d in range(2):
+        L, R = ref["SD"].upwindFirstWENO5a(g, data, d)
+        dL, dR, _ = ref["SD"].upwindFirstENO3aHelper(g, data, d, False, False)
+        wL = 0.1 * np.asarray(dL[0]) + 0.6 * np.asarray(dL[1]) + 0.3 * np.asarray(dL[2])
+        assert np.max(np.abs(np.asarray(L) - wL)) <= 16 * np.finfo(float).eps * np.max(np.abs(wL))

@@ -168,7 +168,6 @@ def run_ours(args):
         import torch.distributed as dist
         from levelsetpy_b200.slab import SlabSolver
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        g, _ = air3d_setup(lsp, n * world, n, n) if False else (None, None)
         # global grid: world*n planes along dim 0; each rank builds only its slab of the initial data
         gg = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / n)]),
                             np.array([n * world, n, n]), pdDims=2, low_mem=True)

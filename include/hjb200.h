@@ -172,6 +172,11 @@ int hj_stage_io(const hj_ctx* ctx, int stage, int* in_buffer, int* out_buffer);
  * (ordered-uint64 encoded) so a slab job can max-allreduce them before the stage.                       */
 int hj_eps_prepass(hj_ctx* ctx, void* stream, int buf, uint64_t** eps_dev);
 
+/* Slab edge ranks: fill the 3 stored halo planes of buffer `buf` on `side` (0 = below plane 0, 1 = above the last
+ * plane) with addGhostExtrapolate ghosts of the slab's own edge planes (add_ghost_extrapolate.py:88-110), for a
+ * global dim-0 boundary that is not periodic.  Interior slab faces get their halos from the neighbour instead. */
+int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
+
 /* odeCFL3(schemeFunc, [t, t_end], y, options{factorCFL,maxStep,singleStep='on'}, schemeData)
  * ExplicitIntegration/Integration/ode_cfl_3.py:11 for one CFL-limited step on a dense array that may live
  * on the host (is_host) -- upload, dt = min(factorCFL*stepBound, t_end-t, maxStep) (:142-143), step,

@@ -417,6 +417,16 @@ int hj_eps_prepass(hj_ctx* c, void* stream, int buf, uint64_t** eps_dev) {
   return HJ_OK;
 }
 
+int hj_fill_edge_halo(hj_ctx* c, void* stream, int buf, int side) {
+  if (!c || buf < 0 || buf > 2 || side < 0 || side > 1) return fail(HJ_ERR_INVALID, "hj_fill_edge_halo: bad argument");
+  if (!c->halo0) return fail(HJ_ERR_STATE, "hj_fill_edge_halo: context has no stored halo planes (dim 0 is not HJ_BC_HALO)");
+  CK(cudaSetDevice(c->device));
+  int r = ensure_buffers(c);
+  if (r) return r;
+  CK(hj_launch_edge_halo(c->buf[buf], c->plane, c->gp.N[0], side, c->gp.slope_mult[0], (cudaStream_t)stream));
+  return HJ_OK;
+}
+
 int hj_dev_alloc(int device, int64_t bytes, void** out) {
   if (!out || bytes < 0) return fail(HJ_ERR_INVALID, "hj_dev_alloc: bad argument");
   CK(cudaSetDevice(device));

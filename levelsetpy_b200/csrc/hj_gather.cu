@@ -219,6 +219,23 @@ __global__ void __launch_bounds__(256) k_repitch(const double* __restrict__ src,
   }
 }
 
+// slab edge ranks: the 3 stored halo planes outside a non-periodic global boundary of dim 0 are the
+// addGhostExtrapolate ghosts of this rank's own first / last two planes (add_ghost_extrapolate.py:88-110)
+__global__ void __launch_bounds__(256) k_edge_halo(double* __restrict__ buf, const long long plane, const int n0,
+                                                   const int side, const double m) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < plane; e += (long long)gridDim.x * blockDim.x) {
+    if (side == 0) {
+      const double edge = buf[(long long)HJ_GHOST * plane + e], next = buf[(long long)(HJ_GHOST + 1) * plane + e];
+#pragma unroll
+      for (int k = 0; k < HJ_GHOST; ++k) buf[(long long)k * plane + e] = ghost_extrapolate(edge, next, HJ_GHOST - k, m);
+    } else {
+      const double edge = buf[(long long)(HJ_GHOST + n0 - 1) * plane + e], next = buf[(long long)(HJ_GHOST + n0 - 2) * plane + e];
+#pragma unroll
+      for (int k = 0; k < HJ_GHOST; ++k) buf[(long long)(HJ_GHOST + n0 + k) * plane + e] = ghost_extrapolate(edge, next, k + 1, m);
+    }
+  }
+}
+
 template <int D>
 long long outer_count(const KGrid& g) {
   long long n = 1;
@@ -326,6 +343,12 @@ cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s
 }
 cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s) {
   k_init_eps<<<1, 32, 0, s>>>(eps, D);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_edge_halo(double* buf, long long plane, int n0, int side, double m, cudaStream_t s) {
+  k_edge_halo<<<flat_blocks(plane), 256, 0, s>>>(buf, plane, n0, side, m);
   hj_count_launch(1);
   return cudaGetLastError();
 }

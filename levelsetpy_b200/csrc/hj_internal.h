@@ -20,6 +20,7 @@ cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long lo
                               cudaStream_t s);
 cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s);
 cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s);
+cudaError_t hj_launch_edge_halo(double* buf, long long plane, int n0, int side, double m, cudaStream_t s);
 cudaError_t hj_launch_pack(const double* dense, double* pitched, const KGrid& g_dense, const KGrid& g_pitched,
                            cudaStream_t s);
 cudaError_t hj_launch_unpack(const double* pitched, double* dense, const KGrid& g_dense, const KGrid& g_pitched,

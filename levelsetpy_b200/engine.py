@@ -73,6 +73,14 @@ class DeviceBuffer:
         self._fin()
 
 
+class _RawCuda:
+    """``__cuda_array_interface__`` wrapper around memory the library owns (no ownership taken)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
 def grid_signature(grid):
     """(N, dx, bc kinds, towardZero, vs) of a reference-style grid Bundle, validated."""
     D = int(grid.dim)
@@ -295,6 +303,28 @@ class Engine:
     @property
     def field_elems(self):
         return int(self.lib.hj_field_elems(self.h))
+
+    # ------------------------------------------------------------------ slab (multi-GPU) support
+    def buffer_tensor(self, which):
+        """Zero-copy torch view (1-D, field_elems doubles, halo planes included) of RK buffer ``which``."""
+        t = _torch()
+        if t is None:
+            import torch as t
+        view = _RawCuda(self.buffer_ptr(which), self.field_elems, "<f8")
+        return t.as_tensor(view, device=t.device("cuda", self.device))
+
+    def fill_edge_halo(self, which, side):
+        L.check(self.lib.hj_fill_edge_halo(self.h, self.stream(), int(which), int(side)))
+
+    def eps_prepass(self, which):
+        """intended WENO: per-dim raw max(D1^2) of buffer ``which`` -> torch int64 view (D entries, ordered
+        encoding: larger value <=> larger int64) that a slab job max-allreduces before the stage."""
+        t = _torch()
+        if t is None:
+            import torch as t
+        p = C.c_void_p()
+        L.check(self.lib.hj_eps_prepass(self.h, self.stream(), int(which), C.byref(p)))
+        return t.as_tensor(_RawCuda(p.value, self.D, "<i8"), device=t.device("cuda", self.device))
 
     def stage_io(self, stage):
         a, b = C.c_int(), C.c_int()

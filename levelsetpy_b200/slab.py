@@ -1,0 +1,267 @@
+"""Multi-GPU: slab decomposition of the grid along dim 0 (the slowest-varying dim, so a slab is contiguous), one
+process per GPU.
+
+Per RK stage every rank
+  1. refreshes the 3 stored halo planes of the buffer the stage reads: interior faces get the neighbour's edge
+     planes (send/recv, NCCL over NVLink under ``torch.distributed``; wrap-around pair when dim 0 is periodic),
+     global non-periodic faces are filled locally with the addGhostExtrapolate ghosts of the rank's own edge planes
+     (add_ghost_extrapolate.py:88-110);
+  2. ('intended' WENO only) max-allreduces the per-dim max(D1^2) that defines the WENO epsilon
+     (upwind_first_weno5a.py:154-156);
+  3. launches the fused stage kernel on its slab.
+max_x alpha_d -- hence dt -- is state-only for every registered system: it is max-allreduced once and dt is then
+computed identically on every rank with the reference's own host arithmetic (artificial_diss_glf.py:104-109,
+ode_cfl_3.py:142-143).  No other data-path collective exists.
+
+The transport is a small strategy object so the same solver runs under ``torch.distributed`` (NCCL on GPUs, gloo
+in the CPU tests) and as several slabs inside one process (``LocalWorld``: the single-GPU test of the halo path).
+"""
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine, weno_mode_of
+from .functors import resolve
+from .integration import rk3_times
+from .utilities import isfield, warn
+
+__all__ = ["partition", "SlabSolver", "DistComm", "LocalWorld"]
+
+GHOST = L.HJ_GHOST
+
+
+def partition(n0, world):
+    """Contiguous [lo, hi) plane ranges of dim 0, sizes differing by at most one (larger slabs first)."""
+    base, rem = divmod(int(n0), int(world))
+    if base < GHOST:
+        raise ValueError("slab decomposition needs >= %d planes of dim 0 per rank (N[0]=%d over %d ranks)" % (GHOST, n0, world))
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class DistComm:
+    """torch.distributed transport (backend nccl on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(self, sends, recvs):
+        """sends/recvs: lists of (tensor, peer, tag).  Posted as one batch; returns after local completion is
+        ordered on the current stream (NCCL) / finished (gloo)."""
+        dist = self.dist
+        ops = [dist.P2POp(dist.irecv, t, p, self.group, tag) for t, p, tag in recvs]
+        ops += [dist.P2POp(dist.isend, t, p, self.group, tag) for t, p, tag in sends]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allreduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+class _LocalComm:
+    """One member of a LocalWorld: exchanges are deferred to the world, which copies between its slabs."""
+
+    def __init__(self, world, rank):
+        self.world_obj, self.rank, self.world = world, rank, world.world
+
+
+class SlabSolver:
+    """One rank's slab of a TVD-RK3 / WENO5 / GLF solve.
+
+    schemeData: the reference's bundle (grid = the GLOBAL grid).  ``comm``: DistComm() by default.
+    ``engine_factory(grid, weno, device, slab, backend)`` builds the per-slab context (default: the CUDA Engine)."""
+
+    def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None):
+        sd = schemeData
+        for f in ("grid", "hamFunc", "partialFunc"):
+            assert isfield(sd, f), "%s not in bundle thisschemeData" % f
+        self.comm = comm if comm is not None else DistComm()
+        self.rank, self.world = self.comm.rank, self.comm.world
+        g = sd.grid
+        self.grid = g
+        self.weno = weno_mode_of(sd)
+        self.adapter = resolve(sd.hamFunc, sd.partialFunc, g)
+        N0 = int(np.asarray(g.N).reshape(-1)[0])
+        self.lo, self.hi = partition(N0, self.world)[self.rank]
+        self.n0 = self.hi - self.lo
+        factory = engine_factory if engine_factory is not None else Engine
+        self.eng = factory(g, self.weno, device, (self.lo, self.hi), backend)
+        self.periodic0 = getattr(g.bdry[0], "__name__", "") == "addGhostPeriodic"
+        self.lo_peer = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.periodic0 else None)
+        self.hi_peer = self.rank + 1 if self.rank < self.world - 1 else (0 if self.periodic0 else None)
+        self.plane = self.eng.plane_elems
+        self.bufs = [self.eng.buffer_tensor(b) for b in range(3)]
+        self._alpha = None
+        self._tables = list(enumerate(self.adapter.tables(g)))
+        self.shape = (self.n0,) + tuple(int(x) for x in np.asarray(g.N).reshape(-1)[1:])
+
+    # ------------------------------------------------------------------ fields
+    def upload(self, slab, field=L.FIELD_STATE):
+        """``slab``: this rank's planes [lo, hi) of the field, shape (hi-lo, N1, ...), numpy or torch CUDA."""
+        self.eng.upload(slab, field)
+
+    def download(self, out=None):
+        y = self.eng.download(shape=self.shape)
+        if out is not None:
+            np.copyto(np.asarray(out).reshape(self.shape), y)
+            return out
+        return y
+
+    # ------------------------------------------------------------------ halos
+    def _faces(self, b):
+        """(send_up, send_down, recv_lo, recv_hi) views of buffer b: my top / bottom 3 interior planes and my
+        lower / upper halo planes."""
+        p, n0, t = self.plane, self.n0, self.bufs[b]
+        return (t[n0 * p:(n0 + GHOST) * p], t[GHOST * p:2 * GHOST * p], t[0:GHOST * p],
+                t[(n0 + GHOST) * p:(n0 + 2 * GHOST) * p])
+
+    def halo_ops(self, b):
+        """Point-to-point operations that refresh buffer b's halos: tag 0 travels up (towards higher ranks), tag 1
+        down.  Receives are listed in the order the peer posts the matching sends (up first, then down), so the
+        two messages of a 2-rank periodic ring pair up correctly on NCCL, which matches by order, not tag."""
+        up, down, rlo, rhi = self._faces(b)
+        sends, recvs = [], []
+        if self.hi_peer is not None and self.hi_peer != self.rank:
+            sends.append((up, self.hi_peer, 0))
+        if self.lo_peer is not None and self.lo_peer != self.rank:
+            sends.append((down, self.lo_peer, 1))
+            recvs.append((rlo, self.lo_peer, 0))
+        if self.hi_peer is not None and self.hi_peer != self.rank:
+            recvs.append((rhi, self.hi_peer, 1))
+        return sends, recvs
+
+    def finish_halos(self, b):
+        """The halo faces no neighbour fills: periodic self-wrap (world == 1) and extrapolated global edges."""
+        up, down, rlo, rhi = self._faces(b)
+        if self.lo_peer == self.rank:
+            rlo.copy_(up)
+            rhi.copy_(down)
+        if self.lo_peer is None:
+            self.eng.fill_edge_halo(b, 0)
+        if self.hi_peer is None:
+            self.eng.fill_edge_halo(b, 1)
+
+    def exchange(self, b):
+        if isinstance(self.comm, _LocalComm):
+            raise RuntimeError("slabs of a LocalWorld are stepped through LocalWorld.step")
+        sends, recvs = self.halo_ops(b)
+        self.comm.exchange(sends, recvs)
+        self.finish_halos(b)
+
+    # ------------------------------------------------------------------ dt
+    def local_alpha(self):
+        """max over THIS slab of the state-only alpha_d (device reduction, cached by the context)."""
+        self.eng.set_system(self.adapter.system_id, self.adapter.block(), self._tables)
+        return np.asarray(self.eng.alpha_max()[0], dtype=np.float64)
+
+    def step_bound(self, block):
+        """stepBound = 1 / sum_d max_x alpha_d / dx_d with the maxima taken over the WHOLE grid
+        (artificial_diss_glf.py:104-109, dims summed in order)."""
+        al = self.adapter.alphas(block)
+        if al is None:
+            if self._alpha is None:
+                import torch
+                local, _ = self.eng.alpha_max()
+                t = torch.tensor(np.asarray(local, dtype=np.float64), device=self.bufs[0].device)  # system set by begin_step
+                self._alpha = [float(x) for x in self.comm.allreduce_max(t).cpu().numpy()]
+            al = self._alpha
+        inv = 0
+        for d in range(self.eng.D):
+            inv = inv + (al[d] / self.eng.dx[d])
+        return 1 / inv
+
+    # ------------------------------------------------------------------ stepping
+    def begin_step(self, t, t_end, factorCFL, maxStep=np.finfo(np.float64).max):
+        """Host part of one odeCFL3 step (ode_cfl_3.py:129-143): parameter blocks for the three RHS evaluations
+        and the CFL-limited dt -- identical on every rank."""
+        ad = self.adapter
+        blocks = [ad.block()]
+        self.eng.set_system(ad.system_id, blocks[0], self._tables)
+        sb = self.step_bound(blocks[0])
+        dt = float(np.min(np.hstack((factorCFL * sb, t_end - t, maxStep))))
+        if ad.time_varying:
+            safety = min(1.0, 1.2 * factorCFL)
+            for name in ("Second", "Third"):
+                b = ad.block()
+                blocks.append(b)
+                sbk = self.step_bound(b)
+                if dt > safety * sbk:
+                    warn("%s substep violated CFL effective number %s" % (name, dt / sbk))
+        else:
+            blocks = [None, None, None]
+        self._step = (t, dt, blocks)
+        return dt
+
+    def run_stage(self, stage, comp=L.COMP_NONE, use_obstacle=False):
+        """Stage kernel on this slab; the halos of the buffer it reads must already be current."""
+        t, dt, blocks = self._step
+        if self.weno == "intended":
+            eps = self.eng.eps_prepass(self.eng.stage_io(stage)[0])
+            if self.world > 1:
+                self.comm.allreduce_max(eps)
+        self.eng.stage(stage, t, dt, blocks[stage - 1], comp, use_obstacle)
+
+    def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
+        """One CFL-limited TVD-RK3 step of the distributed field.  Returns (t_new, dt)."""
+        dt = self.begin_step(t, t_end, factorCFL, maxStep)
+        for stage in (1, 2, 3):
+            self.exchange(self.eng.stage_io(stage)[0])
+            self.run_stage(stage, comp, use_obstacle)
+        return rk3_times(t, dt)[2], dt
+
+
+class LocalWorld:
+    """``world`` slabs driven in lock-step inside ONE process (all on one device): exercises exactly the halo,
+    edge-fill and reduction code of the multi-process path, with tensor copies standing in for send/recv and an
+    element-wise maximum over the slabs standing in for the max-allreduce."""
+
+    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None):
+        self.world = int(world)
+        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory) for r in range(self.world)]
+
+    def upload(self, data, field=L.FIELD_STATE):
+        for s in self.slabs:
+            s.upload(np.ascontiguousarray(data[s.lo:s.hi]), field)
+
+    def download(self):
+        return np.concatenate([s.download() for s in self.slabs], axis=0)
+
+    def _exchange(self, b):
+        for s in self.slabs:
+            sends, _ = s.halo_ops(b)
+            for t, peer, tag in sends:
+                _, _, rlo, rhi = self.slabs[peer]._faces(b)
+                (rlo if tag == 0 else rhi).copy_(t)
+        for s in self.slabs:
+            s.finish_halos(b)
+
+    @staticmethod
+    def _max_over(tensors):
+        import torch
+        m = torch.stack([x.clone() for x in tensors]).max(dim=0).values
+        for x in tensors:
+            x.copy_(m)
+
+    def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
+        if not self.slabs[0].adapter.host_alpha and self.slabs[0]._alpha is None:
+            amax = np.max(np.stack([s.local_alpha() for s in self.slabs]), axis=0)
+            for s in self.slabs:
+                s._alpha = [float(x) for x in amax]
+        dts = [s.begin_step(t, t_end, factorCFL, maxStep) for s in self.slabs]
+        assert all(d == dts[0] for d in dts), "dt must be identical on every rank"
+        for stage in (1, 2, 3):
+            b = self.slabs[0].eng.stage_io(stage)[0]
+            self._exchange(b)
+            if self.slabs[0].weno == "intended":
+                self._max_over([s.eng.eps_prepass(b) for s in self.slabs])
+            for s in self.slabs:
+                t_, dt_, blocks = s._step
+                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+        return rk3_times(t, dts[0])[2], dts[0]

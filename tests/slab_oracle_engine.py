@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for the per-slab CUDA context (levelsetpy_b200.engine.Engine with
+``slab=(lo, hi)``) whose stage "kernel" is the numpy oracle evaluated on the haloed slab.  It lets the world-size-2
+gloo tests run the REAL SlabSolver (partitioning, halo send/recv ordering, edge-halo fill, alpha max-allreduce, dt)
+on CPU and compare against the single-domain oracle.  Same layout as the device context: three RK buffers of
+(3 + n0 + 3) dim-0 planes, interior at plane offset 3."""
+import numpy as np
+import torch
+
+from oracle import hj_oracle as orc
+from oracle import systems as osys
+
+G = 3
+
+
+class _SubGrid:
+    pass
+
+
+class OracleSlabEngine:
+    def __init__(self, grid, weno, device, slab, backend=None):
+        lo, hi = slab
+        self.grid, self.weno, self.lo, self.hi = grid, weno, lo, hi
+        self.D = int(grid.dim)
+        Ng = [int(x) for x in np.asarray(grid.N).reshape(-1)]
+        self.n0 = hi - lo
+        self.N = [self.n0] + Ng[1:]
+        self.dx = [float(x) for x in np.asarray(grid.dx).reshape(-1)]
+        self.plane_elems = int(np.prod(Ng[1:]))
+        self.field_elems = self.plane_elems * (self.n0 + 2 * G)
+        self.hshape = (self.n0 + 2 * G,) + tuple(Ng[1:])
+        self._buf = [np.zeros(self.field_elems) for _ in range(3)]
+        self._aux = self._obs = None
+        self.nparams = 0
+        # haloed sub-grid: dim 0 carries n0+6 nodes whose interior coordinates are the global ones
+        sg = _SubGrid()
+        v0 = np.asarray(grid.vs[0], dtype=np.float64).reshape(-1)
+        ext = v0[lo] + self.dx[0] * (np.arange(self.n0 + 2 * G) - G)
+        ext[G:G + self.n0] = v0[lo:hi]
+        sg.dim, sg.dx, sg.shape = self.D, grid.dx, self.hshape
+        sg.N = np.array(self.hshape).reshape(-1, 1)
+        sg.vs = [ext] + [np.asarray(grid.vs[d]).reshape(-1) for d in range(1, self.D)]
+        sg.bdry = [_extrap] + list(grid.bdry[1:])
+        sg.bdryData = [None] + list(grid.bdryData[1:]) if getattr(grid, "bdryData", None) is not None else None
+        self.sub = sg
+        gd = grid.bdryData[0] if getattr(grid, "bdryData", None) is not None else None
+        self.tz0 = bool(getattr(gd, "towardZero", False)) if gd is not None else False
+
+    # --- the interface SlabSolver uses
+    def buffer_tensor(self, b):
+        return torch.from_numpy(self._buf[b])
+
+    def _interior(self, a):
+        return a.reshape(self.hshape)[G:G + self.n0]
+
+    def upload(self, a, field=0):
+        a = np.asarray(a, dtype=np.float64).reshape(self.N)
+        if field == 0:
+            self._interior(self._buf[0])[...] = a
+        elif field == 1:
+            self._aux = a.copy()
+        else:
+            self._obs = a.copy()
+
+    def download(self, like=None, field=0, shape=None):
+        out = self._interior(self._buf[0]).copy()
+        return out.reshape(shape) if shape is not None else out
+
+    def set_system(self, system_id, params, tables=()):
+        p = np.asarray(params, dtype=np.float64)
+        self.nparams = p.size
+        if system_id == 1:
+            self.sys = osys.DubinsVehicleRel(self.sub, p[0], p[2])
+        elif system_id == 2:
+            self.sys = osys.DoubleIntegrator(self.sub, p[0])
+        else:
+            raise NotImplementedError(system_id)
+
+    def alpha_max(self, t=0.0):
+        sd = orc.OracleSchemeData(grid=self.sub, hamFunc=self.sys.hamiltonian, partialFunc=self.sys.dissipation)
+        a = []
+        for d in range(self.D):
+            al = self.sys.dissipation(t, None, None, None, sd, d)
+            if isinstance(al, np.ndarray):
+                al = np.max(np.broadcast_to(al, self.hshape)[G:G + self.n0])
+            a.append(float(al))
+        return np.array(a), None
+
+    def stage_io(self, stage):
+        return (0, 0, 1, 2)[stage], (0, 1, 2, 0)[stage]
+
+    def fill_edge_halo(self, b, side):
+        h = self._buf[b].reshape(self.hshape)
+        gh = orc.add_ghost_extrapolate(h[G:G + self.n0], 0, G, self.tz0)
+        if side == 0:
+            h[:G] = gh[:G]
+        else:
+            h[G + self.n0:] = gh[G + self.n0:]
+
+    def stage(self, stage, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=False):
+        i, o = self.stage_io(stage)
+        sd = orc.OracleSchemeData(grid=self.sub, hamFunc=self.sys.hamiltonian, partialFunc=self.sys.dissipation)
+        h = self._buf[i].reshape(self.hshape)
+        ydot, _ = orc.term_lax_friedrichs(t, h.reshape(-1, 1), sd, self.weno)
+        ydot = ydot.reshape(self.hshape)[G:G + self.n0]
+        yin = h[G:G + self.n0]
+        y0 = self._interior(self._buf[0]).copy()
+        if stage == 1:
+            out = yin + dt * ydot
+        elif stage == 2:
+            out = 0.25 * (3 * y0 + (yin + dt * ydot))
+        else:
+            out = (1 / 3) * (y0 + 2 * (yin + dt * ydot))
+            if comp == 1:
+                out = np.minimum(out, y0)
+            elif comp == 2:
+                out = np.maximum(out, y0)
+            elif comp == 3:
+                out = np.minimum(out, self._aux)
+            elif comp == 4:
+                out = np.maximum(out, self._aux)
+            if use_obstacle:
+                out = np.maximum(out, -self._obs)
+        self._interior(self._buf[o])[...] = out
+
+
+def _extrap(*a, **k):
+    raise RuntimeError("token only")
+
+
+_extrap.__name__ = "addGhostExtrapolate"

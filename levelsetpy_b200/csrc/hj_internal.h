@@ -27,9 +27,9 @@ cudaError_t hj_launch_unpack(const double* pitched, double* dense, const KGrid& 
                              cudaStream_t s);
 
 // TMA backend (hj_tma.cu)
-struct HjTmaPlan;   // opaque: tensor maps + tile geometry for one context
+struct HjTmaPlan;   // tensor maps + tile geometry for one context (hj_tma_plan.h)
 HjTmaPlan* hj_tma_plan_create(const KGrid& g_pitched, int system_id, int weno, double* const bufs[3], int halo0,
-                              char* err, int errlen);
+                              char* err, int errlen, int tile_y = 0);
 void hj_tma_plan_destroy(HjTmaPlan* p);
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
                                 const KStage& st, int in_buf, cudaStream_t s);

@@ -1,0 +1,485 @@
+// hj_tma_kernel.cuh -- the fused RHS + RK-stage kernel as a streamed plane ring (TMA backend), device side.
+//
+// Layout of the work (grid dims named X = D-1 (contiguous), Y = D-2, Z = D-3, "slow" = 0..D-4):
+//   * a CTA owns a TY x TX tile of (Y, X) and marches a chunk of CZ planes along Z;
+//   * each Z-plane of the tile, with its 3-cell X/Y halo (box (TY+6) x (TX+8) doubles; 4 columns on each side in X
+//     keep every row and every thread's 2-node pair 16-byte aligned), is brought into a ring of R shared-memory
+//     slots by ONE cp.async.bulk.tensor (TMA) per plane, signalled on an mbarrier; out-of-range box parts are
+//     zero-filled by the TMA unit and the threads that own a boundary node replace them IN REGISTERS with the
+//     extrapolated / periodic ghost cells (add_ghost_extrapolate.py:88-110, add_ghost_periodic.py:78-87) -- no
+//     padded copy of the field ever exists, the ring is never written by a thread, and no CTA-wide barrier runs
+//     in the steady state;
+//   * every thread owns two X-adjacent nodes: planes z-3..z-1 of the Z stencil live in a 3-deep register queue,
+//     planes z+1..z+3 are read from their ring slots (they are resident anyway), the X and Y stencils are read
+//     from the current plane's slot, all with 16-byte LDS; slow-dim neighbours (D >= 4) come straight from L2/HBM
+//     with 16-byte read-only loads;
+//   * the march is split into a head, a FAST segment (interior planes of interior tiles: no ghost code in the loop
+//     body) and a tail, so that the steady-state loop is compact;
+//   * the Hamiltonian, GLF dissipation, RK stage algebra and the driver epilogue are applied in registers and
+//     the result leaves with one 16-byte store per thread.  DRAM traffic per node: 8 B read + 8 B write
+//     (+8 B for y0 in stages 2/3) = the algorithmic 16/24/24 B.
+//
+// Reference behaviour restated: see hj_common.cuh header.
+#pragma once
+#include <cuda.h>
+
+#include "hj_common.cuh"
+#include "hj_systems.cuh"
+
+struct TmaGeom {
+  int nxt, nyt, nzc, cz;      // tiles in X, Y; Z chunks; planes per chunk
+  long long nslow;            // product of slow dims
+  long long zcoord0;          // TMA dim-2 coordinate of (slow = 0, z = 0)  (halo planes on dim 0 shift it)
+  int NZ;
+};
+
+// tuning knobs of the plane-ring kernel
+template <int R_, int MINB_, int UNROLL_, int TY_ = 16>
+struct TmaCfg {
+  static constexpr int R = R_;            // ring slots (planes z+1..z+3 are needed, the rest is prefetch distance)
+  static constexpr int MINB = MINB_;      // resident CTAs per SM the register allocation is sized for
+  static constexpr int UNROLL = UNROLL_;  // planes per trip of the fast march loop
+  static constexpr int TX = 32, TY = TY_; // tile (X, Y); one node pair per thread
+  static constexpr int NTHREADS = (TX / 2) * TY;
+  static constexpr int BW = TX + 8, BH = TY + 6, SLOT = BW * BH;   // haloed plane box (doubles)
+  static constexpr int YSLOT_FULL = TX * TY;
+  template <int STAGE>
+  static constexpr size_t smem_bytes() {
+    return (size_t)R * (SLOT + (STAGE >= 2 ? YSLOT_FULL : 0)) * 8 + 2 * R * 8;
+  }
+};
+
+namespace hjtma {
+
+constexpr int TX = 32;
+constexpr int BW = TX + 8;                       // slot row length (doubles)
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+HJ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+HJ_DEV void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+HJ_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+HJ_DEV void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+HJ_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+HJ_DEV void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+HJ_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+HJ_DEV double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// ------------------------------------------------------------------------------------------ stencil math on pairs
+// derivC and 0.5*(derivR - derivL) of the as-shipped (fixed-weight) scheme straight from the 7 nodes; the
+// coefficients are host-precomputed (KGrid::ca1..cb) and used as constant-bank operands:
+//   derivC    = ca1 (v4-v2) + ca2 (v5-v1) + ca3 (v6-v0)                       (= 0.5*(L+R), 6 flops)
+//   0.5*(R-L) = cb (v0+v6 - 6 (v1+v5) + 15 (v2+v4) - 20 v3)                   (sixth difference, 7 flops)
+// i.e. 13 fp64 instructions per node per dim instead of ~60 for the divided-difference tables + weightWENO.
+template <int WENO>
+HJ_DEV void pc_hd(const double v0, const double v1, const double v2, const double v3, const double v4, const double v5,
+                  const double v6, const KGrid& g, const int d, double inv_eps, double& pc, double& hd, double& L,
+                  double& Rr, const bool need_lr) {
+  if (WENO == HJ_WENO_AS_SHIPPED) {
+    pc = g.ca1[d] * (v4 - v2) + g.ca2[d] * (v5 - v1) + g.ca3[d] * (v6 - v0);
+    double t = fma(-6.0, v1 + v5, v0 + v6);
+    t = fma(15.0, v2 + v4, t);
+    t = fma(-20.0, v3, t);
+    hd = g.cb[d] * t;
+    if (need_lr) { L = pc - hd; Rr = pc + hd; }
+  } else {
+    const double v[7] = {v0, v1, v2, v3, v4, v5, v6};
+    upwind5_weno(v, g.dxinv[d], inv_eps, L, Rr);
+    pc = 0.5 * (L + Rr);
+    hd = 0.5 * (Rr - L);
+  }
+}
+
+// one slow-dim neighbour pair (k = -3..3, k != 0) with on-the-fly boundary handling; CTA-uniform branches
+HJ_DEV double2 slow_neighbor(const double* p, int i, int k, int n, long long s, int bc, double m) {
+  const int j = i + k;
+  if ((j >= 0 && j < n) || bc == HJ_BC_HALO) return ldg2(p + (long long)k * s);
+  if (bc == HJ_BC_PERIODIC) return ldg2(p + (long long)((j < 0 ? j + n : j - n) - i) * s);
+  const int e = j < 0 ? 0 : n - 1, nx = j < 0 ? 1 : n - 2, dist = j < 0 ? -j : j - (n - 1);
+  const double2 a = ldg2(p + (long long)(e - i) * s), b = ldg2(p + (long long)(nx - i) * s);
+  return make_double2(ghost_extrapolate(a.x, b.x, dist, m), ghost_extrapolate(a.y, b.y, dist, m));
+}
+
+// ------------------------------------------------------------------------------------------ ghost cells in registers
+// X window of a thread: columns ix-4 .. ix+5 in (w0.x w0.y w1.x w1.y w2.x w2.y w3.x w3.y w4.x w4.y); the stencils of
+// its two nodes use columns ix-3 .. ix+4.  Columns outside [0, NX) were zero-filled by the TMA unit (or belong to a
+// neighbouring tile of a periodic dim) and are replaced here.  `srow` = my row inside the current slot (column
+// x0-4), `grow` = column 0 of my row in global memory.  Only called by threads with a node inside the grid.
+HJ_DEV void patch_x(double2& w0, double2& w1, double2& w2, double2& w3, double2& w4, const int ix, const int x0,
+                    const int NX, const int bc, const double m, const double* srow, const double* grow) {
+  if (ix < 3) {                                               // columns ix-3 .. ix-1 may be < 0
+    double e0 = 0.0, e1 = 0.0;
+    if (bc != HJ_BC_PERIODIC) { e0 = srow[0 - x0 + 4]; e1 = srow[1 - x0 + 4]; }
+    auto gl = [&](int c) { return bc == HJ_BC_PERIODIC ? __ldg(grow + c + NX) : ghost_extrapolate(e0, e1, -c, m); };
+    if (ix - 3 < 0) w0.y = gl(ix - 3);
+    if (ix - 2 < 0) w1.x = gl(ix - 2);
+    if (ix - 1 < 0) w1.y = gl(ix - 1);
+  }
+  if (ix + 4 >= NX) {                                         // columns ix+1 .. ix+4 may be >= NX
+    double f0 = 0.0, f1 = 0.0;
+    if (bc != HJ_BC_PERIODIC) { f0 = srow[NX - 1 - x0 + 4]; f1 = srow[NX - 2 - x0 + 4]; }
+    auto gr = [&](int c) { return bc == HJ_BC_PERIODIC ? __ldg(grow + c - NX) : ghost_extrapolate(f0, f1, c - (NX - 1), m); };
+    if (ix + 1 >= NX) w2.y = gr(ix + 1);
+    if (ix + 2 >= NX) w3.x = gr(ix + 2);
+    if (ix + 3 >= NX) w3.y = gr(ix + 3);
+    if (ix + 4 >= NX) w4.x = gr(ix + 4);
+  }
+}
+
+// Y neighbours of a thread's pair: rows iy-3 .. iy+3.  `scol` = row y0-3 of the current slot at my column pair,
+// `gcol` = row 0 at my column pair in global memory, `ys` = global row stride.
+HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, double2& yp2, double2& yp3, const int iy,
+                    const int y0, const int NY, const int bc, const double m, const double* scol, const double* gcol,
+                    const long long ys) {
+  if (iy < 3) {
+    double2 e0 = make_double2(0.0, 0.0), e1 = e0;
+    if (bc != HJ_BC_PERIODIC) { e0 = lds2(scol + (0 - y0 + 3) * BW); e1 = lds2(scol + (1 - y0 + 3) * BW); }
+    auto gt = [&](int r) {
+      if (bc == HJ_BC_PERIODIC) return ldg2(gcol + (long long)(r + NY) * ys);
+      return make_double2(ghost_extrapolate(e0.x, e1.x, -r, m), ghost_extrapolate(e0.y, e1.y, -r, m));
+    };
+    if (iy - 3 < 0) ym3 = gt(iy - 3);
+    if (iy - 2 < 0) ym2 = gt(iy - 2);
+    if (iy - 1 < 0) ym1 = gt(iy - 1);
+  }
+  if (iy + 3 >= NY) {
+    double2 f0 = make_double2(0.0, 0.0), f1 = f0;
+    if (bc != HJ_BC_PERIODIC) { f0 = lds2(scol + (NY - 1 - y0 + 3) * BW); f1 = lds2(scol + (NY - 2 - y0 + 3) * BW); }
+    auto gb = [&](int r) {
+      if (bc == HJ_BC_PERIODIC) return ldg2(gcol + (long long)(r - NY) * ys);
+      const int dist = r - (NY - 1);
+      return make_double2(ghost_extrapolate(f0.x, f1.x, dist, m), ghost_extrapolate(f0.y, f1.y, dist, m));
+    };
+    if (iy + 1 >= NY) yp1 = gb(iy + 1);
+    if (iy + 2 >= NY) yp2 = gb(iy + 2);
+    if (iy + 3 >= NY) yp3 = gb(iy + 3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+// Producer/consumer ring without a CTA-wide barrier:
+//   full[s]  : armed by the producer thread (expect_tx), completed by the TMA unit when plane box s has landed
+//   empty[s] : one arrival per warp when that warp no longer needs the plane in slot s
+// All 8 warps are consumers (one node pair per thread); lane 0 of warp 0 doubles as the producer: at the top of
+// step z it waits until every warp has released plane z-1 (normally already true: the ring runs R-4 planes
+// ahead of need) and re-arms that slot with plane z+R-1.
+template <class Sys, int WENO, bool RED, int STAGE, class Cfg>
+__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB)
+k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y0, const KGrid g,
+            const KSys ks, const KStage st, const TmaGeom geo) {
+  constexpr int D = Sys::ND;
+  static_assert(D >= 3, "the plane-ring kernel needs a Z dim");
+  constexpr int DX = D - 1, DY = D - 2, DZ = D - 3, NSLOW = D - 3;
+  constexpr int PAIRS = TX / 2;
+  constexpr int R = Cfg::R;
+  constexpr int TY = Cfg::TY, NTHREADS = Cfg::NTHREADS, NCONS_WARPS = NTHREADS / 32;
+  constexpr int SLOT = Cfg::SLOT, YSLOT_FULL = Cfg::YSLOT_FULL;
+  static_assert(Cfg::BW == BW && NTHREADS % 32 == 0, "tile shape");
+  static_assert(PAIRS * TY == NTHREADS, "tile must give every thread one node pair");
+  static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
+  static_assert(R >= 6 && R <= 16, "ring depth");
+  // stages 2/3 also stream the un-haloed y0 tile (TY x TX) of each plane through the ring, on the same barrier
+  constexpr int YSLOT = (STAGE >= 2) ? YSLOT_FULL : 0;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* yring = ring + (size_t)R * SLOT;
+  const uint32_t ring_s = smem_u32(smem_raw);
+  const uint32_t yring_s = ring_s + R * SLOT * 8;
+  const uint32_t full_s = ring_s + R * (SLOT + YSLOT) * 8;
+  const uint32_t empty_s = full_s + R * 8;
+
+  const int tid = threadIdx.x;
+  long long b = blockIdx.x;
+  const int xt = (int)(b % geo.nxt); b /= geo.nxt;
+  const int yt = (int)(b % geo.nyt); b /= geo.nyt;
+  const int zc = (int)(b % geo.nzc); b /= geo.nzc;
+  const long long slow_flat = b;
+  const int NX = g.N[DX], NY = g.N[DY], NZ = g.N[DZ];
+  const int x0 = xt * TX, y0 = yt * TY, z0 = zc * geo.cz;
+  const int z1 = min(z0 + geo.cz, NZ);
+  const int bcx = g.bc[DX], bcy = g.bc[DY], bcz = g.bc[DZ];
+  const unsigned klast = (unsigned)((z1 - 1 + 3) - (z0 - 3));   // ring position of the last plane this chunk needs
+  const int zcoord_base = (int)(geo.zcoord0 + slow_flat * NZ);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) { mbar_init(full_s + 8 * s, 1); mbar_init(empty_s + 8 * s, NCONS_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // plane with ring position k -> slot s: TMA load, or a bare arrival for a computed ghost plane
+  auto issue = [&](unsigned k, unsigned s) {
+    const int zp = z0 - 3 + (int)k;
+    int zsrc = zp;
+    bool load = true;
+    if (zp < 0 || zp >= NZ) {
+      if (bcz == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NZ : zp - NZ;
+      else if (bcz == HJ_BC_EXTRAPOLATE) load = false;          // ghost plane: computed from the register queue
+    }
+    // the y0 tile rides along for planes that will be "current" (ring positions 3 .. klast-3)
+    const bool ytile = STAGE >= 2 && k >= 3 && k + 3 <= klast;
+    const uint32_t fb = full_s + 8 * s;
+    if (load) {
+      mbar_expect_tx(fb, (SLOT + (ytile ? YSLOT : 0)) * 8);
+      tma_load_3d(ring_s + s * (SLOT * 8), &tmap, fb, x0 - 4, y0 - 3, zcoord_base + zsrc);
+      if (ytile) tma_load_3d(yring_s + s * (YSLOT * 8), &tmap_y0, fb, x0, y0, zcoord_base + zp);
+    } else {
+      mbar_arrive(fb);
+    }
+  };
+  if (tid == 0) {
+    for (unsigned k = 0; k < (unsigned)R && k <= klast; ++k) issue(k, k);
+  }
+
+  // ================================================================== consumers
+  const int lane = tid & 31;
+  const int tp = tid % PAIRS, ty = tid / PAIRS;
+  int idx[D];
+  {
+    long long r = slow_flat;
+#pragma unroll
+    for (int d = NSLOW - 1; d >= 0; --d) { idx[d] = (int)(r % g.N[d]); r /= g.N[d]; }
+  }
+  const int ix = x0 + 2 * tp, iy = y0 + ty;
+  const bool ok0 = ix < NX && iy < NY, ok1 = ix + 1 < NX && iy < NY;
+  long long off = (long long)iy * g.stride[DY] + ix + (long long)z0 * g.stride[DZ];   // stride[DX] == 1
+#pragma unroll
+  for (int d = 0; d < NSLOW; ++d) off += (long long)idx[d] * g.stride[d];
+  const long long zstride = g.stride[DZ];
+
+  double inv_eps[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
+  // system state of my two nodes: everything that does not depend on the marching dim is loaded once
+  idx[DZ] = z0;
+  idx[DY] = min(iy, NY - 1);                                 // clamp: masked threads must not read past the axis tables
+  idx[DX] = min(ix, NX - 1);
+  typename Sys::Pt ptA = Sys::load(idx, g, ks);
+  idx[DX] = min(ix + 1, NX - 1);
+  typename Sys::Pt ptB = Sys::load(idx, g, ks);
+
+  const int myoff = (ty + 3) * BW + 4 + 2 * tp;              // my pair inside a slot (doubles); 16-byte aligned
+  // does any node of this tile have an X / Y stencil that leaves the grid?  (CTA-uniform)
+  const bool need_patch_x = x0 - 3 < 0 || x0 + TX + 2 >= NX;
+  const bool need_patch_y = y0 - 3 < 0 || y0 + TY + 2 >= NY;
+
+  RedAcc<D> acc;
+  acc.init();
+
+  // ---- prologue: planes z0-3 .. z0-1 (ring positions 0..2) go into the Z register queue and their slots are handed
+  // back; planes z0 .. z0+2 must have landed before the march starts (the march only waits for plane z+3)
+  double2 q[3];                                              // planes z-3, z-2, z-1 of my pair
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    mbar_wait(full_s + 8 * k, 0);
+    if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
+  }
+  if (bcz == HJ_BC_EXTRAPOLATE && z0 == 0) {
+    const double2 e0 = lds2(ring + (size_t)3 * SLOT + myoff), e1 = lds2(ring + (size_t)4 * SLOT + myoff);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                            // planes -3,-2,-1 from planes 0,1
+      q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - k, g.slope_mult[DZ]);
+      q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - k, g.slope_mult[DZ]);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { mbar_arrive(empty_s + 0); mbar_arrive(empty_s + 8); mbar_arrive(empty_s + 16); }
+  if (tid == 0) {
+    for (unsigned k = R; k < (unsigned)R + 3 && k <= klast; ++k) {     // the slots of z0-3..z0-1 get planes R..R+2
+      mbar_wait(empty_s + 8 * (k - R), 0);
+      issue(k, k - R);
+    }
+  }
+
+  // ---- march
+  unsigned kc = 3;                                           // ring position of the current plane
+  // slot of ring position kc + j (j = -1..3) and the phase parity of positions kc-1 / kc+3, maintained incrementally
+  unsigned s_prev = 2 % R, s_cur = 3 % R, s_p1 = 4 % R, s_p2 = 5 % R, s_new = 6 % R;
+  unsigned p_prev = 0, p_cur = 0, p_new = (6 / R) & 1;
+  int z = z0;
+  double2 raw_next = Sys::template fetch<DZ>(z0, g, ks);
+
+  // one plane.  FAST: interior plane of an interior tile -- the plane to prefetch (z+R-1) exists and will be
+  // "current" in this chunk, plane z+3 exists, no stencil leaves the grid in X/Y: no ghost code in the loop body.
+  auto plane = [&]<bool FAST>() {
+    if constexpr (FAST) {
+      if (tid == 0) {                                        // producer duty: recycle the slot of plane z-1
+        mbar_wait(empty_s + 8 * s_prev, p_prev);
+        const uint32_t fb = full_s + 8 * s_prev;
+        mbar_expect_tx(fb, (SLOT + YSLOT) * 8);
+        tma_load_3d(ring_s + s_prev * (SLOT * 8), &tmap, fb, x0 - 4, y0 - 3, zcoord_base + z + R - 1);
+        if (STAGE >= 2) tma_load_3d(yring_s + s_prev * (YSLOT * 8), &tmap_y0, fb, x0, y0, zcoord_base + z + R - 1);
+      }
+    } else {
+      if (tid == 0 && kc >= 4 && kc - 1 + R <= klast) {
+        mbar_wait(empty_s + 8 * s_prev, p_prev);
+        issue(kc - 1 + R, s_prev);
+      }
+    }
+    Sys::template apply<DZ>(ptA, raw_next, ks);              // the marching dim is shared by my two nodes
+    Sys::template apply<DZ>(ptB, raw_next, ks);
+    raw_next = Sys::template fetch<DZ>(min(z + 1, NZ - 1), g, ks);
+
+    // early global loads: aux / obstacle pairs, slow-dim neighbours
+    double2 y0v = make_double2(0.0, 0.0), auxv = y0v, obsv = y0v;
+    if (STAGE == 3 && ok0) {
+      if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
+      if (st.use_obs) obsv = ldg2(st.obs + off);
+    }
+    double2 sn[NSLOW > 0 ? NSLOW : 1][6];
+    if (ok0) {
+#pragma unroll
+      for (int d = 0; d < NSLOW; ++d) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          sn[d][k] = slow_neighbor(st.in + off, idx[d], k < 3 ? k - 3 : k - 2, g.N[d], g.stride[d], g.bc[d], g.slope_mult[d]);
+      }
+    }
+
+    const double* cur = ring + (size_t)s_cur * SLOT;
+    // X window: columns ix-4 .. ix+5 of my row (w2 = my pair); Y neighbours of the pair
+    const double2* rowp = reinterpret_cast<const double2*>(cur + myoff);
+    double2 w0 = rowp[-2], w1 = rowp[-1], w2 = rowp[0], w3 = rowp[1], w4 = rowp[2];
+    double2 ym3 = lds2(cur + myoff - 3 * BW), ym2 = lds2(cur + myoff - 2 * BW), ym1 = lds2(cur + myoff - 1 * BW);
+    double2 yp1 = lds2(cur + myoff + 1 * BW), yp2 = lds2(cur + myoff + 2 * BW), yp3 = lds2(cur + myoff + 3 * BW);
+    if (STAGE >= 2) y0v = lds2(yring + (size_t)s_cur * YSLOT + ty * TX + 2 * tp);
+    // Z neighbours above: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
+    double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
+    mbar_wait(full_s + 8 * s_new, p_new);
+    zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
+    const double2 ctr = w2;
+    if constexpr (!FAST) {
+      if (bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {         // ghost planes above the grid: edge plane NZ-1 = z+ke
+        const int ke = NZ - 1 - z;                           // 0..2
+        const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
+        const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
+        const double m = g.slope_mult[DZ];
+        if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
+        if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
+        zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
+      }
+      // ghost cells of the current plane in X / Y (tiles touching the domain boundary only), in registers
+      if (need_patch_x && ok0)
+        patch_x(w0, w1, w2, w3, w4, ix, x0, NX, bcx, g.slope_mult[DX], cur + (ty + 3) * BW, st.in + off - ix);
+      if (need_patch_y && ok0)
+        patch_y(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
+                st.in + off - (long long)iy * g.stride[DY], g.stride[DY]);
+    }
+    // this warp is done with the current plane's slot
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
+
+    double pcA[D], hdA[D], pcB[D], hdB[D];
+    double L, Rr;
+    constexpr bool red = RED;
+#define HJ_RED(d, ok)                                              \
+  if (red && (ok)) {                                               \
+    acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));                  \
+    acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));                  \
+  }
+    // X: node A uses columns ix-3..ix+3 = (w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y); node B is shifted by one
+    pc_hd<WENO>(w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, g, DX, inv_eps[DX], pcA[DX], hdA[DX], L, Rr, red);
+    HJ_RED(DX, ok0)
+    pc_hd<WENO>(w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, w4.x, g, DX, inv_eps[DX], pcB[DX], hdB[DX], L, Rr, red);
+    HJ_RED(DX, ok1)
+    // Y
+    pc_hd<WENO>(ym3.x, ym2.x, ym1.x, ctr.x, yp1.x, yp2.x, yp3.x, g, DY, inv_eps[DY], pcA[DY], hdA[DY], L, Rr, red);
+    HJ_RED(DY, ok0)
+    pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, g, DY, inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
+    HJ_RED(DY, ok1)
+    // Z
+    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
+    HJ_RED(DZ, ok0)
+    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
+    HJ_RED(DZ, ok1)
+    // slow dims
+#pragma unroll
+    for (int d = 0; d < NSLOW; ++d) {
+      pc_hd<WENO>(sn[d][0].x, sn[d][1].x, sn[d][2].x, ctr.x, sn[d][3].x, sn[d][4].x, sn[d][5].x, g, d, inv_eps[d], pcA[d], hdA[d], L, Rr, red);
+      HJ_RED(d, ok0)
+      pc_hd<WENO>(sn[d][0].y, sn[d][1].y, sn[d][2].y, ctr.y, sn[d][3].y, sn[d][4].y, sn[d][5].y, g, d, inv_eps[d], pcB[d], hdB[d], L, Rr, red);
+      HJ_RED(d, ok1)
+    }
+#undef HJ_RED
+
+    // Hamiltonian + GLF dissipation (artificial_diss_glf.py:100: diss += 0.5*(R-L)*alpha)
+    const double hamA = Sys::ham(ptA, pcA, ks), hamB = Sys::ham(ptB, pcB, ks);
+    double ydA = -hamA, ydB = -hamB;                         // ydot = -(ham - diss)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double aA = Sys::alpha(d, ptA, ks), aB = Sys::alpha(d, ptB, ks);
+      ydA = fma(hdA[d], aA, ydA);
+      ydB = fma(hdB[d], aB, ydB);
+      if (red) {
+        if (ok0) acc.amax[d] = fmax(acc.amax[d], aA);
+        if (ok1) acc.amax[d] = fmax(acc.amax[d], aB);
+      }
+    }
+
+    // RK stage algebra + driver epilogue (see stage_update in hj_common.cuh), on the pair
+    double oA, oB;
+    if (STAGE == 0) { oA = ydA; oB = ydB; }
+    else if (STAGE == 1) { oA = ctr.x + st.dt * ydA; oB = ctr.y + st.dt * ydB; }
+    else if (STAGE == 2) {
+      oA = 0.25 * (3.0 * y0v.x + (ctr.x + st.dt * ydA));
+      oB = 0.25 * (3.0 * y0v.y + (ctr.y + st.dt * ydB));
+    } else {
+      oA = (1.0 / 3.0) * (y0v.x + 2.0 * (ctr.x + st.dt * ydA));
+      oB = (1.0 / 3.0) * (y0v.y + 2.0 * (ctr.y + st.dt * ydB));
+      switch (st.comp) {
+        case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
+        case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;
+        case HJ_COMP_MIN_WITH_AUX: oA = fmin(oA, auxv.x); oB = fmin(oB, auxv.y); break;
+        case HJ_COMP_MAX_WITH_AUX: oA = fmax(oA, auxv.x); oB = fmax(oB, auxv.y); break;
+        default: break;
+      }
+      if (st.use_obs) { oA = fmax(oA, -obsv.x); oB = fmax(oB, -obsv.y); }
+    }
+    if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
+    else if (ok0) st.out[off] = oA;
+    if (red && ((ok0 && oA != oA) || (ok1 && oB != oB))) acc.nan = 1;
+
+    q[0] = q[1]; q[1] = q[2]; q[2] = ctr;
+    ++z; ++kc; off += zstride;
+    s_prev = s_cur; p_prev = p_cur;
+    s_cur = s_p1; if (s_cur == 0) p_cur ^= 1;
+    s_p1 = s_p2; s_p2 = s_new;
+    if (++s_new == (unsigned)R) { s_new = 0; p_new ^= 1; }
+  };
+
+  // head (general body) -> fast segment z in [z0+1, z1-R] (the prefetched plane z+R-1 <= z1-1 <= NZ-1) -> tail
+  const int zf_end = (need_patch_x || need_patch_y) ? z0 : z1 - R + 1;
+  plane.template operator()<false>();
+  while (z < zf_end) {
+#pragma unroll
+    for (int u = 0; u < Cfg::UNROLL; ++u) {
+      plane.template operator()<true>();
+      if (z >= zf_end) break;
+    }
+  }
+  while (z < z1) plane.template operator()<false>();
+  if (RED) acc.flush(st.red);
+}
+
+}  // namespace hjtma

@@ -1,0 +1,13 @@
+// hj_tma_plan.h -- host-side plan of the TMA backend: one tensor map per RK buffer + tile geometry.
+#pragma once
+#include <cuda.h>
+
+#include "hj_tma_kernel.cuh"
+
+struct HjTmaPlan {
+  CUtensorMap tmap[3];     // haloed (TY+6) x (TX+8) boxes on the three RK buffers
+  CUtensorMap tmap_y0;     // un-haloed TY x TX box on buffer 0 (y at the start of the step)
+  TmaGeom geo;
+  int tx, ty;
+  long long nblocks;
+};

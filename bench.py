@@ -44,10 +44,55 @@ def air3d_setup(lsp, N0, N1, N2):
     return g, data0
 
 
-def scheme_for(lsp, g, weno):
-    s = lsp.DubinsVehicleRel(g, 5, 1)
+def scheme_for(lsp, g, weno, system=None):
+    s = system if system is not None else lsp.DubinsVehicleRel(g, 5, 1)
     return lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation, wenoMode=weno,
                            dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+
+
+def product_setup(lsp, kind, n, planes0=None):
+    """the 4-D double-integrator pair (161^4) and the 6-D relative-Dubins pair (41^6).
+    Returns (grid, system, fill) where fill(view, lo, hi) writes the initial data of dim-0 planes lo..hi into a torch
+    view shaped [hi-lo, N1, ..., N_{D-2}, pitch] ON THE DEVICE (a 41^6 field is 38 GB: it is never staged on the host)."""
+    import torch
+    n0 = planes0 if planes0 is not None else n
+    if kind == "dint4d":
+        g = lsp.createGrid(np.array([-1.0] * 4), np.array([1.0] * 4), np.array([n0, n, n, n]), low_mem=True)
+        system = lsp.ProductSystem(g, [lsp.DoubleIntegrator(g, 1.0), lsp.DoubleIntegrator(g, 1.0)])
+
+        def fill(view, lo, hi):
+            v = [torch.as_tensor(g.vs[d].reshape(-1), device=view.device) for d in range(4)]
+            x1 = v[0][lo:hi].reshape(-1, 1, 1, 1); v1 = v[1].reshape(1, -1, 1, 1)
+            x2 = v[2].reshape(1, 1, -1, 1); v2 = v[3].reshape(1, 1, 1, -1)
+            view[..., :n] = torch.sqrt((x1 - x2) ** 2 + (v1 - v2) ** 2) - 0.2
+        return g, system, fill
+    if kind == "dubins6d":
+        lo3, hi3 = [-6.0, -10.0, 0.0], [20.0, 10.0, 2 * np.pi * (1 - 1 / n)]
+        g = lsp.createGrid(np.array(lo3 + lo3), np.array(hi3 + hi3), np.array([n0, n, n, n, n, n]), pdDims=[2, 5],
+                           low_mem=True)
+        system = lsp.ProductSystem(g, [lsp.DubinsVehicleRel(g, 5, 1), lsp.DubinsVehicleRel(g, 5, 1)])
+
+        def fill(view, lo, hi):
+            v = [torch.as_tensor(g.vs[d].reshape(-1), device=view.device) for d in range(6)]
+            a = torch.sqrt(v[0][lo:hi].reshape(-1, 1) ** 2 + v[1].reshape(1, -1) ** 2) - 5.0
+            b = torch.sqrt(v[3].reshape(-1, 1) ** 2 + v[4].reshape(1, -1) ** 2) - 5.0
+            view[..., :n] = torch.minimum(a.reshape(hi - lo, n, 1, 1, 1, 1), b.reshape(1, 1, 1, n, n, 1))
+        return g, system, fill
+    raise SystemExit("unknown workload %r" % kind)
+
+
+def fill_resident(eng, g, fill, planes_per_chunk=None):
+    """Initial data straight into RK buffer 0 (pitched layout), a few dim-0 planes at a time."""
+    N = [int(x) for x in np.asarray(g.N).reshape(-1)]
+    pitch = (N[-1] + 1) // 2 * 2
+    buf = eng.buffer_tensor(0)
+    halo = (buf.numel() - int(np.prod(N[:-1])) * pitch) // 2
+    body = buf[halo:buf.numel() - halo].view(*N[:-1], pitch)
+    per_plane = int(np.prod(N[1:-1])) * pitch * 8
+    step = planes_per_chunk or max(1, int(2e9 // per_plane))
+    for lo in range(0, N[0], step):
+        hi = min(N[0], lo + step)
+        fill(body[lo:hi], lo, hi)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -137,6 +182,12 @@ def run_reference(args):
 
 def workload_name(args):
     n = args.n
+    if args.workload == "dint4d":
+        return ("4-D double-integrator pair %s fp64 (GLF, WENO5a, odeCFL3, minVOverTime), %d GPU(s), %d dim-0 planes "
+                "per GPU" % ("x".join([str(n * args.gpus)] + [str(n)] * 3), args.gpus, n))
+    if args.workload == "dubins6d":
+        return ("6-D relative-Dubins pair %s fp64 (GLF, WENO5a, odeCFL3, minVOverTime), %d GPU(s), %d dim-0 planes "
+                "per GPU" % ("x".join([str(args.planes0 or n)] + [str(n)] * 5), args.gpus, (args.planes0 or n) // args.gpus))
     if args.gpus == 1:
         return "air3D %d^3 fp64 (Dubins relative, GLF, WENO5a, odeCFL3, minVOverTime), 1xB200" % n
     return ("air3D %dx%dx%d fp64 slab-decomposed along dim 0 over %d GPUs (%d planes/GPU, 3-plane halo exchange "
@@ -179,6 +230,16 @@ def run_ours(args):
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
         points = float(n) ** 3 * world
         barrier = lambda: dist.barrier()
+    elif args.workload != "air3d":
+        g, system, fill = product_setup(lsp, args.workload, n, args.planes0)
+        sd = scheme_for(lsp, g, args.weno, system)
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(backend)
+        fill_resident(eng, g, fill)
+        data0 = None
+        step = lambda t: rk3_step_resident(eng, ad, g, t, 1e9, 0.8, np.finfo(np.float64).max, comp)[0]
+        points = float(np.prod(np.asarray(g.N, dtype=np.float64)))
+        barrier = lambda: None
     else:
         g, data0 = air3d_setup(lsp, n, n, n)
         sd = scheme_for(lsp, g, args.weno)
@@ -223,6 +284,8 @@ def run_ours(args):
     e2e = None
     if args.e2e_steps <= 0:
         pass
+    elif world == 1 and data0 is None:
+        pass                                   # product workloads: resident-state numbers only (no host copy of a 38 GB field)
     elif world == 1:
         y_host = torch.from_numpy(data0.reshape(-1)).pin_memory()
         y_np = y_host.numpy()
@@ -270,7 +333,7 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "weno": args.weno, "backend": args.backend,
                    "factorCFL": 0.8, "compMethod": "minVOverTime",
-                   "l2": "inputs larger than L2 (3 x %.2f GB fields per GPU)" % (float(n) ** 3 * 8e-9),
+                   "l2": "inputs larger than L2 (3 x %.2f GB fields per GPU)" % (points / world * 8e-9),
                    "point_stage_updates_per_s": 3 * value},
         "clocks": clocks,
         "e2e": e2e,
@@ -294,7 +357,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="nodes per dim (per GPU along dim 0)")
+    ap.add_argument("--n", type=int, default=None, help="nodes per dim (per GPU along dim 0); default per workload")
+    ap.add_argument("--workload", default="air3d", choices=["air3d", "dint4d", "dubins6d"],
+                    help="air3d = configs[1] (the bench line); dint4d / dubins6d = configs[2] / [3] (1 GPU, resident state)")
+    ap.add_argument("--planes0", type=int, default=None, help="dubins6d: dim-0 extent (default n)")
     ap.add_argument("--weno", default="as_shipped", choices=["as_shipped", "intended"])
     ap.add_argument("--backend", default="auto", choices=["auto", "gather", "tma"])
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -303,6 +369,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from an ncu --set full capture")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = {"air3d": 512, "dint4d": 161, "dubins6d": 41}[args.workload]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

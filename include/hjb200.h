@@ -126,7 +126,9 @@ int hj_upload(hj_ctx* ctx, void* stream, int field, const double* dense, int is_
 int hj_download(hj_ctx* ctx, void* stream, int field, double* dense, int is_host); /* synchronises if is_host */
 int64_t hj_num_nodes(const hj_ctx* ctx);          /* prod N[d]                      */
 int64_t hj_field_elems(const hj_ctx* ctx);        /* pitched elements incl. halos   */
-/* Device pointer + element offset of halo plane blocks of the resident state (slab exchange).    */
+/* Device pointer of RK buffer 0..2 (pitched layout, halo planes included): slab halo exchange, and on-device
+ * initialisation of grids too large to stage on the host.  Taking buffer 0 marks the state as resident: the
+ * caller owns its contents from then on. */
 int hj_state_ptr(hj_ctx* ctx, int which_buffer, double** dev_ptr);
 int64_t hj_plane_elems(const hj_ctx* ctx);        /* pitched elements of one dim-0 plane */
 

@@ -211,6 +211,7 @@ int hj_state_ptr(hj_ctx* c, int which, double** p) {
   int r = ensure_buffers(c);
   if (r) return r;
   *p = c->buf[which];
+  if (which == 0) c->have_state = true;   // the caller now owns the contents of the resident state
   return HJ_OK;
 }
 

@@ -347,14 +347,15 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
       if (st.use_obs) obsv = ldg2(st.obs + off);
     }
-    double2 sn[NSLOW > 0 ? NSLOW : 1][6];
-    if (ok0) {
+    // slow dims with few neighbours in flight: the pair loads of ONE slow dim are issued early (they overlap the
+    // shared-memory phase); the remaining slow dims are loaded one dim at a time (6 x 16 B in flight per thread)
+    // so that a 6-D system does not need 72 registers of neighbour data
+    double2 sn0[6];
+    if (NSLOW > 0 && ok0) {
 #pragma unroll
-      for (int d = 0; d < NSLOW; ++d) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          sn[d][k] = slow_neighbor(st.in + off, idx[d], k < 3 ? k - 3 : k - 2, g.N[d], g.stride[d], g.bc[d], g.slope_mult[d]);
-      }
+      for (int k = 0; k < 6; ++k)
+        sn0[k] = slow_neighbor(st.in + off, idx[NSLOW - 1], k < 3 ? k - 3 : k - 2, g.N[NSLOW - 1], g.stride[NSLOW - 1],
+                               g.bc[NSLOW - 1], g.slope_mult[NSLOW - 1]);
     }
 
     const double* cur = ring + (size_t)s_cur * SLOT;
@@ -415,10 +416,19 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     HJ_RED(DZ, ok1)
     // slow dims
 #pragma unroll
-    for (int d = 0; d < NSLOW; ++d) {
-      pc_hd<WENO>(sn[d][0].x, sn[d][1].x, sn[d][2].x, ctr.x, sn[d][3].x, sn[d][4].x, sn[d][5].x, g, d, inv_eps[d], pcA[d], hdA[d], L, Rr, red);
+    for (int d = NSLOW - 1; d >= 0; --d) {
+      double2 sn[6];
+      if (d == NSLOW - 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sn[k] = sn0[k];
+      } else if (ok0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          sn[k] = slow_neighbor(st.in + off, idx[d], k < 3 ? k - 3 : k - 2, g.N[d], g.stride[d], g.bc[d], g.slope_mult[d]);
+      }
+      pc_hd<WENO>(sn[0].x, sn[1].x, sn[2].x, ctr.x, sn[3].x, sn[4].x, sn[5].x, g, d, inv_eps[d], pcA[d], hdA[d], L, Rr, red);
       HJ_RED(d, ok0)
-      pc_hd<WENO>(sn[d][0].y, sn[d][1].y, sn[d][2].y, ctr.y, sn[d][3].y, sn[d][4].y, sn[d][5].y, g, d, inv_eps[d], pcB[d], hdB[d], L, Rr, red);
+      pc_hd<WENO>(sn[0].y, sn[1].y, sn[2].y, ctr.y, sn[3].y, sn[4].y, sn[5].y, g, d, inv_eps[d], pcB[d], hdB[d], L, Rr, red);
       HJ_RED(d, ok1)
     }
 #undef HJ_RED

@@ -479,6 +479,9 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
   st.dt = dt;
   st.in = c->buf[in_[stage]] + c->origin;
   st.y0 = c->buf[0] + c->origin;
+  // dimension-split path: pass 1 parks in + dt F_B(in) in the stage's output buffer (stage 3: buffer 1, which is
+  // free by then -- buffer 0 still holds y0)
+  st.tmp = (stage == 3 ? c->buf[1] : c->buf[out_[stage]]) + c->origin;
   st.aux = c->aux ? c->aux + c->origin : nullptr;
   st.obs = c->obs ? c->obs + c->origin : nullptr;
   st.out = c->buf[out_[stage]] + c->origin;

@@ -42,6 +42,7 @@ struct KStage {
   double dt;
   const double* in;   // field the stencil reads
   const double* y0;   // y at the start of the step (stages 2,3), pointwise
+  const double* tmp;  // dimension-split path, pass 2: in + dt * F_B(in) written by pass 1 (pointwise)
   const double* aux;  // target / V0 (stage 3, comp 3/4)
   const double* obs;  // obstacle (stage 3)
   double* out;

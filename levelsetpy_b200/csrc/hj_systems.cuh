@@ -23,7 +23,7 @@
 
 template <int BASE, int PB, int TB>
 struct DubinsRelF {
-  static constexpr int ND = 3;
+  static constexpr int ND = 3, BASE_DIM = BASE;
   // x1, x2 and the two x3-only coefficients of dubins_relative.py:81-82, evaluated un-fused like numpy does
   struct Pt { double x1, x2, p1c, p2c; };
   HJ_DEV static void set3(Pt& q, int i3, const KSys& k) {
@@ -70,7 +70,7 @@ struct DubinsRelF {
 
 template <int BASE, int PB>
 struct DoubleIntF {
-  static constexpr int ND = 2;
+  static constexpr int ND = 2, BASE_DIM = BASE;
   struct Pt { double x2; };
   HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
     Pt q;
@@ -95,7 +95,7 @@ struct DoubleIntF {
 };
 
 struct FlockF {
-  static constexpr int ND = 3;
+  static constexpr int ND = 3, BASE_DIM = 0;
   struct Pt { int dummy; };
   HJ_DEV static Pt load(const int*, const KGrid&, const KSys&) { return Pt{0}; }
   template <int GD>
@@ -122,7 +122,9 @@ struct FlockF {
 
 template <class A, class B>
 struct PairF {
-  static constexpr int ND = A::ND + B::ND;
+  static constexpr int ND = A::ND + B::ND, BASE_DIM = 0;
+  using First = A;     // dim block [0, A::ND)
+  using Second = B;    // dim block [A::ND, ND): the trailing (contiguous) dims
   struct Pt { typename A::Pt a; typename B::Pt b; };
   HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
     Pt q;
@@ -148,6 +150,12 @@ struct PairF {
     return dl < A::ND ? A::alpha(dl, q.a, k) : B::alpha(dl - A::ND, q.b, k);
   }
 };
+
+// dimension-split trait: a product system is advanced as two passes, one per dim block (hj_vec_kernel.cuh)
+template <class S>
+struct SysSplit { static constexpr bool value = false; };
+template <class A, class B>
+struct SysSplit<PairF<A, B>> { static constexpr bool value = true; };
 
 using SysDubinsRel = DubinsRelF<0, 0, 0>;
 using SysDoubleInt = DoubleIntF<0, 0>;

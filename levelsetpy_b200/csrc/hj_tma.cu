@@ -8,11 +8,19 @@
 #include "hj_internal.h"
 #include "hj_tma_kernel.cuh"
 #include "hj_tma_plan.h"
+#include "hj_vec_kernel.cuh"
 
 using namespace hjtma;
 
-// production configuration of the ring kernel (see tools/tune_tma.cu for the measured alternatives)
+// production configurations (see tools/tune_tma.cu for the measured alternatives).
+//   whole 3-D systems: 32 x 16 tile, 8-slot ring, 2 CTAs/SM.
+//   product systems (dimension-split, hj_vec_kernel.cuh): pass 1 takes a tile shaped for the trailing block's
+//   plane (42 x 12 for the 41 x 41 planes of the 6-D pair, 54 x 9 for the 161 x 161 planes of the 4-D pair),
+//   pass 2 a {vector pairs, T1, T2} tile of the leading block.
 using ProdCfg = TmaCfg<8, 2, 1>;
+template <class Sys> struct SplitCfg;
+template <> struct SplitCfg<SysDubinsRelPair> { using P1 = TmaCfg<8, 2, 1, 12, 21>; using P2 = VecCfg<3, 8, 2, 4, 7, 7>; };
+template <> struct SplitCfg<SysDoubleIntPair> { using P1 = TmaCfg<8, 2, 1, 9, 27>;  using P2 = VecCfg<2, 8, 2, 16, 16, 1>; };
 
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -31,10 +39,10 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-template <class Sys, int WENO, bool RED, int STAGE, class Cfg>
+template <class Sys, int GD, int WENO, bool RED, int STAGE, class Cfg>
 static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const KGrid& g, const KSys& ks,
                               const KStage& st, cudaStream_t s) {
-  auto kern = k_stage_tma<Sys, WENO, RED, STAGE, Cfg>;
+  auto kern = k_stage_tma<Sys, GD, WENO, RED, STAGE, Cfg>;
   constexpr size_t smem = Cfg::template smem_bytes<STAGE>();
   static bool attr_set = false;
   if (!attr_set) {
@@ -46,28 +54,71 @@ static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const K
   return cudaGetLastError();
 }
 
+template <class Blk, int GD, int WENO, bool RED, int STAGE, class Cfg>
+static cudaError_t launch_vec(const HjTmaPlan* p, const CUtensorMap& tm, const KGrid& g, const KSys& ks,
+                              const KStage& st, cudaStream_t s) {
+  auto kern = k_stage_vec<Blk, GD, WENO, RED, STAGE, Cfg>;
+  constexpr size_t smem = Cfg::smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<(unsigned)p->vblocks, Cfg::NTHREADS, smem, s>>>(tm, g, ks, st, p->vgeo);
+  return cudaGetLastError();
+}
+
 struct TmaLauncher {
   const HjTmaPlan* p;
-  const CUtensorMap& tm;
+  int in_buf;
   int weno;
   const KGrid& g;
   const KSys& ks;
   const KStage& st;
   cudaStream_t s;
   cudaError_t err = cudaSuccess;
+  int launches = 0;
+  // whole system: one fused kernel per stage
   template <class Sys, int WENO, bool RED>
   cudaError_t by_stage() {
+    const CUtensorMap& tm = p->tmap[in_buf];
+    launches = 1;
     switch (st.stage) {
-      case 1: return launch_one<Sys, WENO, RED, 1, ProdCfg>(p, tm, g, ks, st, s);
-      case 2: return launch_one<Sys, WENO, RED, 2, ProdCfg>(p, tm, g, ks, st, s);
-      case 3: return launch_one<Sys, WENO, RED, 3, ProdCfg>(p, tm, g, ks, st, s);
+      case 1: return launch_one<Sys, Sys::ND, WENO, RED, 1, ProdCfg>(p, tm, g, ks, st, s);
+      case 2: return launch_one<Sys, Sys::ND, WENO, RED, 2, ProdCfg>(p, tm, g, ks, st, s);
+      case 3: return launch_one<Sys, Sys::ND, WENO, RED, 3, ProdCfg>(p, tm, g, ks, st, s);
+      default: return cudaErrorNotSupported;
+    }
+  }
+  // product system: pass 1 (trailing block, tmp = in + dt F_B(in)) then pass 2 (leading block + stage algebra)
+  template <class Sys, int WENO, bool RED>
+  cudaError_t split_by_stage() {
+    using P1 = typename SplitCfg<Sys>::P1;
+    using P2 = typename SplitCfg<Sys>::P2;
+    KStage s1 = st;
+    s1.stage = 1;
+    s1.comp = HJ_COMP_NONE;
+    s1.use_obs = 0;
+    s1.out = const_cast<double*>(st.tmp);
+    cudaError_t e = launch_one<typename Sys::Second, Sys::ND, WENO, RED, 1, P1>(p, p->tmap[in_buf], g, ks, s1, s);
+    if (e != cudaSuccess) return e;
+    launches = 2;
+    const CUtensorMap& vm = p->vmap[in_buf];
+    switch (st.stage) {
+      case 1: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 1, P2>(p, vm, g, ks, st, s);
+      case 2: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 2, P2>(p, vm, g, ks, st, s);
+      case 3: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 3, P2>(p, vm, g, ks, st, s);
       default: return cudaErrorNotSupported;
     }
   }
   template <class Sys>
   void operator()() {
-    if constexpr (Sys::ND >= 3) {
-      const bool red = st.want_reduce != 0;
+    const bool red = st.want_reduce != 0;
+    if constexpr (SysSplit<Sys>::value) {
+      if (weno == HJ_WENO_AS_SHIPPED) err = red ? split_by_stage<Sys, HJ_WENO_AS_SHIPPED, true>() : split_by_stage<Sys, HJ_WENO_AS_SHIPPED, false>();
+      else err = red ? split_by_stage<Sys, HJ_WENO_INTENDED, true>() : split_by_stage<Sys, HJ_WENO_INTENDED, false>();
+    } else if constexpr (Sys::ND >= 3) {
       if (weno == HJ_WENO_AS_SHIPPED) err = red ? by_stage<Sys, HJ_WENO_AS_SHIPPED, true>() : by_stage<Sys, HJ_WENO_AS_SHIPPED, false>();
       else err = red ? by_stage<Sys, HJ_WENO_INTENDED, true>() : by_stage<Sys, HJ_WENO_INTENDED, false>();
     } else {
@@ -76,11 +127,31 @@ struct TmaLauncher {
   }
 };
 
+// tile shapes of a system's kernels, for the plan
+struct PlanShape {
+  int txp = ProdCfg::TXP, ty = ProdCfg::TY;
+  bool split = false;
+  int ns = 0, vb = 0, t1 = 0, t2 = 0;
+  template <class Sys>
+  void operator()() {
+    if constexpr (SysSplit<Sys>::value) {
+      using P1 = typename SplitCfg<Sys>::P1;
+      using P2 = typename SplitCfg<Sys>::P2;
+      txp = P1::TXP; ty = P1::TY;
+      split = true;
+      ns = P2::NS; vb = P2::VB; t1 = P2::T1; t2 = P2::T2;
+    }
+  }
+};
+
 HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* const bufs[3], int halo0, char* err,
                               int errlen, int tile_y) {
   (void)weno;
   const int D = g.D;
-  const int TY = tile_y > 0 ? tile_y : ProdCfg::TY;
+  PlanShape shape;
+  if (!hj_dispatch_system(system_id, shape)) { snprintf(err, errlen, "unknown system"); return nullptr; }
+  const int TY = tile_y > 0 ? tile_y : shape.ty;
+  const int TX = 2 * shape.txp;
   if (D < 3) { snprintf(err, errlen, "2-D grids use the gather backend"); return nullptr; }
   if (hj_system_ndim(system_id) != D) { snprintf(err, errlen, "system/grid dim mismatch"); return nullptr; }
   PFN_encodeTiled enc = get_encode();
@@ -131,6 +202,54 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
       return nullptr;
     }
   }
+  p->split = shape.split;
+  if (shape.split) {
+    // pass 2: [V, (N2,) N1, N0 (+ halo planes)] with V = the flattened trailing dims; box {VB, (T2+6,) T1+6, 1}
+    const int NS = shape.ns;
+    const long long V = g.stride[NS - 1];
+    const long long planes0 = g.N[0] + (halo0 ? 2 * HJ_GHOST : 0);
+    VecGeom& vg = p->vgeo;
+    vg.nvc = (int)((V + shape.vb - 1) / shape.vb);
+    vg.nt1 = (g.N[1] + shape.t1 - 1) / shape.t1;
+    vg.nt2 = NS == 3 ? (g.N[2] + shape.t2 - 1) / shape.t2 : 1;
+    vg.cz = g.N[0];
+    vg.nzc = 1;
+    vg.zcoord0 = halo0 ? HJ_GHOST : 0;
+    vg.pitch = (int)pitch;
+    vg.NX = NX;
+    p->vblocks = (long long)vg.nvc * vg.nt1 * vg.nt2 * vg.nzc;
+    if (g.N[0] < 4 || V > 0x7fffffffLL || p->vblocks > 0x7fffffffLL) {
+      delete p;
+      snprintf(err, errlen, "grid shape not supported by the dimension-split path");
+      return nullptr;
+    }
+    for (int bidx = 0; bidx < 3; ++bidx) {
+      cuuint64_t dims[4];
+      cuuint64_t strides[3];
+      cuuint32_t box[4];
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      int rank;
+      if (NS == 3) {
+        rank = 4;
+        dims[0] = (cuuint64_t)V; dims[1] = (cuuint64_t)g.N[2]; dims[2] = (cuuint64_t)g.N[1]; dims[3] = (cuuint64_t)planes0;
+        strides[0] = (cuuint64_t)g.stride[2] * 8; strides[1] = (cuuint64_t)g.stride[1] * 8; strides[2] = (cuuint64_t)g.stride[0] * 8;
+        box[0] = shape.vb; box[1] = shape.t2 + 6; box[2] = shape.t1 + 6; box[3] = 1;
+      } else {
+        rank = 3;
+        dims[0] = (cuuint64_t)V; dims[1] = (cuuint64_t)g.N[1]; dims[2] = (cuuint64_t)planes0;
+        strides[0] = (cuuint64_t)g.stride[1] * 8; strides[1] = (cuuint64_t)g.stride[0] * 8;
+        box[0] = shape.vb; box[1] = shape.t1 + 6; box[2] = 1;
+      }
+      CUresult r = enc(&p->vmap[bidx], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, (void*)bufs[bidx], dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled (pass 2) failed (%d)", (int)r);
+        delete p;
+        return nullptr;
+      }
+    }
+  }
   return p;
 }
 
@@ -138,8 +257,8 @@ void hj_tma_plan_destroy(HjTmaPlan* p) { delete p; }
 
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
                                 const KStage& st, int in_buf, cudaStream_t s) {
-  TmaLauncher l{plan, plan->tmap[in_buf], weno, g, ks, st, s};
+  TmaLauncher l{plan, in_buf, weno, g, ks, st, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
-  if (l.err == cudaSuccess) hj_count_launch(1);
+  hj_count_launch(l.launches);
   return l.err;
 }

@@ -34,15 +34,19 @@ struct TmaGeom {
 };
 
 // tuning knobs of the plane-ring kernel
-template <int R_, int MINB_, int UNROLL_, int TY_ = 16>
+template <int R_, int MINB_, int UNROLL_, int TY_ = 16, int TXP_ = 16>
 struct TmaCfg {
   static constexpr int R = R_;            // ring slots (planes z+1..z+3 are needed, the rest is prefetch distance)
   static constexpr int MINB = MINB_;      // resident CTAs per SM the register allocation is sized for
   static constexpr int UNROLL = UNROLL_;  // planes per trip of the fast march loop
-  static constexpr int TX = 32, TY = TY_; // tile (X, Y); one node pair per thread
-  static constexpr int NTHREADS = (TX / 2) * TY;
-  static constexpr int BW = TX + 8, BH = TY + 6, SLOT = BW * BH;   // haloed plane box (doubles)
-  static constexpr int YSLOT_FULL = TX * TY;
+  static constexpr int TXP = TXP_;        // node pairs per tile row: one node pair per thread
+  static constexpr int TX = 2 * TXP_, TY = TY_;   // tile (X, Y)
+  static constexpr int NACTIVE = TXP * TY;
+  static constexpr int NTHREADS = (NACTIVE + 31) / 32 * 32;        // whole warps; the surplus threads idle
+  static constexpr int BW = TX + 8, BH = TY + 6;                   // haloed plane box (doubles)
+  static constexpr int BOX = BW * BH, YBOX = TX * TY;              // doubles the TMA unit writes per plane
+  static constexpr int SLOT = (BOX + 15) / 16 * 16;                // slot strides keep 128-byte alignment
+  static constexpr int YSLOT_FULL = (YBOX + 15) / 16 * 16;
   template <int STAGE>
   static constexpr size_t smem_bytes() {
     return (size_t)R * (SLOT + (STAGE >= 2 ? YSLOT_FULL : 0)) * 8 + 2 * R * 8;
@@ -50,9 +54,6 @@ struct TmaCfg {
 };
 
 namespace hjtma {
-
-constexpr int TX = 32;
-constexpr int BW = TX + 8;                       // slot row length (doubles)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 HJ_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,6 +148,7 @@ HJ_DEV void patch_x(double2& w0, double2& w1, double2& w2, double2& w3, double2&
 
 // Y neighbours of a thread's pair: rows iy-3 .. iy+3.  `scol` = row y0-3 of the current slot at my column pair,
 // `gcol` = row 0 at my column pair in global memory, `ys` = global row stride.
+template <int BW>
 HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, double2& yp2, double2& yp3, const int iy,
                     const int y0, const int NY, const int bc, const double m, const double* scol, const double* gcol,
                     const long long ys) {
@@ -182,23 +184,31 @@ HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, doub
 // All 8 warps are consumers (one node pair per thread); lane 0 of warp 0 doubles as the producer: at the top of
 // step z it waits until every warp has released plane z-1 (normally already true: the ring runs R-4 planes
 // ahead of need) and re-arms that slot with plane z+R-1.
-template <class Sys, int WENO, bool RED, int STAGE, class Cfg>
+//
+// `Sys` is the functor of the dim block [BASE_DIM, BASE_DIM + ND) of a GD-dimensional grid and the kernel
+// differentiates along those dims only.  A whole system has BASE = 0, ND = GD.  The trailing block of a product
+// system (BASE + ND == GD, dimension-split path, see hj_vec_kernel.cuh) makes this kernel the first of two passes:
+// out = in + dt * F_B(in) with STAGE = 1.
+template <class Sys, int GD, int WENO, bool RED, int STAGE, class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB)
 k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y0, const KGrid g,
             const KSys ks, const KStage st, const TmaGeom geo) {
-  constexpr int D = Sys::ND;
+  constexpr int D = GD;
+  constexpr int B0 = Sys::BASE_DIM;                              // first differentiated dim
+  static_assert(B0 + Sys::ND == GD, "the plane-ring kernel takes the trailing dim block");
   static_assert(D >= 3, "the plane-ring kernel needs a Z dim");
   constexpr int DX = D - 1, DY = D - 2, DZ = D - 3, NSLOW = D - 3;
-  constexpr int PAIRS = TX / 2;
+  static_assert(DY >= B0, "X and Y must belong to the block");
+  constexpr bool ZIN = DZ >= B0;                             // is the marching dim differentiated?
+  constexpr int TX = Cfg::TX, BW = Cfg::BW, PAIRS = Cfg::TXP;
   constexpr int R = Cfg::R;
   constexpr int TY = Cfg::TY, NTHREADS = Cfg::NTHREADS, NCONS_WARPS = NTHREADS / 32;
   constexpr int SLOT = Cfg::SLOT, YSLOT_FULL = Cfg::YSLOT_FULL;
-  static_assert(Cfg::BW == BW && NTHREADS % 32 == 0, "tile shape");
-  static_assert(PAIRS * TY == NTHREADS, "tile must give every thread one node pair");
-  static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
+  static_assert((SLOT * 8) % 128 == 0 && (YSLOT_FULL * 8) % 128 == 0, "slots must keep 128-byte alignment");
   static_assert(R >= 6 && R <= 16, "ring depth");
   // stages 2/3 also stream the un-haloed y0 tile (TY x TX) of each plane through the ring, on the same barrier
   constexpr int YSLOT = (STAGE >= 2) ? YSLOT_FULL : 0;
+  constexpr int YBOX = (STAGE >= 2) ? Cfg::YBOX : 0;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
@@ -241,7 +251,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     const bool ytile = STAGE >= 2 && k >= 3 && k + 3 <= klast;
     const uint32_t fb = full_s + 8 * s;
     if (load) {
-      mbar_expect_tx(fb, (SLOT + (ytile ? YSLOT : 0)) * 8);
+      mbar_expect_tx(fb, (Cfg::BOX + (ytile ? YBOX : 0)) * 8);
       tma_load_3d(ring_s + s * (SLOT * 8), &tmap, fb, x0 - 4, y0 - 3, zcoord_base + zsrc);
       if (ytile) tma_load_3d(yring_s + s * (YSLOT * 8), &tmap_y0, fb, x0, y0, zcoord_base + zp);
     } else {
@@ -254,7 +264,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 
   // ================================================================== consumers
   const int lane = tid & 31;
-  const int tp = tid % PAIRS, ty = tid / PAIRS;
+  const bool live = tid < Cfg::NACTIVE;                     // surplus threads of the last warp only keep the barriers
+  const int tp = tid % PAIRS, ty = live ? tid / PAIRS : TY - 1;
   int idx[D];
   {
     long long r = slow_flat;
@@ -262,7 +273,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     for (int d = NSLOW - 1; d >= 0; --d) { idx[d] = (int)(r % g.N[d]); r /= g.N[d]; }
   }
   const int ix = x0 + 2 * tp, iy = y0 + ty;
-  const bool ok0 = ix < NX && iy < NY, ok1 = ix + 1 < NX && iy < NY;
+  const bool ok0 = live && ix < NX && iy < NY, ok1 = live && ix + 1 < NX && iy < NY;
   long long off = (long long)iy * g.stride[DY] + ix + (long long)z0 * g.stride[DZ];   // stride[DX] == 1
 #pragma unroll
   for (int d = 0; d < NSLOW; ++d) off += (long long)idx[d] * g.stride[d];
@@ -327,7 +338,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       if (tid == 0) {                                        // producer duty: recycle the slot of plane z-1
         mbar_wait(empty_s + 8 * s_prev, p_prev);
         const uint32_t fb = full_s + 8 * s_prev;
-        mbar_expect_tx(fb, (SLOT + YSLOT) * 8);
+        mbar_expect_tx(fb, (Cfg::BOX + YBOX) * 8);
         tma_load_3d(ring_s + s_prev * (SLOT * 8), &tmap, fb, x0 - 4, y0 - 3, zcoord_base + z + R - 1);
         if (STAGE >= 2) tma_load_3d(yring_s + s_prev * (YSLOT * 8), &tmap_y0, fb, x0, y0, zcoord_base + z + R - 1);
       }
@@ -351,7 +362,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     // shared-memory phase); the remaining slow dims are loaded one dim at a time (6 x 16 B in flight per thread)
     // so that a 6-D system does not need 72 registers of neighbour data
     double2 sn0[6];
-    if (NSLOW > 0 && ok0) {
+    if (NSLOW > B0 && ok0) {
 #pragma unroll
       for (int k = 0; k < 6; ++k)
         sn0[k] = slow_neighbor(st.in + off, idx[NSLOW - 1], k < 3 ? k - 3 : k - 2, g.N[NSLOW - 1], g.stride[NSLOW - 1],
@@ -366,12 +377,13 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     double2 yp1 = lds2(cur + myoff + 1 * BW), yp2 = lds2(cur + myoff + 2 * BW), yp3 = lds2(cur + myoff + 3 * BW);
     if (STAGE >= 2) y0v = lds2(yring + (size_t)s_cur * YSLOT + ty * TX + 2 * tp);
     // Z neighbours above: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
-    double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
+    double2 zp1 = make_double2(0.0, 0.0), zp2 = zp1, zp3 = zp1;
+    if (ZIN) { zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff); zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff); }
     mbar_wait(full_s + 8 * s_new, p_new);
-    zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
+    if (ZIN) zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
     const double2 ctr = w2;
     if constexpr (!FAST) {
-      if (bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {         // ghost planes above the grid: edge plane NZ-1 = z+ke
+      if (ZIN && bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {         // ghost planes above the grid: edge plane NZ-1 = z+ke
         const int ke = NZ - 1 - z;                           // 0..2
         const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
         const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
@@ -384,7 +396,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       if (need_patch_x && ok0)
         patch_x(w0, w1, w2, w3, w4, ix, x0, NX, bcx, g.slope_mult[DX], cur + (ty + 3) * BW, st.in + off - ix);
       if (need_patch_y && ok0)
-        patch_y(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
+        patch_y<BW>(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
                 st.in + off - (long long)iy * g.stride[DY], g.stride[DY]);
     }
     // this warp is done with the current plane's slot
@@ -410,13 +422,15 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, g, DY, inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
     HJ_RED(DY, ok1)
     // Z
-    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
-    HJ_RED(DZ, ok0)
-    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
-    HJ_RED(DZ, ok1)
-    // slow dims
+    if constexpr (ZIN) {
+      pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
+      HJ_RED(DZ, ok0)
+      pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
+      HJ_RED(DZ, ok1)
+    }
+    // slow dims (of the block)
 #pragma unroll
-    for (int d = NSLOW - 1; d >= 0; --d) {
+    for (int d = NSLOW - 1; d >= B0; --d) {
       double2 sn[6];
       if (d == NSLOW - 1) {
 #pragma unroll
@@ -437,8 +451,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     const double hamA = Sys::ham(ptA, pcA, ks), hamB = Sys::ham(ptB, pcB, ks);
     double ydA = -hamA, ydB = -hamB;                         // ydot = -(ham - diss)
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double aA = Sys::alpha(d, ptA, ks), aB = Sys::alpha(d, ptB, ks);
+    for (int d = B0; d < D; ++d) {
+      const double aA = Sys::alpha(d - B0, ptA, ks), aB = Sys::alpha(d - B0, ptB, ks);
       ydA = fma(hdA[d], aA, ydA);
       ydB = fma(hdB[d], aB, ydB);
       if (red) {

@@ -3,6 +3,7 @@
 #include <cuda.h>
 
 #include "hj_tma_kernel.cuh"
+#include "hj_vec_kernel.cuh"
 
 struct HjTmaPlan {
   CUtensorMap tmap[3];     // haloed (TY+6) x (TX+8) boxes on the three RK buffers
@@ -10,4 +11,9 @@ struct HjTmaPlan {
   TmaGeom geo;
   int tx, ty;
   long long nblocks;
+  // dimension-split path (product systems): pass 2 tensor maps + geometry
+  bool split = false;
+  CUtensorMap vmap[3];
+  VecGeom vgeo;
+  long long vblocks = 0;
 };

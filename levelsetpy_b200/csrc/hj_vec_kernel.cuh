@@ -1,0 +1,308 @@
+// hj_vec_kernel.cuh -- second pass of the dimension-split path for product systems (device side).
+//
+// A product system (the 4-D double-integrator pair, the 6-D relative-Dubins pair) has
+//     H(x, p) = H_A(x_A, p_A) + H_B(x_B, p_B),   alpha_d = alpha_d(x_block(d)),
+// so one RHS is  F(y) = F_A(y) + F_B(y)  where F_A only differentiates along the leading dim block A and F_B along
+// the trailing (contiguous) block B.  A star stencil of radius 3 in 6 dims has no tile that fits shared memory or L2
+// with useful reuse in all dims, but each block alone is a 2-D/3-D stencil.  The stage is therefore two kernels:
+//     pass 1 (k_stage_tma on block B):  tmp = in + dt * F_B(in)                                   8 B r + 8 B w
+//     pass 2 (this kernel, block A):    out = RK_s(y0, tmp + dt * F_A(in))  [+ driver epilogue]   16(24) B r + 8 B w
+// i.e. 40 / 48 / 48 B per node for the three stages instead of the 16 / 24 / 24 B of a (hypothetical) fully fused
+// 6-D tile, but every byte is streamed once, coalesced, at HBM speed.
+//
+// Layout of pass 2: the trailing dims are flattened into one contiguous "vector" axis of V = stride[NS-1] elements
+// that carries no stencil.  A CTA owns VB consecutive vector elements (VP thread pairs) times a T1 x T2 tile of block
+// dims 1, 2 and marches along block dim 0.  Each plane of the tile with its 3-cell halo in dims 1, 2 -- a box
+// {VB, T2+6, T1+6, 1} of a 4-D tensor map [V, N2, N1, N0] (3-D for a 2-dim block) -- arrives by one TMA load into an
+// R-slot ring; the marching dim uses a 3-deep register queue + the ring slots of planes z+1..z+3, exactly like the
+// plane-ring kernel.  Both nodes of a thread's pair share their block-A state (x_A does not vary along the vector
+// axis).  Ghost cells are made in registers from the TMA zero fill, as in hj_tma_kernel.cuh.
+#pragma once
+#include "hj_tma_kernel.cuh"
+
+struct VecGeom {
+  int nvc;          // chunks along the vector axis
+  int nt1, nt2;     // tiles along block dims 1, 2 (nt2 = 1 for a 2-dim block)
+  int nzc, cz;      // chunks / planes per chunk along the marching dim (block dim 0)
+  int zcoord0;      // TMA coordinate of plane 0 of the marching dim (stored halo planes shift it)
+  int pitch, NX;    // innermost padded / true extent: pad columns are excluded from stores and reductions
+};
+
+template <int NS_, int R_, int MINB_, int VP_, int T1_, int T2_>
+struct VecCfg {
+  static constexpr int NS = NS_;          // dims of the leading block (2 or 3)
+  static constexpr int R = R_, MINB = MINB_;
+  static constexpr int VP = VP_, VB = 2 * VP_;                    // thread pairs / doubles along the vector axis
+  static constexpr int T1 = T1_, T2 = NS_ == 3 ? T2_ : 1;          // tile of block dims 1, 2
+  static constexpr int H1 = T1 + 6, H2 = NS_ == 3 ? T2 + 6 : 1;    // haloed tile
+  static constexpr int S2 = VB, S1 = H2 * VB;                      // slot strides (doubles) of block dims 2, 1
+  static constexpr int NACTIVE = VP * T1 * T2;
+  static constexpr int NTHREADS = (NACTIVE + 31) / 32 * 32;
+  static constexpr int BOX = H1 * H2 * VB;
+  static constexpr int SLOT = (BOX + 15) / 16 * 16;
+  static constexpr size_t smem_bytes() { return (size_t)R * SLOT * 8 + 2 * R * 8; }
+};
+
+namespace hjtma {
+
+HJ_DEV void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <class Blk, int GD, int WENO, bool RED, int STAGE, class Cfg>
+__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB)
+k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys ks, const KStage st, const VecGeom geo) {
+  constexpr int NS = Cfg::NS;
+  static_assert(Blk::BASE_DIM == 0 && Blk::ND == NS && NS < GD, "pass 2 takes the leading dim block");
+  static_assert(STAGE >= 1 && STAGE <= 3, "RK stages only");
+  constexpr int R = Cfg::R, SLOT = Cfg::SLOT, VB = Cfg::VB, VP = Cfg::VP, T1 = Cfg::T1, T2 = Cfg::T2;
+  constexpr int S1 = Cfg::S1, S2 = Cfg::S2;
+  constexpr int NTHREADS = Cfg::NTHREADS, NWARPS = NTHREADS / 32;
+  static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  const uint32_t ring_s = smem_u32(smem_raw);
+  const uint32_t full_s = ring_s + R * SLOT * 8;
+  const uint32_t empty_s = full_s + R * 8;
+
+  const int tid = threadIdx.x;
+  long long b = blockIdx.x;
+  const int t2 = (int)(b % geo.nt2); b /= geo.nt2;
+  const int t1 = (int)(b % geo.nt1); b /= geo.nt1;
+  const int zc = (int)(b % geo.nzc); b /= geo.nzc;
+  const int v0 = (int)b * VB;
+  const int N0 = g.N[0], N1 = g.N[1], N2 = NS == 3 ? g.N[2] : 1;
+  const long long V = g.stride[NS - 1];
+  const int i10 = t1 * T1, i20 = t2 * T2, z0 = zc * geo.cz;
+  const int z1 = min(z0 + geo.cz, N0);
+  const int bc0 = g.bc[0], bc1 = g.bc[1], bc2 = NS == 3 ? g.bc[2] : HJ_BC_EXTRAPOLATE;
+  const unsigned klast = (unsigned)((z1 - 1 + 3) - (z0 - 3));
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) { mbar_init(full_s + 8 * s, 1); mbar_init(empty_s + 8 * s, NWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tma_plane = [&](unsigned s, int zsrc) {
+    const uint32_t fb = full_s + 8 * s;
+    mbar_expect_tx(fb, Cfg::BOX * 8);
+    if constexpr (NS == 3) tma_load_4d(ring_s + s * (SLOT * 8), &tmap, fb, v0, i20 - 3, i10 - 3, geo.zcoord0 + zsrc);
+    else tma_load_3d(ring_s + s * (SLOT * 8), &tmap, fb, v0, i10 - 3, geo.zcoord0 + zsrc);
+  };
+  // plane with ring position k -> slot s: TMA load, or a bare arrival for a computed ghost plane
+  auto issue = [&](unsigned k, unsigned s) {
+    const int zp = z0 - 3 + (int)k;
+    int zsrc = zp;
+    bool load = true;
+    if (zp < 0 || zp >= N0) {
+      if (bc0 == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + N0 : zp - N0;
+      else if (bc0 == HJ_BC_EXTRAPOLATE) load = false;
+    }
+    if (load) tma_plane(s, zsrc);
+    else mbar_arrive(full_s + 8 * s);
+  };
+  if (tid == 0) {
+    for (unsigned k = 0; k < (unsigned)R && k <= klast; ++k) issue(k, k);
+  }
+
+  // ================================================================== consumers
+  const int lane = tid & 31;
+  const bool live = tid < Cfg::NACTIVE;
+  const int vp = tid % VP;
+  const int pos = live ? tid / VP : 0;
+  const int a2 = pos % T2, a1 = pos / T2;
+  const long long iv = (long long)v0 + 2 * vp;
+  const int i1 = i10 + a1, i2 = i20 + a2;
+  const bool inb = live && iv < V && i1 < N1 && i2 < N2;
+  const int xcol = (int)(iv % geo.pitch);                    // innermost index of node A: pad columns are not nodes
+  const bool ok0 = inb && xcol < geo.NX, ok1 = inb && xcol + 1 < geo.NX;
+  long long off = (long long)z0 * g.stride[0] + (long long)i1 * g.stride[1] + iv;
+  if (NS == 3) off += (long long)i2 * g.stride[2];
+  const long long zstride = g.stride[0];
+
+  double inv_eps[NS];
+#pragma unroll
+  for (int d = 0; d < NS; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(st.epsmax[d]) : 0.0;
+  int idx[GD];
+#pragma unroll
+  for (int d = 0; d < GD; ++d) idx[d] = 0;
+  idx[0] = z0;
+  idx[1] = min(i1, N1 - 1);
+  if (NS == 3) idx[2] = min(i2, N2 - 1);
+  typename Blk::Pt pt = Blk::load(idx, g, ks);               // x_A is shared by the two nodes of my pair
+
+  const int myoff = ((a1 + 3) * Cfg::H2 + (NS == 3 ? a2 + 3 : 0)) * VB + 2 * vp;
+  const bool need_patch_1 = i10 - 3 < 0 || i10 + T1 + 2 >= N1;
+  const bool need_patch_2 = NS == 3 && (i20 - 3 < 0 || i20 + T2 + 2 >= N2);
+
+  RedAcc<GD> acc;
+  acc.init();
+
+  // ---- prologue (see k_stage_tma)
+  double2 q[3];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    mbar_wait(full_s + 8 * k, 0);
+    if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
+  }
+  if (bc0 == HJ_BC_EXTRAPOLATE && z0 == 0) {
+    const double2 e0 = lds2(ring + (size_t)3 * SLOT + myoff), e1 = lds2(ring + (size_t)4 * SLOT + myoff);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - k, g.slope_mult[0]);
+      q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - k, g.slope_mult[0]);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { mbar_arrive(empty_s + 0); mbar_arrive(empty_s + 8); mbar_arrive(empty_s + 16); }
+  if (tid == 0) {
+    for (unsigned k = R; k < (unsigned)R + 3 && k <= klast; ++k) {
+      mbar_wait(empty_s + 8 * (k - R), 0);
+      issue(k, k - R);
+    }
+  }
+
+  // ---- march
+  unsigned kc = 3;
+  unsigned s_prev = 2 % R, s_cur = 3 % R, s_p1 = 4 % R, s_p2 = 5 % R, s_new = 6 % R;
+  unsigned p_prev = 0, p_cur = 0, p_new = (6 / R) & 1;
+  int z = z0;
+  double2 raw_next = Blk::template fetch<0>(z0, g, ks);
+  // pointwise streams are fetched one plane ahead
+  const double2 zero2 = make_double2(0.0, 0.0);
+  double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;
+  double2 y0_next = (STAGE >= 2 && inb) ? ldg2(st.y0 + off) : zero2;
+
+  auto plane = [&]<bool FAST>() {
+    if constexpr (FAST) {
+      if (tid == 0) {
+        mbar_wait(empty_s + 8 * s_prev, p_prev);
+        tma_plane(s_prev, z + R - 1);
+      }
+    } else {
+      if (tid == 0 && kc >= 4 && kc - 1 + R <= klast) {
+        mbar_wait(empty_s + 8 * s_prev, p_prev);
+        issue(kc - 1 + R, s_prev);
+      }
+    }
+    Blk::template apply<0>(pt, raw_next, ks);
+    raw_next = Blk::template fetch<0>(min(z + 1, N0 - 1), g, ks);
+    const double2 tmpv = tmp_next, y0v = y0_next;
+    if (inb && z + 1 < z1) {
+      tmp_next = ldg2(st.tmp + off + zstride);
+      if (STAGE >= 2) y0_next = ldg2(st.y0 + off + zstride);
+    }
+    double2 auxv = zero2, obsv = zero2;
+    if (STAGE == 3 && inb) {
+      if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
+      if (st.use_obs) obsv = ldg2(st.obs + off);
+    }
+
+    const double* cur = ring + (size_t)s_cur * SLOT + myoff;
+    const double2 ctr = lds2(cur);
+    double2 am3 = lds2(cur - 3 * S1), am2 = lds2(cur - 2 * S1), am1 = lds2(cur - 1 * S1);
+    double2 ap1 = lds2(cur + 1 * S1), ap2 = lds2(cur + 2 * S1), ap3 = lds2(cur + 3 * S1);
+    double2 bm3 = zero2, bm2 = zero2, bm1 = zero2, bp1 = zero2, bp2 = zero2, bp3 = zero2;
+    if (NS == 3) {
+      bm3 = lds2(cur - 3 * S2); bm2 = lds2(cur - 2 * S2); bm1 = lds2(cur - 1 * S2);
+      bp1 = lds2(cur + 1 * S2); bp2 = lds2(cur + 2 * S2); bp3 = lds2(cur + 3 * S2);
+    }
+    double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
+    mbar_wait(full_s + 8 * s_new, p_new);
+    zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
+    if constexpr (!FAST) {
+      if (bc0 == HJ_BC_EXTRAPOLATE && z + 3 >= N0) {
+        const int ke = N0 - 1 - z;
+        const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
+        const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
+        const double m = g.slope_mult[0];
+        if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
+        if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
+        zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
+      }
+      if (need_patch_1 && inb)
+        patch_y<S1>(am3, am2, am1, ap1, ap2, ap3, i1, i10, N1, bc1, g.slope_mult[1], cur - (a1 + 3) * S1,
+                    st.in + off - (long long)i1 * g.stride[1], g.stride[1]);
+      if (need_patch_2 && inb)
+        patch_y<S2>(bm3, bm2, bm1, bp1, bp2, bp3, i2, i20, N2, bc2, g.slope_mult[NS == 3 ? 2 : 0], cur - (a2 + 3) * S2,
+                    st.in + off - (long long)i2 * g.stride[NS == 3 ? 2 : 0], g.stride[NS == 3 ? 2 : 0]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
+
+    double pcA[NS], hdA[NS], pcB[NS], hdB[NS];
+    double L, Rr;
+    constexpr bool red = RED;
+#define HJ_RED(d, ok)                                              \
+  if (red && (ok)) {                                               \
+    acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));                  \
+    acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));                  \
+  }
+    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, 0, inv_eps[0], pcA[0], hdA[0], L, Rr, red);
+    HJ_RED(0, ok0)
+    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, 0, inv_eps[0], pcB[0], hdB[0], L, Rr, red);
+    HJ_RED(0, ok1)
+    pc_hd<WENO>(am3.x, am2.x, am1.x, ctr.x, ap1.x, ap2.x, ap3.x, g, 1, inv_eps[1], pcA[1], hdA[1], L, Rr, red);
+    HJ_RED(1, ok0)
+    pc_hd<WENO>(am3.y, am2.y, am1.y, ctr.y, ap1.y, ap2.y, ap3.y, g, 1, inv_eps[1], pcB[1], hdB[1], L, Rr, red);
+    HJ_RED(1, ok1)
+    if constexpr (NS == 3) {
+      pc_hd<WENO>(bm3.x, bm2.x, bm1.x, ctr.x, bp1.x, bp2.x, bp3.x, g, 2, inv_eps[2], pcA[2], hdA[2], L, Rr, red);
+      HJ_RED(2, ok0)
+      pc_hd<WENO>(bm3.y, bm2.y, bm1.y, ctr.y, bp1.y, bp2.y, bp3.y, g, 2, inv_eps[2], pcB[2], hdB[2], L, Rr, red);
+      HJ_RED(2, ok1)
+    }
+#undef HJ_RED
+
+    double ydA = -Blk::ham(pt, pcA, ks), ydB = -Blk::ham(pt, pcB, ks);
+#pragma unroll
+    for (int d = 0; d < NS; ++d) {
+      const double a = Blk::alpha(d, pt, ks);
+      ydA = fma(hdA[d], a, ydA);
+      ydB = fma(hdB[d], a, ydB);
+      if (red && ok0) acc.amax[d] = fmax(acc.amax[d], a);
+    }
+
+    // tmp already holds in + dt * F_B(in): add this block's share, then the RK algebra + driver epilogue
+    const double vA = tmpv.x + st.dt * ydA, vB = tmpv.y + st.dt * ydB;
+    double oA, oB;
+    if (STAGE == 1) { oA = vA; oB = vB; }
+    else if (STAGE == 2) { oA = 0.25 * (3.0 * y0v.x + vA); oB = 0.25 * (3.0 * y0v.y + vB); }
+    else {
+      oA = (1.0 / 3.0) * (y0v.x + 2.0 * vA);
+      oB = (1.0 / 3.0) * (y0v.y + 2.0 * vB);
+      switch (st.comp) {
+        case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
+        case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;
+        case HJ_COMP_MIN_WITH_AUX: oA = fmin(oA, auxv.x); oB = fmin(oB, auxv.y); break;
+        case HJ_COMP_MAX_WITH_AUX: oA = fmax(oA, auxv.x); oB = fmax(oB, auxv.y); break;
+        default: break;
+      }
+      if (st.use_obs) { oA = fmax(oA, -obsv.x); oB = fmax(oB, -obsv.y); }
+    }
+    if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
+    else if (ok0) st.out[off] = oA;
+    if (red && ((ok0 && oA != oA) || (ok1 && oB != oB))) acc.nan = 1;
+
+    q[0] = q[1]; q[1] = q[2]; q[2] = ctr;
+    ++z; ++kc; off += zstride;
+    s_prev = s_cur; p_prev = p_cur;
+    s_cur = s_p1; if (s_cur == 0) p_cur ^= 1;
+    s_p1 = s_p2; s_p2 = s_new;
+    if (++s_new == (unsigned)R) { s_new = 0; p_new ^= 1; }
+  };
+
+  const int zf_end = (need_patch_1 || need_patch_2) ? z0 : z1 - R + 1;
+  plane.template operator()<false>();
+  while (z < zf_end) plane.template operator()<true>();
+  while (z < z1) plane.template operator()<false>();
+  if (RED) acc.flush(st.red);
+}
+
+}  // namespace hjtma

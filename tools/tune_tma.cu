@@ -63,7 +63,7 @@ static unsigned long long checksum(Problem& P, const double* p) {
 
 template <class Cfg, int STAGE>
 static float run_stage(Problem& P, int reps, unsigned long long* sum) {
-  auto kern = k_stage_tma<SysDubinsRel, HJ_WENO_AS_SHIPPED, false, STAGE, Cfg>;
+  auto kern = k_stage_tma<SysDubinsRel, 3, HJ_WENO_AS_SHIPPED, false, STAGE, Cfg>;
   constexpr size_t smem = Cfg::template smem_bytes<STAGE>();
   constexpr int NTHREADS = Cfg::NTHREADS;
   if (!P.plans[Cfg::TY]) {

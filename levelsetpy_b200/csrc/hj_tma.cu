@@ -15,8 +15,9 @@ using namespace hjtma;
 // production configurations (see tools/tune_tma.cu for the measured alternatives).
 //   whole 3-D systems: 32 x 16 tile, 8-slot ring, 2 CTAs/SM.
 //   product systems (dimension-split, hj_vec_kernel.cuh): pass 1 takes a tile shaped for the trailing block's
-//   plane (42 x 12 for the 41 x 41 planes of the 6-D pair, 54 x 9 for the 161 x 161 planes of the 4-D pair),
-//   pass 2 a {vector pairs, T1, T2} tile of the leading block.
+//   plane (42 x 12 for the 41 x 41 planes of the 6-D pair -- measured faster than the bank-conflict-free 48 x 7
+//   at 6 warps per CTA; 54 x 9 for the 161 x 161 planes of the 4-D pair), pass 2 a {vector pairs, TA, TB} tile of
+//   the leading block.
 using ProdCfg = TmaCfg<8, 2, 1>;
 template <class Sys> struct SplitCfg;
 template <> struct SplitCfg<SysDubinsRelPair> { using P1 = TmaCfg<8, 2, 1, 12, 21>; using P2 = VecCfg<3, 8, 2, 4, 7, 7>; };
@@ -131,7 +132,7 @@ struct TmaLauncher {
 struct PlanShape {
   int txp = ProdCfg::TXP, ty = ProdCfg::TY;
   bool split = false;
-  int ns = 0, vb = 0, t1 = 0, t2 = 0;
+  int ns = 0, vb = 0, ta = 0, tb = 0;
   template <class Sys>
   void operator()() {
     if constexpr (SysSplit<Sys>::value) {
@@ -139,7 +140,7 @@ struct PlanShape {
       using P2 = typename SplitCfg<Sys>::P2;
       txp = P1::TXP; ty = P1::TY;
       split = true;
-      ns = P2::NS; vb = P2::VB; t1 = P2::T1; t2 = P2::T2;
+      ns = P2::NS; vb = P2::VB; ta = P2::TA; tb = P2::TB;
     }
   }
 };
@@ -204,21 +205,22 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   }
   p->split = shape.split;
   if (shape.split) {
-    // pass 2: [V, (N2,) N1, N0 (+ halo planes)] with V = the flattened trailing dims; box {VB, (T2+6,) T1+6, 1}
-    const int NS = shape.ns;
+    // pass 2: [V, (N2,) N1, N0 (+ halo planes)] with V = the flattened trailing dims; the block's last dim is marched
+    // (box extent 1), the others are tiled with a 3-cell halo
+    const int NS = shape.ns, MD = NS - 1;
     const long long V = g.stride[NS - 1];
     const long long planes0 = g.N[0] + (halo0 ? 2 * HJ_GHOST : 0);
     VecGeom& vg = p->vgeo;
     vg.nvc = (int)((V + shape.vb - 1) / shape.vb);
-    vg.nt1 = (g.N[1] + shape.t1 - 1) / shape.t1;
-    vg.nt2 = NS == 3 ? (g.N[2] + shape.t2 - 1) / shape.t2 : 1;
-    vg.cz = g.N[0];
+    vg.nta = (g.N[0] + shape.ta - 1) / shape.ta;
+    vg.ntb = NS == 3 ? (g.N[1] + shape.tb - 1) / shape.tb : 1;
+    vg.cz = g.N[MD];
     vg.nzc = 1;
     vg.zcoord0 = halo0 ? HJ_GHOST : 0;
     vg.pitch = (int)pitch;
     vg.NX = NX;
-    p->vblocks = (long long)vg.nvc * vg.nt1 * vg.nt2 * vg.nzc;
-    if (g.N[0] < 4 || V > 0x7fffffffLL || p->vblocks > 0x7fffffffLL) {
+    p->vblocks = (long long)vg.nvc * vg.nta * vg.ntb * vg.nzc;
+    if (g.N[MD] < 4 || V > 0x7fffffffLL || p->vblocks > 0x7fffffffLL) {
       delete p;
       snprintf(err, errlen, "grid shape not supported by the dimension-split path");
       return nullptr;
@@ -233,12 +235,12 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
         rank = 4;
         dims[0] = (cuuint64_t)V; dims[1] = (cuuint64_t)g.N[2]; dims[2] = (cuuint64_t)g.N[1]; dims[3] = (cuuint64_t)planes0;
         strides[0] = (cuuint64_t)g.stride[2] * 8; strides[1] = (cuuint64_t)g.stride[1] * 8; strides[2] = (cuuint64_t)g.stride[0] * 8;
-        box[0] = shape.vb; box[1] = shape.t2 + 6; box[2] = shape.t1 + 6; box[3] = 1;
+        box[0] = shape.vb; box[1] = 1; box[2] = shape.tb + 6; box[3] = shape.ta + 6;
       } else {
         rank = 3;
         dims[0] = (cuuint64_t)V; dims[1] = (cuuint64_t)g.N[1]; dims[2] = (cuuint64_t)planes0;
         strides[0] = (cuuint64_t)g.stride[1] * 8; strides[1] = (cuuint64_t)g.stride[0] * 8;
-        box[0] = shape.vb; box[1] = shape.t1 + 6; box[2] = 1;
+        box[0] = shape.vb; box[1] = 1; box[2] = shape.ta + 6;
       }
       CUresult r = enc(&p->vmap[bidx], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, (void*)bufs[bidx], dims, strides, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -34,8 +34,9 @@ struct TmaGeom {
 };
 
 // tuning knobs of the plane-ring kernel
-template <int R_, int MINB_, int UNROLL_, int TY_ = 16, int TXP_ = 16>
+template <int R_, int MINB_, int UNROLL_, int TY_ = 16, int TXP_ = 16, bool SEQ_ = false>
 struct TmaCfg {
+  static constexpr bool SEQ = SEQ_;       // evaluate the stencil one dim at a time (smaller live set)
   static constexpr int R = R_;            // ring slots (planes z+1..z+3 are needed, the rest is prefetch distance)
   static constexpr int MINB = MINB_;      // resident CTAs per SM the register allocation is sized for
   static constexpr int UNROLL = UNROLL_;  // planes per trip of the fast march loop
@@ -126,11 +127,16 @@ HJ_DEV double2 slow_neighbor(const double* p, int i, int k, int n, long long s, 
 // neighbouring tile of a periodic dim) and are replaced here.  `srow` = my row inside the current slot (column
 // x0-4), `grow` = column 0 of my row in global memory.  Only called by threads with a node inside the grid.
 HJ_DEV void patch_x(double2& w0, double2& w1, double2& w2, double2& w3, double2& w4, const int ix, const int x0,
-                    const int NX, const int bc, const double m, const double* srow, const double* grow) {
+                    const int NX, const int bc, const double m, const double* srow, const double* grow,
+                    const bool whole) {
+  // `whole`: the tile spans the whole row (x0 == 0, NX <= TX), so periodic images are in the slot too
   if (ix < 3) {                                               // columns ix-3 .. ix-1 may be < 0
     double e0 = 0.0, e1 = 0.0;
     if (bc != HJ_BC_PERIODIC) { e0 = srow[0 - x0 + 4]; e1 = srow[1 - x0 + 4]; }
-    auto gl = [&](int c) { return bc == HJ_BC_PERIODIC ? __ldg(grow + c + NX) : ghost_extrapolate(e0, e1, -c, m); };
+    auto gl = [&](int c) {
+      if (bc == HJ_BC_PERIODIC) return whole ? srow[c + NX + 4] : __ldg(grow + c + NX);
+      return ghost_extrapolate(e0, e1, -c, m);
+    };
     if (ix - 3 < 0) w0.y = gl(ix - 3);
     if (ix - 2 < 0) w1.x = gl(ix - 2);
     if (ix - 1 < 0) w1.y = gl(ix - 1);
@@ -138,7 +144,10 @@ HJ_DEV void patch_x(double2& w0, double2& w1, double2& w2, double2& w3, double2&
   if (ix + 4 >= NX) {                                         // columns ix+1 .. ix+4 may be >= NX
     double f0 = 0.0, f1 = 0.0;
     if (bc != HJ_BC_PERIODIC) { f0 = srow[NX - 1 - x0 + 4]; f1 = srow[NX - 2 - x0 + 4]; }
-    auto gr = [&](int c) { return bc == HJ_BC_PERIODIC ? __ldg(grow + c - NX) : ghost_extrapolate(f0, f1, c - (NX - 1), m); };
+    auto gr = [&](int c) {
+      if (bc == HJ_BC_PERIODIC) return whole ? srow[c - NX + 4] : __ldg(grow + c - NX);
+      return ghost_extrapolate(f0, f1, c - (NX - 1), m);
+    };
     if (ix + 1 >= NX) w2.y = gr(ix + 1);
     if (ix + 2 >= NX) w3.x = gr(ix + 2);
     if (ix + 3 >= NX) w3.y = gr(ix + 3);
@@ -151,12 +160,13 @@ HJ_DEV void patch_x(double2& w0, double2& w1, double2& w2, double2& w3, double2&
 template <int BW>
 HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, double2& yp2, double2& yp3, const int iy,
                     const int y0, const int NY, const int bc, const double m, const double* scol, const double* gcol,
-                    const long long ys) {
+                    const long long ys, const bool whole) {
+  // `whole`: the tile spans the whole dim (y0 == 0, NY <= tile), so periodic images are in the slot too
   if (iy < 3) {
     double2 e0 = make_double2(0.0, 0.0), e1 = e0;
     if (bc != HJ_BC_PERIODIC) { e0 = lds2(scol + (0 - y0 + 3) * BW); e1 = lds2(scol + (1 - y0 + 3) * BW); }
     auto gt = [&](int r) {
-      if (bc == HJ_BC_PERIODIC) return ldg2(gcol + (long long)(r + NY) * ys);
+      if (bc == HJ_BC_PERIODIC) return whole ? lds2(scol + (r + NY + 3) * BW) : ldg2(gcol + (long long)(r + NY) * ys);
       return make_double2(ghost_extrapolate(e0.x, e1.x, -r, m), ghost_extrapolate(e0.y, e1.y, -r, m));
     };
     if (iy - 3 < 0) ym3 = gt(iy - 3);
@@ -167,7 +177,7 @@ HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, doub
     double2 f0 = make_double2(0.0, 0.0), f1 = f0;
     if (bc != HJ_BC_PERIODIC) { f0 = lds2(scol + (NY - 1 - y0 + 3) * BW); f1 = lds2(scol + (NY - 2 - y0 + 3) * BW); }
     auto gb = [&](int r) {
-      if (bc == HJ_BC_PERIODIC) return ldg2(gcol + (long long)(r - NY) * ys);
+      if (bc == HJ_BC_PERIODIC) return whole ? lds2(scol + (r - NY + 3) * BW) : ldg2(gcol + (long long)(r - NY) * ys);
       const int dist = r - (NY - 1);
       return make_double2(ghost_extrapolate(f0.x, f1.x, dist, m), ghost_extrapolate(f0.y, f1.y, dist, m));
     };
@@ -369,40 +379,6 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
                                g.bc[NSLOW - 1], g.slope_mult[NSLOW - 1]);
     }
 
-    const double* cur = ring + (size_t)s_cur * SLOT;
-    // X window: columns ix-4 .. ix+5 of my row (w2 = my pair); Y neighbours of the pair
-    const double2* rowp = reinterpret_cast<const double2*>(cur + myoff);
-    double2 w0 = rowp[-2], w1 = rowp[-1], w2 = rowp[0], w3 = rowp[1], w4 = rowp[2];
-    double2 ym3 = lds2(cur + myoff - 3 * BW), ym2 = lds2(cur + myoff - 2 * BW), ym1 = lds2(cur + myoff - 1 * BW);
-    double2 yp1 = lds2(cur + myoff + 1 * BW), yp2 = lds2(cur + myoff + 2 * BW), yp3 = lds2(cur + myoff + 3 * BW);
-    if (STAGE >= 2) y0v = lds2(yring + (size_t)s_cur * YSLOT + ty * TX + 2 * tp);
-    // Z neighbours above: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
-    double2 zp1 = make_double2(0.0, 0.0), zp2 = zp1, zp3 = zp1;
-    if (ZIN) { zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff); zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff); }
-    mbar_wait(full_s + 8 * s_new, p_new);
-    if (ZIN) zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
-    const double2 ctr = w2;
-    if constexpr (!FAST) {
-      if (ZIN && bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {         // ghost planes above the grid: edge plane NZ-1 = z+ke
-        const int ke = NZ - 1 - z;                           // 0..2
-        const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
-        const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
-        const double m = g.slope_mult[DZ];
-        if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
-        if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
-        zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
-      }
-      // ghost cells of the current plane in X / Y (tiles touching the domain boundary only), in registers
-      if (need_patch_x && ok0)
-        patch_x(w0, w1, w2, w3, w4, ix, x0, NX, bcx, g.slope_mult[DX], cur + (ty + 3) * BW, st.in + off - ix);
-      if (need_patch_y && ok0)
-        patch_y<BW>(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
-                st.in + off - (long long)iy * g.stride[DY], g.stride[DY]);
-    }
-    // this warp is done with the current plane's slot
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
-
     double pcA[D], hdA[D], pcB[D], hdB[D];
     double L, Rr;
     constexpr bool red = RED;
@@ -411,23 +387,67 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));                  \
     acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));                  \
   }
+    // Cfg::SEQ: one dim at a time (loads next to their use, compiler barriers in between) -- trades shared-memory
+    // latency hiding inside a warp for a smaller live set, i.e. more resident warps
+#define HJ_SEQ_BARRIER if constexpr (Cfg::SEQ) asm volatile("" ::: "memory");
+    const double* cur = ring + (size_t)s_cur * SLOT;
+    // X window: columns ix-4 .. ix+5 of my row (w2 = my pair)
+    const double2* rowp = reinterpret_cast<const double2*>(cur + myoff);
+    double2 w0 = rowp[-2], w1 = rowp[-1], w2 = rowp[0], w3 = rowp[1], w4 = rowp[2];
+    if constexpr (!FAST) {
+      // ghost cells of the current plane in X (tiles touching the domain boundary only), in registers
+      if (need_patch_x && ok0)
+        patch_x(w0, w1, w2, w3, w4, ix, x0, NX, bcx, g.slope_mult[DX], cur + (ty + 3) * BW, st.in + off - ix, NX <= TX);
+    }
+    const double2 ctr = w2;
     // X: node A uses columns ix-3..ix+3 = (w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y); node B is shifted by one
     pc_hd<WENO>(w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, g, DX, inv_eps[DX], pcA[DX], hdA[DX], L, Rr, red);
     HJ_RED(DX, ok0)
     pc_hd<WENO>(w1.x, w1.y, w2.x, w2.y, w3.x, w3.y, w4.x, g, DX, inv_eps[DX], pcB[DX], hdB[DX], L, Rr, red);
     HJ_RED(DX, ok1)
-    // Y
-    pc_hd<WENO>(ym3.x, ym2.x, ym1.x, ctr.x, yp1.x, yp2.x, yp3.x, g, DY, inv_eps[DY], pcA[DY], hdA[DY], L, Rr, red);
-    HJ_RED(DY, ok0)
-    pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, g, DY, inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
-    HJ_RED(DY, ok1)
-    // Z
-    if constexpr (ZIN) {
-      pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
-      HJ_RED(DZ, ok0)
-      pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
-      HJ_RED(DZ, ok1)
+    HJ_SEQ_BARRIER
+    {  // Y neighbours of the pair
+      double2 ym3 = lds2(cur + myoff - 3 * BW), ym2 = lds2(cur + myoff - 2 * BW), ym1 = lds2(cur + myoff - 1 * BW);
+      double2 yp1 = lds2(cur + myoff + 1 * BW), yp2 = lds2(cur + myoff + 2 * BW), yp3 = lds2(cur + myoff + 3 * BW);
+      if constexpr (!FAST) {
+        if (need_patch_y && ok0)
+          patch_y<BW>(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
+                      st.in + off - (long long)iy * g.stride[DY], g.stride[DY], NY <= TY);
+      }
+      pc_hd<WENO>(ym3.x, ym2.x, ym1.x, ctr.x, yp1.x, yp2.x, yp3.x, g, DY, inv_eps[DY], pcA[DY], hdA[DY], L, Rr, red);
+      HJ_RED(DY, ok0)
+      pc_hd<WENO>(ym3.y, ym2.y, ym1.y, ctr.y, yp1.y, yp2.y, yp3.y, g, DY, inv_eps[DY], pcB[DY], hdB[DY], L, Rr, red);
+      HJ_RED(DY, ok1)
     }
+    HJ_SEQ_BARRIER
+    if (STAGE >= 2) y0v = lds2(yring + (size_t)s_cur * YSLOT + ty * TX + 2 * tp);
+    {  // Z neighbours above: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
+      double2 zp1 = make_double2(0.0, 0.0), zp2 = zp1, zp3 = zp1;
+      if (ZIN) { zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff); zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff); }
+      mbar_wait(full_s + 8 * s_new, p_new);
+      if (ZIN) zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
+      if constexpr (!FAST) {
+        if (ZIN && bcz == HJ_BC_EXTRAPOLATE && z + 3 >= NZ) {  // ghost planes above the grid: edge plane NZ-1 = z+ke
+          const int ke = NZ - 1 - z;                           // 0..2
+          const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
+          const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
+          const double m = g.slope_mult[DZ];
+          if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
+          if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
+          zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
+        }
+      }
+      // this warp is done with the current plane's slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
+      if constexpr (ZIN) {
+        pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, DZ, inv_eps[DZ], pcA[DZ], hdA[DZ], L, Rr, red);
+        HJ_RED(DZ, ok0)
+        pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, DZ, inv_eps[DZ], pcB[DZ], hdB[DZ], L, Rr, red);
+        HJ_RED(DZ, ok1)
+      }
+    }
+    HJ_SEQ_BARRIER
     // slow dims (of the block)
 #pragma unroll
     for (int d = NSLOW - 1; d >= B0; --d) {
@@ -446,6 +466,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       HJ_RED(d, ok1)
     }
 #undef HJ_RED
+#undef HJ_SEQ_BARRIER
 
     // Hamiltonian + GLF dissipation (artificial_diss_glf.py:100: diss += 0.5*(R-L)*alpha)
     const double hamA = Sys::ham(ptA, pcA, ks), hamB = Sys::ham(ptB, pcB, ks);

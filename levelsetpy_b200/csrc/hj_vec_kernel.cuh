@@ -11,34 +11,39 @@
 // 6-D tile, but every byte is streamed once, coalesced, at HBM speed.
 //
 // Layout of pass 2: the trailing dims are flattened into one contiguous "vector" axis of V = stride[NS-1] elements
-// that carries no stencil.  A CTA owns VB consecutive vector elements (VP thread pairs) times a T1 x T2 tile of block
-// dims 1, 2 and marches along block dim 0.  Each plane of the tile with its 3-cell halo in dims 1, 2 -- a box
-// {VB, T2+6, T1+6, 1} of a 4-D tensor map [V, N2, N1, N0] (3-D for a 2-dim block) -- arrives by one TMA load into an
-// R-slot ring; the marching dim uses a 3-deep register queue + the ring slots of planes z+1..z+3, exactly like the
-// plane-ring kernel.  Both nodes of a thread's pair share their block-A state (x_A does not vary along the vector
+// that carries no stencil.  A CTA owns VB consecutive vector elements (VP thread pairs) times a TA x TB tile of the
+// first block dims and marches along the last block dim.  Each plane of the tile with its 3-cell halo in the tiled
+// dims -- a box {VB, 1, TB+6, TA+6} of a 4-D tensor map [V, N2, N1, N0] (3-D for a 2-dim block) -- arrives by one
+// TMA load into an R-slot ring; the marching dim uses a 3-deep register queue + the ring slots of planes z+1..z+3,
+// exactly like the plane-ring kernel.  Both nodes of a thread's pair share their block-A state (x_A does not vary along the vector
 // axis).  Ghost cells are made in registers from the TMA zero fill, as in hj_tma_kernel.cuh.
 #pragma once
 #include "hj_tma_kernel.cuh"
 
 struct VecGeom {
   int nvc;          // chunks along the vector axis
-  int nt1, nt2;     // tiles along block dims 1, 2 (nt2 = 1 for a 2-dim block)
-  int nzc, cz;      // chunks / planes per chunk along the marching dim (block dim 0)
-  int zcoord0;      // TMA coordinate of plane 0 of the marching dim (stored halo planes shift it)
+  int nta, ntb;     // tiles along the two tiled block dims (ntb = 1 for a 2-dim block)
+  int nzc, cz;      // chunks / planes per chunk along the marching block dim
+  int zcoord0;      // TMA coordinate shift of dim 0 (stored halo planes of a slab context)
   int pitch, NX;    // innermost padded / true extent: pad columns are excluded from stores and reductions
 };
 
-template <int NS_, int R_, int MINB_, int VP_, int T1_, int T2_>
+// The marching dim MD is the LAST dim of the block: for the relative-Dubins block that is the periodic heading, whose
+// wrap-around costs nothing when it is the marched dim (the ring simply loads plane z +- N), and on a slab context
+// dim 0 (thin, with stored halo planes) is then a tiled dim that one tile covers.
+template <int NS_, int R_, int MINB_, int VP_, int TA_, int TB_>
 struct VecCfg {
   static constexpr int NS = NS_;          // dims of the leading block (2 or 3)
+  static constexpr int MD = NS_ - 1;      // marching block dim
+  static constexpr int DA = 0, DB = NS_ == 3 ? 1 : -1;             // tiled block dims (DA slower in memory)
   static constexpr int R = R_, MINB = MINB_;
   static constexpr int VP = VP_, VB = 2 * VP_;                    // thread pairs / doubles along the vector axis
-  static constexpr int T1 = T1_, T2 = NS_ == 3 ? T2_ : 1;          // tile of block dims 1, 2
-  static constexpr int H1 = T1 + 6, H2 = NS_ == 3 ? T2 + 6 : 1;    // haloed tile
-  static constexpr int S2 = VB, S1 = H2 * VB;                      // slot strides (doubles) of block dims 2, 1
-  static constexpr int NACTIVE = VP * T1 * T2;
+  static constexpr int TA = TA_, TB = NS_ == 3 ? TB_ : 1;          // tile of the tiled dims
+  static constexpr int HA = TA + 6, HB = NS_ == 3 ? TB + 6 : 1;    // haloed tile
+  static constexpr int SB = VB, SA = HB * VB;                      // slot strides (doubles) of dims DB, DA
+  static constexpr int NACTIVE = VP * TA * TB;
   static constexpr int NTHREADS = (NACTIVE + 31) / 32 * 32;
-  static constexpr int BOX = H1 * H2 * VB;
+  static constexpr int BOX = HA * HB * VB;
   static constexpr int SLOT = (BOX + 15) / 16 * 16;
   static constexpr size_t smem_bytes() { return (size_t)R * SLOT * 8 + 2 * R * 8; }
 };
@@ -55,11 +60,11 @@ HJ_DEV void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int
 template <class Blk, int GD, int WENO, bool RED, int STAGE, class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB)
 k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys ks, const KStage st, const VecGeom geo) {
-  constexpr int NS = Cfg::NS;
+  constexpr int NS = Cfg::NS, MD = Cfg::MD, DA = Cfg::DA, DB = Cfg::DB >= 0 ? Cfg::DB : 0;
   static_assert(Blk::BASE_DIM == 0 && Blk::ND == NS && NS < GD, "pass 2 takes the leading dim block");
   static_assert(STAGE >= 1 && STAGE <= 3, "RK stages only");
-  constexpr int R = Cfg::R, SLOT = Cfg::SLOT, VB = Cfg::VB, VP = Cfg::VP, T1 = Cfg::T1, T2 = Cfg::T2;
-  constexpr int S1 = Cfg::S1, S2 = Cfg::S2;
+  constexpr int R = Cfg::R, SLOT = Cfg::SLOT, VB = Cfg::VB, VP = Cfg::VP, TA = Cfg::TA, TB = Cfg::TB;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB;
   constexpr int NTHREADS = Cfg::NTHREADS, NWARPS = NTHREADS / 32;
   static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
 
@@ -71,16 +76,18 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
   const int tid = threadIdx.x;
   long long b = blockIdx.x;
-  const int t2 = (int)(b % geo.nt2); b /= geo.nt2;
-  const int t1 = (int)(b % geo.nt1); b /= geo.nt1;
+  const int tb = (int)(b % geo.ntb); b /= geo.ntb;
+  const int ta = (int)(b % geo.nta); b /= geo.nta;
   const int zc = (int)(b % geo.nzc); b /= geo.nzc;
   const int v0 = (int)b * VB;
-  const int N0 = g.N[0], N1 = g.N[1], N2 = NS == 3 ? g.N[2] : 1;
+  const int NM = g.N[MD], NA = g.N[DA], NB = NS == 3 ? g.N[DB] : 1;
   const long long V = g.stride[NS - 1];
-  const int i10 = t1 * T1, i20 = t2 * T2, z0 = zc * geo.cz;
-  const int z1 = min(z0 + geo.cz, N0);
-  const int bc0 = g.bc[0], bc1 = g.bc[1], bc2 = NS == 3 ? g.bc[2] : HJ_BC_EXTRAPOLATE;
+  const int ia0 = ta * TA, ib0 = tb * TB, z0 = zc * geo.cz;
+  const int z1 = min(z0 + geo.cz, NM);
+  const int bcm = g.bc[MD], bca = g.bc[DA], bcb = NS == 3 ? g.bc[DB] : HJ_BC_EXTRAPOLATE;
   const unsigned klast = (unsigned)((z1 - 1 + 3) - (z0 - 3));
+  // stored halo planes of dim 0 (slab context) shift its TMA coordinate; dim 0 is the tiled dim DA
+  const int ca0 = ia0 - 3 + geo.zcoord0;
 
   if (tid == 0) {
 #pragma unroll
@@ -92,17 +99,18 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   auto tma_plane = [&](unsigned s, int zsrc) {
     const uint32_t fb = full_s + 8 * s;
     mbar_expect_tx(fb, Cfg::BOX * 8);
-    if constexpr (NS == 3) tma_load_4d(ring_s + s * (SLOT * 8), &tmap, fb, v0, i20 - 3, i10 - 3, geo.zcoord0 + zsrc);
-    else tma_load_3d(ring_s + s * (SLOT * 8), &tmap, fb, v0, i10 - 3, geo.zcoord0 + zsrc);
+    // tensor dims, fastest first: [V, N2, N1, N0] resp. [V, N1, N0]; the marching dim is the block's last dim
+    if constexpr (NS == 3) tma_load_4d(ring_s + s * (SLOT * 8), &tmap, fb, v0, zsrc, ib0 - 3, ca0);
+    else tma_load_3d(ring_s + s * (SLOT * 8), &tmap, fb, v0, zsrc, ca0);
   };
   // plane with ring position k -> slot s: TMA load, or a bare arrival for a computed ghost plane
   auto issue = [&](unsigned k, unsigned s) {
     const int zp = z0 - 3 + (int)k;
     int zsrc = zp;
     bool load = true;
-    if (zp < 0 || zp >= N0) {
-      if (bc0 == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + N0 : zp - N0;
-      else if (bc0 == HJ_BC_EXTRAPOLATE) load = false;
+    if (zp < 0 || zp >= NM) {
+      if (bcm == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NM : zp - NM;
+      else load = false;                                        // extrapolated ghost plane (the marched dim is never dim 0)
     }
     if (load) tma_plane(s, zsrc);
     else mbar_arrive(full_s + 8 * s);
@@ -116,15 +124,15 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   const bool live = tid < Cfg::NACTIVE;
   const int vp = tid % VP;
   const int pos = live ? tid / VP : 0;
-  const int a2 = pos % T2, a1 = pos / T2;
+  const int ab = pos % TB, aa = pos / TB;
   const long long iv = (long long)v0 + 2 * vp;
-  const int i1 = i10 + a1, i2 = i20 + a2;
-  const bool inb = live && iv < V && i1 < N1 && i2 < N2;
+  const int ia = ia0 + aa, ib = ib0 + ab;
+  const bool inb = live && iv < V && ia < NA && ib < NB;
   const int xcol = (int)(iv % geo.pitch);                    // innermost index of node A: pad columns are not nodes
   const bool ok0 = inb && xcol < geo.NX, ok1 = inb && xcol + 1 < geo.NX;
-  long long off = (long long)z0 * g.stride[0] + (long long)i1 * g.stride[1] + iv;
-  if (NS == 3) off += (long long)i2 * g.stride[2];
-  const long long zstride = g.stride[0];
+  long long off = (long long)z0 * g.stride[MD] + (long long)ia * g.stride[DA] + iv;
+  if (NS == 3) off += (long long)ib * g.stride[DB];
+  const long long zstride = g.stride[MD];
 
   double inv_eps[NS];
 #pragma unroll
@@ -132,14 +140,14 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   int idx[GD];
 #pragma unroll
   for (int d = 0; d < GD; ++d) idx[d] = 0;
-  idx[0] = z0;
-  idx[1] = min(i1, N1 - 1);
-  if (NS == 3) idx[2] = min(i2, N2 - 1);
+  idx[MD] = z0;
+  idx[DA] = min(ia, NA - 1);
+  if (NS == 3) idx[DB] = min(ib, NB - 1);
   typename Blk::Pt pt = Blk::load(idx, g, ks);               // x_A is shared by the two nodes of my pair
 
-  const int myoff = ((a1 + 3) * Cfg::H2 + (NS == 3 ? a2 + 3 : 0)) * VB + 2 * vp;
-  const bool need_patch_1 = i10 - 3 < 0 || i10 + T1 + 2 >= N1;
-  const bool need_patch_2 = NS == 3 && (i20 - 3 < 0 || i20 + T2 + 2 >= N2);
+  const int myoff = ((aa + 3) * Cfg::HB + (NS == 3 ? ab + 3 : 0)) * VB + 2 * vp;
+  const bool need_patch_a = bca != HJ_BC_HALO && (ia0 - 3 < 0 || ia0 + TA + 2 >= NA);
+  const bool need_patch_b = NS == 3 && (ib0 - 3 < 0 || ib0 + TB + 2 >= NB);
 
   RedAcc<GD> acc;
   acc.init();
@@ -151,12 +159,12 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     mbar_wait(full_s + 8 * k, 0);
     if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
   }
-  if (bc0 == HJ_BC_EXTRAPOLATE && z0 == 0) {
+  if (bcm == HJ_BC_EXTRAPOLATE && z0 == 0) {
     const double2 e0 = lds2(ring + (size_t)3 * SLOT + myoff), e1 = lds2(ring + (size_t)4 * SLOT + myoff);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - k, g.slope_mult[0]);
-      q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - k, g.slope_mult[0]);
+      q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - k, g.slope_mult[MD]);
+      q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - k, g.slope_mult[MD]);
     }
   }
   __syncwarp();
@@ -173,11 +181,9 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   unsigned s_prev = 2 % R, s_cur = 3 % R, s_p1 = 4 % R, s_p2 = 5 % R, s_new = 6 % R;
   unsigned p_prev = 0, p_cur = 0, p_new = (6 / R) & 1;
   int z = z0;
-  double2 raw_next = Blk::template fetch<0>(z0, g, ks);
-  // pointwise streams are fetched one plane ahead
+  double2 raw_next = Blk::template fetch<MD>(z0, g, ks);
   const double2 zero2 = make_double2(0.0, 0.0);
-  double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;
-  double2 y0_next = (STAGE >= 2 && inb) ? ldg2(st.y0 + off) : zero2;
+  double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;       // pass-1 result: fetched one plane ahead
 
   auto plane = [&]<bool FAST>() {
     if constexpr (FAST) {
@@ -191,50 +197,20 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
         issue(kc - 1 + R, s_prev);
       }
     }
-    Blk::template apply<0>(pt, raw_next, ks);
-    raw_next = Blk::template fetch<0>(min(z + 1, N0 - 1), g, ks);
-    const double2 tmpv = tmp_next, y0v = y0_next;
-    if (inb && z + 1 < z1) {
-      tmp_next = ldg2(st.tmp + off + zstride);
-      if (STAGE >= 2) y0_next = ldg2(st.y0 + off + zstride);
+    Blk::template apply<MD>(pt, raw_next, ks);
+    raw_next = Blk::template fetch<MD>(min(z + 1, NM - 1), g, ks);
+    // pointwise streams: issued first, consumed last
+    const double2 tmpv = tmp_next;
+    double2 y0v = zero2;
+    if (inb) {
+      if (z + 1 < z1) tmp_next = ldg2(st.tmp + off + zstride);
+      if (STAGE >= 2) y0v = ldg2(st.y0 + off);
     }
     double2 auxv = zero2, obsv = zero2;
     if (STAGE == 3 && inb) {
       if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
       if (st.use_obs) obsv = ldg2(st.obs + off);
     }
-
-    const double* cur = ring + (size_t)s_cur * SLOT + myoff;
-    const double2 ctr = lds2(cur);
-    double2 am3 = lds2(cur - 3 * S1), am2 = lds2(cur - 2 * S1), am1 = lds2(cur - 1 * S1);
-    double2 ap1 = lds2(cur + 1 * S1), ap2 = lds2(cur + 2 * S1), ap3 = lds2(cur + 3 * S1);
-    double2 bm3 = zero2, bm2 = zero2, bm1 = zero2, bp1 = zero2, bp2 = zero2, bp3 = zero2;
-    if (NS == 3) {
-      bm3 = lds2(cur - 3 * S2); bm2 = lds2(cur - 2 * S2); bm1 = lds2(cur - 1 * S2);
-      bp1 = lds2(cur + 1 * S2); bp2 = lds2(cur + 2 * S2); bp3 = lds2(cur + 3 * S2);
-    }
-    double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
-    mbar_wait(full_s + 8 * s_new, p_new);
-    zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
-    if constexpr (!FAST) {
-      if (bc0 == HJ_BC_EXTRAPOLATE && z + 3 >= N0) {
-        const int ke = N0 - 1 - z;
-        const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
-        const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
-        const double m = g.slope_mult[0];
-        if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
-        if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
-        zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
-      }
-      if (need_patch_1 && inb)
-        patch_y<S1>(am3, am2, am1, ap1, ap2, ap3, i1, i10, N1, bc1, g.slope_mult[1], cur - (a1 + 3) * S1,
-                    st.in + off - (long long)i1 * g.stride[1], g.stride[1]);
-      if (need_patch_2 && inb)
-        patch_y<S2>(bm3, bm2, bm1, bp1, bp2, bp3, i2, i20, N2, bc2, g.slope_mult[NS == 3 ? 2 : 0], cur - (a2 + 3) * S2,
-                    st.in + off - (long long)i2 * g.stride[NS == 3 ? 2 : 0], g.stride[NS == 3 ? 2 : 0]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
 
     double pcA[NS], hdA[NS], pcB[NS], hdB[NS];
     double L, Rr;
@@ -244,19 +220,60 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));                  \
     acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));                  \
   }
-    pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, 0, inv_eps[0], pcA[0], hdA[0], L, Rr, red);
-    HJ_RED(0, ok0)
-    pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, 0, inv_eps[0], pcB[0], hdB[0], L, Rr, red);
-    HJ_RED(0, ok1)
-    pc_hd<WENO>(am3.x, am2.x, am1.x, ctr.x, ap1.x, ap2.x, ap3.x, g, 1, inv_eps[1], pcA[1], hdA[1], L, Rr, red);
-    HJ_RED(1, ok0)
-    pc_hd<WENO>(am3.y, am2.y, am1.y, ctr.y, ap1.y, ap2.y, ap3.y, g, 1, inv_eps[1], pcB[1], hdB[1], L, Rr, red);
-    HJ_RED(1, ok1)
-    if constexpr (NS == 3) {
-      pc_hd<WENO>(bm3.x, bm2.x, bm1.x, ctr.x, bp1.x, bp2.x, bp3.x, g, 2, inv_eps[2], pcA[2], hdA[2], L, Rr, red);
-      HJ_RED(2, ok0)
-      pc_hd<WENO>(bm3.y, bm2.y, bm1.y, ctr.y, bp1.y, bp2.y, bp3.y, g, 2, inv_eps[2], pcB[2], hdB[2], L, Rr, red);
-      HJ_RED(2, ok1)
+    // One dim at a time (loads next to their use, compiler barriers in between): three haloed dims at once would
+    // need 72 registers of neighbour data.
+    const double* cur = ring + (size_t)s_cur * SLOT + myoff;
+    const double2 ctr = lds2(cur);
+    {  // tiled dim DA
+      double2 am3 = lds2(cur - 3 * SA), am2 = lds2(cur - 2 * SA), am1 = lds2(cur - 1 * SA);
+      double2 ap1 = lds2(cur + 1 * SA), ap2 = lds2(cur + 2 * SA), ap3 = lds2(cur + 3 * SA);
+      if constexpr (!FAST) {
+        if (need_patch_a && inb)
+          patch_y<SA>(am3, am2, am1, ap1, ap2, ap3, ia, ia0, NA, bca, g.slope_mult[DA], cur - (aa + 3) * SA,
+                      st.in + off - (long long)ia * g.stride[DA], g.stride[DA], NA <= TA);
+      }
+      pc_hd<WENO>(am3.x, am2.x, am1.x, ctr.x, ap1.x, ap2.x, ap3.x, g, DA, inv_eps[DA], pcA[DA], hdA[DA], L, Rr, red);
+      HJ_RED(DA, ok0)
+      pc_hd<WENO>(am3.y, am2.y, am1.y, ctr.y, ap1.y, ap2.y, ap3.y, g, DA, inv_eps[DA], pcB[DA], hdB[DA], L, Rr, red);
+      HJ_RED(DA, ok1)
+    }
+    asm volatile("" ::: "memory");
+    if constexpr (NS == 3) {  // tiled dim DB
+      double2 bm3 = lds2(cur - 3 * SB), bm2 = lds2(cur - 2 * SB), bm1 = lds2(cur - 1 * SB);
+      double2 bp1 = lds2(cur + 1 * SB), bp2 = lds2(cur + 2 * SB), bp3 = lds2(cur + 3 * SB);
+      if constexpr (!FAST) {
+        if (need_patch_b && inb)
+          patch_y<SB>(bm3, bm2, bm1, bp1, bp2, bp3, ib, ib0, NB, bcb, g.slope_mult[DB], cur - (ab + 3) * SB,
+                      st.in + off - (long long)ib * g.stride[DB], g.stride[DB], NB <= TB);
+      }
+      pc_hd<WENO>(bm3.x, bm2.x, bm1.x, ctr.x, bp1.x, bp2.x, bp3.x, g, DB, inv_eps[DB], pcA[DB], hdA[DB], L, Rr, red);
+      HJ_RED(DB, ok0)
+      pc_hd<WENO>(bm3.y, bm2.y, bm1.y, ctr.y, bp1.y, bp2.y, bp3.y, g, DB, inv_eps[DB], pcB[DB], hdB[DB], L, Rr, red);
+      HJ_RED(DB, ok1)
+      asm volatile("" ::: "memory");
+    }
+    {  // marching dim: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
+      double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
+      mbar_wait(full_s + 8 * s_new, p_new);
+      zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
+      if constexpr (!FAST) {
+        if (bcm == HJ_BC_EXTRAPOLATE && z + 3 >= NM) {
+          const int ke = NM - 1 - z;
+          const double2 ed = ke == 0 ? ctr : (ke == 1 ? zp1 : zp2);
+          const double2 nx = ke == 0 ? q[2] : (ke == 1 ? ctr : zp1);
+          const double m = g.slope_mult[MD];
+          if (ke < 1) zp1 = make_double2(ghost_extrapolate(ed.x, nx.x, 1 - ke, m), ghost_extrapolate(ed.y, nx.y, 1 - ke, m));
+          if (ke < 2) zp2 = make_double2(ghost_extrapolate(ed.x, nx.x, 2 - ke, m), ghost_extrapolate(ed.y, nx.y, 2 - ke, m));
+          zp3 = make_double2(ghost_extrapolate(ed.x, nx.x, 3 - ke, m), ghost_extrapolate(ed.y, nx.y, 3 - ke, m));
+        }
+      }
+      // this warp is done with the current plane's slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + 8 * s_cur);
+      pc_hd<WENO>(q[0].x, q[1].x, q[2].x, ctr.x, zp1.x, zp2.x, zp3.x, g, MD, inv_eps[MD], pcA[MD], hdA[MD], L, Rr, red);
+      HJ_RED(MD, ok0)
+      pc_hd<WENO>(q[0].y, q[1].y, q[2].y, ctr.y, zp1.y, zp2.y, zp3.y, g, MD, inv_eps[MD], pcB[MD], hdB[MD], L, Rr, red);
+      HJ_RED(MD, ok1)
     }
 #undef HJ_RED
 
@@ -298,7 +315,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     if (++s_new == (unsigned)R) { s_new = 0; p_new ^= 1; }
   };
 
-  const int zf_end = (need_patch_1 || need_patch_2) ? z0 : z1 - R + 1;
+  const int zf_end = (need_patch_a || need_patch_b) ? z0 : z1 - R + 1;
   plane.template operator()<false>();
   while (z < zf_end) plane.template operator()<true>();
   while (z < z1) plane.template operator()<false>();

@@ -170,11 +170,13 @@ int main(int argc, char** argv) {
   P.only = argc > 4 ? argv[4] : nullptr;
   printf("N=%d reps=%d\n", N, reps);
   unsigned long long ref[3] = {0, 0, 0};
-#define V(R, MINB, U, TY) run_variant<TmaCfg<R, MINB, U, TY>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY, reps, ref)
-  V(8, 2, 1, 16);
-  V(8, 2, 1, 18);
-  V(7, 2, 1, 18);
-  V(8, 4, 1, 8);
-  V(12, 4, 1, 8);
+#define V(R, MINB, U, TY, SEQ) run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ, reps, ref)
+  V(8, 2, 1, 16, false);
+  V(8, 2, 1, 16, true);
+  V(6, 3, 1, 16, true);
+  V(6, 3, 1, 16, false);
+  V(8, 3, 1, 12, true);
+  V(6, 5, 1, 8, true);
+  V(8, 4, 1, 8, true);
   return 0;
 }

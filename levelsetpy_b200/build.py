@@ -36,7 +36,8 @@ def _deps_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [nvcc()] + ARCH + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("HJ_EXTRA_NVCC_FLAGS", "").split()      # developer hook (tile-shape experiments)
+    cmd = [nvcc()] + ARCH + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJ, src + ".log")
     with open(log, "w") as fh:

@@ -17,10 +17,27 @@ using namespace hjtma;
 //   product systems (dimension-split, hj_vec_kernel.cuh): pass 1 takes a tile shaped for the trailing block's
 //   plane (42 x 12 for the 41 x 41 planes of the 6-D pair -- measured faster than the bank-conflict-free 48 x 7
 //   at 6 warps per CTA; 54 x 9 for the 161 x 161 planes of the 4-D pair), pass 2 a {vector pairs, TA, TB} tile of
-//   the leading block.
+//   the leading block.  Pass 2 of the 6-D pair is bound by the TMA unit's row rate: 128-byte rows (8 pairs) with a
+//   4 x 7 tile and a 6-slot ring (2 CTAs/SM) measured best: 53.6 / 65.5 / 65.3 ms per launch at 41^6 against
+//   73.7 / 90.5 / 90.0 ms for 64-byte rows with a 7 x 7 tile.
 using ProdCfg = TmaCfg<8, 2, 1>;
 template <class Sys> struct SplitCfg;
-template <> struct SplitCfg<SysDubinsRelPair> { using P1 = TmaCfg<8, 2, 1, 12, 21>; using P2 = VecCfg<3, 8, 2, 4, 7, 7>; };
+// tile shapes of the 6-D pair; the -D overrides are a developer hook (HJ_EXTRA_NVCC_FLAGS in build.py)
+#ifndef HJ_P2_R
+#define HJ_P2_R 6
+#define HJ_P2_MINB 2
+#define HJ_P2_VP 8
+#define HJ_P2_TA 4
+#define HJ_P2_TB 7
+#endif
+#ifndef HJ_P1_TY
+#define HJ_P1_MINB 2
+#define HJ_P1_TY 12
+#define HJ_P1_TXP 21
+#endif
+#define HJ_P2_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, HJ_P2_TA, HJ_P2_TB>
+#define HJ_P1_6D TmaCfg<8, HJ_P1_MINB, 1, HJ_P1_TY, HJ_P1_TXP>
+template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; };
 template <> struct SplitCfg<SysDoubleIntPair> { using P1 = TmaCfg<8, 2, 1, 9, 27>;  using P2 = VecCfg<2, 8, 2, 16, 16, 1>; };
 
 // ------------------------------------------------------------------------------------------ host side

@@ -73,3 +73,36 @@ def test_slabs_4d_pair_with_obstacle(lsp):
         assert t == to
         want = yo.reshape(g.shape)
         assert np.max(np.abs(w.download() - want)) <= 1e-9 * (want.max() - want.min())
+
+
+def test_slabs_6d_pair_split_path(lsp):
+    """6-D relative-Dubins pair on 2 slabs: the dimension-split path with stored halo planes on dim 0, which is a TILED
+    dim of pass 2 (one tile covers the thin slab) and is not touched by pass 1."""
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.slab import LocalWorld
+    N = [10, 9, 8, 7, 9, 12]
+    gmin = [-6, -10, 0, -6, -10, 0.]
+    gmax = [20, 10, 2 * np.pi * (1 - 1 / N[2]), 20, 10, 2 * np.pi * (1 - 1 / N[5])]
+    g = lsp.createGrid(np.array(gmin), np.array(gmax), np.array(N), pdDims=[2, 5])
+    x = np.meshgrid(*[np.asarray(v).reshape(-1) for v in g.vs], indexing="ij")
+    rng = np.random.default_rng(4)
+    d0 = np.minimum(np.sqrt(x[0] ** 2 + x[1] ** 2) - 5, np.sqrt(x[3] ** 2 + x[4] ** 2) - 5) \
+        + 0.3 * np.sin(x[2] + x[5]) + 0.02 * rng.standard_normal(g.shape)
+    s = lsp.ProductSystem(g, [lsp.DubinsVehicleRel(g, 5, 1), lsp.DubinsVehicleRel(g, 4, 1.2)])
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation))
+    o = osys.ProductSystem([osys.DubinsVehicleRel(g, 5, 1, dims=(0, 1, 2)), osys.DubinsVehicleRel(g, 4, 1.2, dims=(3, 4, 5))])
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    to, yo = 0.0, d0.reshape(-1, 1)
+    for _ in range(2):
+        y_last = yo
+        to, yo, _ = orc.ode_cfl3([to, 1.0], yo, osd, factor_cfl=0.8, single_step=True)
+        yo = np.minimum(yo, y_last)
+    want = yo.reshape(g.shape)
+    for be in (L.BACKEND_GATHER, L.BACKEND_TMA):
+        w = LocalWorld(sd, 2, backend=be)
+        w.upload(d0)
+        t = 0.0
+        for _ in range(2):
+            t, dt = w.step(t, 1.0, 0.8, comp=L.COMP_MIN_OVER_TIME)
+        assert t == to
+        assert np.max(np.abs(w.download() - want)) <= 1e-9 * (want.max() - want.min())

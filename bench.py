@@ -81,6 +81,23 @@ def product_setup(lsp, kind, n, planes0=None):
     raise SystemExit("unknown workload %r" % kind)
 
 
+def flock_batch_setup(lsp, nb, n):
+    """nb independent n^3 grids (flockGrid-style boxes shifted by 0.2 j), a 4-bird Flock each."""
+    sds, data = [], []
+    for j in range(nb):
+        sh = 0.2 * j
+        g = lsp.createGrid(np.array([-1 + sh, -1 + sh, -np.pi]), np.array([1 + sh, 1 + sh, np.pi * (1 - 2 / n)]),
+                           np.array([n, n, n]), pdDims=2, low_mem=True)
+        birds = [lsp.Bird(g, 1.0, 1.0, init_xyw=np.array([[0.1 * j + 0.01 * k], [0.2 * j - 0.02 * k], [0.3 * j + 0.1 * k]]),
+                          label=k, neigh_rad=3) for k in range(4)]
+        f = lsp.Flock(g, birds)
+        sds.append(lsp.Bundle(dict(grid=g, hamFunc=f.hamiltonian, partialFunc=f.dissipation)))
+        x = g.vs[0].reshape(-1, 1, 1) - sh
+        y = g.vs[1].reshape(1, -1, 1) - sh
+        data.append(np.broadcast_to(np.sqrt(x ** 2 + y ** 2) - 0.3, (n, n, n)))
+    return sds, data
+
+
 def fill_resident(eng, g, fill, planes_per_chunk=None):
     """Initial data straight into RK buffer 0 (pitched layout), a few dim-0 planes at a time."""
     N = [int(x) for x in np.asarray(g.N).reshape(-1)]
@@ -185,6 +202,9 @@ def workload_name(args):
     if args.workload == "dint4d":
         return ("4-D double-integrator pair %s fp64 (GLF, WENO5a, odeCFL3, minVOverTime), %d GPU(s), %d dim-0 planes "
                 "per GPU" % ("x".join([str(n * args.gpus)] + [str(n)] * 3), args.gpus, n))
+    if args.workload == "flockbatch":
+        return ("batch of %d independent %d^3 Flock grids (4 birds each, per-grid dt), one launch per RK stage for the "
+                "whole batch" % (args.batch, n))
     if args.workload == "dubins6d":
         return ("6-D relative-Dubins pair %s fp64 (GLF, WENO5a, odeCFL3, minVOverTime), %d GPU(s), %d dim-0 planes "
                 "per GPU" % ("x".join([str(args.planes0 or n)] + [str(n)] * 5), args.gpus, (args.planes0 or n) // args.gpus))
@@ -230,6 +250,14 @@ def run_ours(args):
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
         points = float(n) ** 3 * world
         barrier = lambda: dist.barrier()
+    elif args.workload == "flockbatch":
+        sds, data = flock_batch_setup(lsp, args.batch, n)
+        bsolver = lsp.BatchSolver(sds, device=local)
+        bsolver.upload(np.stack(data))
+        data0 = None
+        step = lambda t: float(bsolver.step(1e9, 0.8, comp)[0][0])
+        points = float(args.batch) * float(n) ** 3
+        barrier = lambda: None
     elif args.workload != "air3d":
         g, system, fill = product_setup(lsp, args.workload, n, args.planes0)
         sd = scheme_for(lsp, g, args.weno, system)
@@ -358,9 +386,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="nodes per dim (per GPU along dim 0); default per workload")
-    ap.add_argument("--workload", default="air3d", choices=["air3d", "dint4d", "dubins6d"],
+    ap.add_argument("--workload", default="air3d", choices=["air3d", "dint4d", "dubins6d", "flockbatch"],
                     help="air3d = configs[1] (the bench line); dint4d / dubins6d = configs[2] / [3] (1 GPU, resident state)")
     ap.add_argument("--planes0", type=int, default=None, help="dubins6d: dim-0 extent (default n)")
+    ap.add_argument("--batch", type=int, default=256, help="flockbatch: number of grids")
     ap.add_argument("--weno", default="as_shipped", choices=["as_shipped", "intended"])
     ap.add_argument("--backend", default="auto", choices=["auto", "gather", "tma"])
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -370,7 +399,7 @@ def main():
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes/launch from an ncu --set full capture")
     args = ap.parse_args()
     if args.n is None:
-        args.n = {"air3d": 512, "dint4d": 161, "dubins6d": 41}[args.workload]
+        args.n = {"air3d": 512, "dint4d": 161, "dubins6d": 41, "flockbatch": 101}[args.workload]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

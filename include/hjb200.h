@@ -186,6 +186,21 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
 int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
                        double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out);
 
+/* Batch contexts (many small independent grids, e.g. one 101^3 grid per Flock).
+ * nbatch grids of identical shape / dx / boundary kinds share one context: fields are [nbatch, N0, N1, N2]
+ * (hj_upload / hj_download move all of them at once), every grid has its own system parameter block and its own
+ * dt, and one launch per RK stage advances the whole batch.  Replaces the reference's Python loop over grids, each
+ * iteration of which is a full odeCFL3 call (ode_cfl_3.py:11) on an L2-sized field.  3-D grids, HJ_SYS_FLOCK,
+ * as_shipped WENO, TMA backend.  hj_set_system(ctx, HJ_SYS_FLOCK, NULL, nparams) registers the block length;
+ * hj_step_batch takes dt[nbatch] and the per-stage blocks [3][nbatch][nparams] (flock.py:213 re-derives the
+ * headings on each of the three RHS evaluations) from host memory. */
+int hj_create_batch(hj_ctx** ctx, int device, int nbatch, int ndim, const int64_t* N, const double* dx,
+                    const int* bc_kind, const int* bc_toward_zero, int weno_mode);
+int hj_step_batch(hj_ctx* ctx, void* stream, const double* dt_host, const double* stage_params_host, int comp,
+                  int use_obstacle);
+int hj_batch_size(const hj_ctx* ctx);
+
+
 /* Plain device-memory helpers so a host language without its own CUDA binding can drive the dense-array entry
  * points (the Python shim uses them when it is handed numpy arrays).  kind: 1 = H2D, 2 = D2H, 3 = D2D.       */
 int hj_device_count(void);

@@ -17,3 +17,4 @@ from .solver import HJIPDE_solve  # noqa: F401
 from .engine import Engine, engine_for_grid, clear_engine_cache  # noqa: F401
 
 __version__ = "0.1.0"
+from .batch import BatchSolver, batch_step_plan  # noqa: F401

@@ -52,6 +52,9 @@ struct hj_ctx {
   bool have_state = false, alpha_valid = false;
   double alpha_cache[HJ_MAX_DIM] = {};
   double step_bound_cache = 0.0;
+  int nbatch = 0;                // > 0: batch context (dim 0 of the internal grid is the batch index)
+  double* batch_dt = nullptr;    // [nbatch] per-element dt of the current step
+  double* batch_params = nullptr;// [3][nbatch][nparams] per-stage parameter blocks
   HjTmaPlan* plan = nullptr;
   bool plan_tried = false;
   std::string plan_err;
@@ -135,6 +138,8 @@ int hj_destroy(hj_ctx* c) {
   for (int b = 0; b < 3; ++b) cudaFree(c->buf[b]);
   for (int d = 0; d < HJ_MAX_DIM; ++d) cudaFree(c->vs_dev[d]);
   for (int t = 0; t < HJ_MAX_TABLES; ++t) cudaFree(c->tab_dev[t]);
+  cudaFree(c->batch_dt);
+  cudaFree(c->batch_params);
   cudaFree(c->aux);
   cudaFree(c->obs);
   cudaFree(c->staging);
@@ -160,7 +165,8 @@ static int upload_vec(double** dst, const double* host, int64_t n) {
 
 int hj_set_axis(hj_ctx* c, int dim, const double* vs_host, int64_t n) {
   if (!c || !vs_host) return fail(HJ_ERR_INVALID, "hj_set_axis: null argument");
-  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "hj_set_axis: Illegal dim parameter");
+  if (c->nbatch) dim += 1;       // user dims of a batch context sit behind the batch dim
+  if (dim < (c->nbatch ? 1 : 0) || dim >= c->D) return fail(HJ_ERR_INVALID, "hj_set_axis: Illegal dim parameter");
   if (n != c->gp.N[dim]) return fail(HJ_ERR_INVALID, "hj_set_axis: vs[%d] has %lld entries, grid.N is %d", dim, (long long)n, c->gp.N[dim]);
   CK(cudaSetDevice(c->device));
   int r = upload_vec(&c->vs_dev[dim], vs_host, n);
@@ -184,11 +190,19 @@ int hj_set_table(hj_ctx* c, int slot, const double* tab_host, int64_t n) {
 
 int hj_set_system(hj_ctx* c, int system_id, const double* params, int nparams) {
   if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (c->nbatch) {
+    if (system_id != HJ_SYS_FLOCK)
+      return fail(HJ_ERR_UNSUPPORTED, "hj_set_system: only HJ_SYS_FLOCK has a batch functor (got system id %d)", system_id);
+    system_id = HJ_SYS_FLOCK_BATCH;
+  }
   const int nd = hj_system_ndim(system_id);
   if (nd < 0) return fail(HJ_ERR_UNSUPPORTED, "hj_set_system: system id %d has no registered device functor", system_id);
-  if (nd != c->D) return fail(HJ_ERR_INVALID, "hj_set_system: system is %d-D but the grid is %d-D", nd, c->D);
-  if (nparams < 0 || nparams > HJ_MAX_PARAMS || (nparams && !params)) return fail(HJ_ERR_INVALID, "hj_set_system: bad parameter block");
-  if (system_id == HJ_SYS_FLOCK) {
+  if (nd != c->D) return fail(HJ_ERR_INVALID, "hj_set_system: system is %d-D but the grid is %d-D", nd - (c->nbatch ? 1 : 0), c->D - (c->nbatch ? 1 : 0));
+  if (nparams < 0 || nparams > HJ_MAX_PARAMS || (nparams && !params && !c->nbatch)) return fail(HJ_ERR_INVALID, "hj_set_system: bad parameter block");
+  if (system_id == HJ_SYS_FLOCK_BATCH) {
+    if (nparams < HJ_FLOCK_HDR || nparams > HJ_MAX_PARAMS) return fail(HJ_ERR_INVALID, "hj_set_system: batch flock block length must be %d..%d doubles", HJ_FLOCK_HDR, HJ_MAX_PARAMS);
+    params = nullptr;            // per-element blocks arrive with hj_step_batch
+  } else if (system_id == HJ_SYS_FLOCK) {
     if (nparams < HJ_FLOCK_HDR) return fail(HJ_ERR_INVALID, "hj_set_system: flock block needs >= %d doubles", HJ_FLOCK_HDR);
     const int K = (int)params[0];
     if (K < 0 || HJ_FLOCK_HDR + 3 * K > nparams) return fail(HJ_ERR_INVALID, "hj_set_system: flock block too short for %d birds", K);
@@ -196,7 +210,7 @@ int hj_set_system(hj_ctx* c, int system_id, const double* params, int nparams) {
   c->system_id = system_id;
   c->nparams = nparams;
   std::memset(c->ks.p, 0, sizeof c->ks.p);
-  if (nparams) std::memcpy(c->ks.p, params, nparams * sizeof(double));
+  if (nparams && params) std::memcpy(c->ks.p, params, nparams * sizeof(double));
   c->alpha_valid = false;
   return HJ_OK;
 }
@@ -350,7 +364,7 @@ int hj_rhs(hj_ctx* c, void* stream, double t, const double* y_dev, double* ydot_
   int r = check_ready(c, true);
   if (r) return r;
   if (!y_dev || !ydot_dev) return fail(HJ_ERR_INVALID, "hj_rhs: null argument");
-  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_rhs: dense-array entry point is not available on a slab context");
+  if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_rhs: dense-array entry point is not available on a slab / batch context");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* red = c->red + 3 * RED_STRIDE;
@@ -381,6 +395,7 @@ int hj_alpha_max(hj_ctx* c, void* stream, double t, double* alpha_max_host, doub
   (void)t;
   int r = check_ready(c, true);
   if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_alpha_max: batch flock alphas are host scalars of the parameter blocks");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (!c->alpha_valid) {
@@ -467,11 +482,16 @@ static bool use_tma(hj_ctx* c) {
 }
 
 static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
-                      int want_reduce, bool run_prepass) {
+                      int want_reduce, bool run_prepass, bool batch = false) {
   static const int in_[4] = {0, 0, 1, 2}, out_[4] = {0, 1, 2, 0};
   KSys ks = c->ks;
   if (params) std::memcpy(ks.p, params, c->nparams * sizeof(double));
   KStage st{};
+  if (batch) {                    // per-element parameter blocks of this stage + per-element dt
+    ks.p[0] = (double)c->nparams;
+    ks.tab[HJ_BATCH_TABLE] = c->batch_params + (size_t)(stage - 1) * c->nbatch * c->nparams;
+    st.dt_arr = c->batch_dt;
+  }
   st.stage = stage;
   st.comp = (stage == 3) ? comp : HJ_COMP_NONE;
   st.use_obs = (stage == 3) ? use_obs : 0;
@@ -498,6 +518,8 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
   }
   if (use_tma(c)) {
     CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s));
+  } else if (c->nbatch) {
+    return fail(HJ_ERR_UNSUPPORTED, "batch contexts run on the TMA backend only: %s", c->plan_err.c_str());
   } else {
     if (c->backend == HJ_BACKEND_TMA)
       return fail(HJ_ERR_UNSUPPORTED, "TMA backend unavailable for this grid: %s", c->plan_err.c_str());
@@ -511,6 +533,7 @@ int hj_stage(hj_ctx* c, void* stream, int stage, double t, double dt, const doub
   (void)t;
   int r = check_ready(c, true);
   if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_stage: use hj_step_batch on a batch context");
   if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage: no resident state (hj_upload first)");
   if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage: stage must be 1..3");
   CK(cudaSetDevice(c->device));
@@ -523,6 +546,7 @@ int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_pa
   (void)t;
   int r = check_ready(c, true);
   if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_step: use hj_step_batch on a batch context");
   if (!c->have_state) return fail(HJ_ERR_STATE, "hj_step: no resident state (hj_upload first)");
   if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_step: on a slab context drive hj_stage and exchange halos between stages");
   CK(cudaSetDevice(c->device));
@@ -550,7 +574,7 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   int r = check_ready(c, true);
   if (r) return r;
   if (!y_inout) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_single: null y");
-  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab context");
+  if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab / batch context");
   if (factor_cfl < 0.0) return fail(HJ_ERR_INVALID, "FactorCFL must be a positive scalar double value");   // ode_cfl_set.py:104
   if (max_step < 0.0) return fail(HJ_ERR_INVALID, "MaxStep must be a positive scalar double value");       // ode_cfl_set.py:106
   r = hj_upload(c, stream, HJ_FIELD_STATE, y_inout, is_host);
@@ -576,5 +600,62 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   if (dt_out) *dt_out = dt;
   return HJ_OK;
 }
+
+int hj_create_batch(hj_ctx** out, int device, int nbatch, int ndim, const int64_t* N, const double* dx,
+                    const int* bc_kind, const int* bc_toward_zero, int weno_mode) {
+  if (!out || !N || !dx || !bc_kind) return fail(HJ_ERR_INVALID, "hj_create_batch: null argument");
+  if (nbatch < 1) return fail(HJ_ERR_INVALID, "hj_create_batch: nbatch must be >= 1");
+  if (ndim != 3) return fail(HJ_ERR_UNSUPPORTED, "hj_create_batch: batches of 3-D grids only (got %d-D)", ndim);
+  if (weno_mode != HJ_WENO_AS_SHIPPED)
+    return fail(HJ_ERR_UNSUPPORTED, "hj_create_batch: the 'maxOverGrid' epsilon of the intended WENO is per grid; batch contexts run as_shipped only");
+  int64_t Nb[HJ_MAX_DIM];
+  double dxb[HJ_MAX_DIM];
+  int bcb[HJ_MAX_DIM], tzb[HJ_MAX_DIM];
+  Nb[0] = nbatch; dxb[0] = 1.0; bcb[0] = HJ_BC_EXTRAPOLATE; tzb[0] = 0;
+  for (int d = 0; d < ndim; ++d) {
+    if (bc_kind[d] == HJ_BC_HALO) return fail(HJ_ERR_UNSUPPORTED, "hj_create_batch: halo dims are for slab contexts");
+    Nb[d + 1] = N[d]; dxb[d + 1] = dx[d]; bcb[d + 1] = bc_kind[d]; tzb[d + 1] = bc_toward_zero ? bc_toward_zero[d] : 0;
+  }
+  hj_ctx* c = nullptr;
+  // hj_create wants N >= 4 per dim; the batch dim is never differentiated, so a batch of < 4 grids is legal:
+  // create with a padded extent and shrink it afterwards
+  const int64_t nb_create = nbatch < 4 ? 4 : nbatch;
+  Nb[0] = nb_create;
+  int r = hj_create(&c, device, ndim + 1, Nb, dxb, bcb, tzb, weno_mode);
+  if (r) return r;
+  if (nb_create != nbatch) {         // shrink the batch extent: strides of dims >= 1 do not depend on N[0]
+    c->gp.N[0] = c->gd.N[0] = nbatch;
+    c->nodes = c->nodes / nb_create * nbatch;
+    c->elems = c->plane * nbatch;
+  }
+  c->nbatch = nbatch;
+  c->axes_set |= 1u;                 // the batch dim has no axis
+  cudaError_t e = cudaMalloc(&c->batch_dt, nbatch * sizeof(double));
+  if (e != cudaSuccess) { hj_destroy(c); return fail(HJ_ERR_CUDA, "hj_create_batch: allocation failed: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return HJ_OK;
+}
+
+int hj_step_batch(hj_ctx* c, void* stream, const double* dt_host, const double* stage_params_host, int comp,
+                  int use_obstacle) {
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (!c->nbatch) return fail(HJ_ERR_STATE, "hj_step_batch: not a batch context (hj_create_batch)");
+  if (!dt_host || !stage_params_host) return fail(HJ_ERR_INVALID, "hj_step_batch: null argument");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_step_batch: no resident state (hj_upload first)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t np = (size_t)3 * c->nbatch * c->nparams;
+  if (!c->batch_params) CK(cudaMalloc(&c->batch_params, (size_t)3 * c->nbatch * HJ_MAX_PARAMS * sizeof(double)));
+  CK(cudaMemcpyAsync(c->batch_dt, dt_host, c->nbatch * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->batch_params, stage_params_host, np * sizeof(double), cudaMemcpyHostToDevice, s));
+  for (int stage = 1; stage <= 3; ++stage) {
+    r = stage_impl(c, s, stage, 0.0, nullptr, comp, use_obstacle, 0, false, true);
+    if (r) return r;
+  }
+  return HJ_OK;
+}
+
+int hj_batch_size(const hj_ctx* c) { return c ? c->nbatch : 0; }
 
 }  // extern "C"

@@ -40,6 +40,7 @@ struct KStage {
   int use_obs;      // stage 3 only
   int want_reduce;
   double dt;
+  const double* dt_arr; // batch contexts: one dt per batch element (dim 0), else nullptr
   const double* in;   // field the stencil reads
   const double* y0;   // y at the start of the step (stages 2,3), pointwise
   const double* tmp;  // dimension-split path, pass 2: in + dt * F_B(in) written by pass 1 (pointwise)

@@ -260,13 +260,18 @@ struct StageLauncher {
   const KSys& ks;
   const KStage& st;
   cudaStream_t s;
+  bool ok = true;
   template <class Sys>
   void operator()() {
-    constexpr int D = Sys::ND;
-    const long long no = outer_count<D>(g);
-    const dim3 grid = tile_grid(g, D, no), block(BX, BY);
-    if (weno == HJ_WENO_AS_SHIPPED) k_stage_gather<Sys, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, ks, st, no);
-    else k_stage_gather<Sys, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, ks, st, no);
+    if constexpr (Sys::BASE_DIM == 0) {
+      constexpr int D = Sys::ND;
+      const long long no = outer_count<D>(g);
+      const dim3 grid = tile_grid(g, D, no), block(BX, BY);
+      if (weno == HJ_WENO_AS_SHIPPED) k_stage_gather<Sys, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, ks, st, no);
+      else k_stage_gather<Sys, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, ks, st, no);
+    } else {
+      ok = false;    // batch functors only exist for the plane-ring kernel
+    }
   }
 };
 
@@ -275,11 +280,16 @@ struct AlphaLauncher {
   const KSys& ks;
   unsigned long long* red;
   cudaStream_t s;
+  bool ok = true;
   template <class Sys>
   void operator()() {
-    constexpr int D = Sys::ND;
-    const long long no = outer_count<D>(g);
-    k_alpha_max<Sys><<<tile_grid(g, D, no), dim3(BX, BY), 0, s>>>(g, ks, red, no);
+    if constexpr (Sys::BASE_DIM == 0) {
+      constexpr int D = Sys::ND;
+      const long long no = outer_count<D>(g);
+      k_alpha_max<Sys><<<tile_grid(g, D, no), dim3(BX, BY), 0, s>>>(g, ks, red, no);
+    } else {
+      ok = false;
+    }
   }
 };
 
@@ -289,6 +299,7 @@ cudaError_t hj_launch_stage_gather(int system_id, int weno, const KGrid& g, cons
                                    cudaStream_t s) {
   StageLauncher l{weno, g, ks, st, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
+  if (!l.ok) return cudaErrorNotSupported;
   hj_count_launch(1);
   return cudaGetLastError();
 }
@@ -317,6 +328,7 @@ cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, u
                                 cudaStream_t s) {
   AlphaLauncher l{g, ks, red, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
+  if (!l.ok) return cudaErrorNotSupported;
   hj_count_launch(1);
   return cudaGetLastError();
 }

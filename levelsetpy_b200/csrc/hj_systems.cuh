@@ -23,14 +23,14 @@
 
 template <int BASE, int PB, int TB>
 struct DubinsRelF {
-  static constexpr int ND = 3, BASE_DIM = BASE;
+  static constexpr int ND = 3, BASE_DIM = BASE, NSCRATCH = 0;
   // x1, x2 and the two x3-only coefficients of dubins_relative.py:81-82, evaluated un-fused like numpy does
   struct Pt { double x1, x2, p1c, p2c; };
   HJ_DEV static void set3(Pt& q, int i3, const KSys& k) {
     q.p1c = __dsub_rn(k.p[PB + 0], __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 0] + i3)));   // v_e - v_p cos x3
     q.p2c = __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 1] + i3));                          // v_p sin x3
   }
-  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k, const double* = nullptr) {
     Pt q;
     q.x1 = __ldg(g.vs[BASE + 0] + idx[BASE + 0]);
     q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
@@ -70,9 +70,9 @@ struct DubinsRelF {
 
 template <int BASE, int PB>
 struct DoubleIntF {
-  static constexpr int ND = 2, BASE_DIM = BASE;
+  static constexpr int ND = 2, BASE_DIM = BASE, NSCRATCH = 0;
   struct Pt { double x2; };
-  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k, const double* = nullptr) {
     Pt q;
     q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
     return q;
@@ -95,9 +95,9 @@ struct DoubleIntF {
 };
 
 struct FlockF {
-  static constexpr int ND = 3, BASE_DIM = 0;
+  static constexpr int ND = 3, BASE_DIM = 0, NSCRATCH = 0;
   struct Pt { int dummy; };
-  HJ_DEV static Pt load(const int*, const KGrid&, const KSys&) { return Pt{0}; }
+  HJ_DEV static Pt load(const int*, const KGrid&, const KSys&, const double* = nullptr) { return Pt{0}; }
   template <int GD>
   HJ_DEV static double2 fetch(int, const KGrid&, const KSys&) { return make_double2(0.0, 0.0); }
   template <int GD>
@@ -120,13 +120,49 @@ struct FlockF {
   HJ_DEV static double alpha(int dl, const Pt&, const KSys& k) { return k.p[7 + dl]; }
 };
 
+// Batch of independent Flock grids: the field is [nbatch, N0, N1, N2], dim 0 is the batch
+// index and carries no stencil; every batch element has its own parameter block (layout as FlockF) in the device
+// table k.tab[HJ_BATCH_TABLE] (k.p[0] = doubles per block), copied once per CTA into shared-memory scratch.
+#define HJ_BATCH_TABLE (HJ_MAX_TABLES - 1)
+struct FlockBatchF {
+  static constexpr int ND = 3, BASE_DIM = 1, NSCRATCH = HJ_MAX_PARAMS;
+  struct Pt { const double* P; };
+  HJ_DEV static void fill_scratch(double* scratch, long long batch, const KSys& k, int tid, int nthreads) {
+    const int n = (int)k.p[0];
+    const double* src = k.tab[HJ_BATCH_TABLE] + batch * n;
+    for (int i = tid; i < n; i += nthreads) scratch[i] = __ldg(src + i);
+  }
+  HJ_DEV static Pt load(const int*, const KGrid&, const KSys&, const double* scratch) { return Pt{scratch}; }
+  template <int GD>
+  HJ_DEV static double2 fetch(int, const KGrid&, const KSys&) { return make_double2(0.0, 0.0); }
+  template <int GD>
+  HJ_DEV static void apply(Pt&, const double2, const KSys&) {}
+  HJ_DEV static double ham(const Pt& q, const double* p, const KSys&) {
+    const double* P = q.P;
+    const int K = (int)P[0];
+    const double p1 = p[1], p2 = p[2], p3 = p[3];
+    double h = INFINITY;
+    for (int j = 0; j < K; ++j) {
+      const double* c = P + HJ_FLOCK_HDR + 3 * j;
+      h = fmin(h, p1 * c[0] + p2 * c[1] + p3 * c[2]);                      // bird.py:266-273
+    }
+    if (P[1] != 0.0) {
+      const double W = P[2];
+      const double ha = (p1 * P[3] - p2 * P[4]) + W * fabs(p2 * P[5] - p1 * P[6] + p3) + W * fabs(p3);
+      h = fmin(h, ha);                                                     // bird.py:305-316, flock.py:232-233
+    }
+    return h;
+  }
+  HJ_DEV static double alpha(int dl, const Pt& q, const KSys&) { return q.P[7 + dl]; }
+};
+
 template <class A, class B>
 struct PairF {
-  static constexpr int ND = A::ND + B::ND, BASE_DIM = 0;
+  static constexpr int ND = A::ND + B::ND, BASE_DIM = 0, NSCRATCH = 0;
   using First = A;     // dim block [0, A::ND)
   using Second = B;    // dim block [A::ND, ND): the trailing (contiguous) dims
   struct Pt { typename A::Pt a; typename B::Pt b; };
-  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k) {
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k, const double* = nullptr) {
     Pt q;
     q.a = A::load(idx, g, k);
     q.b = B::load(idx, g, k);
@@ -162,6 +198,8 @@ using SysDoubleInt = DoubleIntF<0, 0>;
 using SysFlock = FlockF;
 using SysDubinsRelPair = PairF<DubinsRelF<0, 0, 0>, DubinsRelF<3, HJ_DUBINS_NP, 2>>;
 using SysDoubleIntPair = PairF<DoubleIntF<0, 0>, DoubleIntF<2, HJ_DINT_NP>>;
+using SysFlockBatch = FlockBatchF;
+#define HJ_SYS_FLOCK_BATCH 100   // internal id: HJ_SYS_FLOCK registered on a batch context
 
 // host-side dispatch helper: calls f.template operator()<Sys>() for the functor registered under `id`
 template <class F>
@@ -172,6 +210,7 @@ inline bool hj_dispatch_system(int id, F&& f) {
     case HJ_SYS_FLOCK: f.template operator()<SysFlock>(); return true;
     case HJ_SYS_DUBINS_REL_PAIR: f.template operator()<SysDubinsRelPair>(); return true;
     case HJ_SYS_DOUBLE_INT_PAIR: f.template operator()<SysDoubleIntPair>(); return true;
+    case HJ_SYS_FLOCK_BATCH: f.template operator()<SysFlockBatch>(); return true;
     default: return false;
   }
 }
@@ -182,6 +221,7 @@ inline int hj_system_ndim(int id) {
     case HJ_SYS_FLOCK: return 3;
     case HJ_SYS_DUBINS_REL_PAIR: return 6;
     case HJ_SYS_DOUBLE_INT_PAIR: return 4;
+    case HJ_SYS_FLOCK_BATCH: return 4;   // grid dims incl. the batch dim
     default: return -1;
   }
 }

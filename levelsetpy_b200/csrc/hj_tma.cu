@@ -61,7 +61,7 @@ template <class Sys, int GD, int WENO, bool RED, int STAGE, class Cfg>
 static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const KGrid& g, const KSys& ks,
                               const KStage& st, cudaStream_t s) {
   auto kern = k_stage_tma<Sys, GD, WENO, RED, STAGE, Cfg>;
-  constexpr size_t smem = Cfg::template smem_bytes<STAGE>();
+  constexpr size_t smem = Cfg::template smem_bytes<STAGE>() + Sys::NSCRATCH * 8;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -103,9 +103,9 @@ struct TmaLauncher {
     const CUtensorMap& tm = p->tmap[in_buf];
     launches = 1;
     switch (st.stage) {
-      case 1: return launch_one<Sys, Sys::ND, WENO, RED, 1, ProdCfg>(p, tm, g, ks, st, s);
-      case 2: return launch_one<Sys, Sys::ND, WENO, RED, 2, ProdCfg>(p, tm, g, ks, st, s);
-      case 3: return launch_one<Sys, Sys::ND, WENO, RED, 3, ProdCfg>(p, tm, g, ks, st, s);
+      case 1: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 1, ProdCfg>(p, tm, g, ks, st, s);
+      case 2: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 2, ProdCfg>(p, tm, g, ks, st, s);
+      case 3: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 3, ProdCfg>(p, tm, g, ks, st, s);
       default: return cudaErrorNotSupported;
     }
   }

@@ -246,6 +246,13 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     for (int s = 0; s < R; ++s) { mbar_init(full_s + 8 * s, 1); mbar_init(empty_s + 8 * s, NCONS_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // batch functors keep the parameter block of this CTA's batch element (= the slow index) in shared memory
+  double* scratch = reinterpret_cast<double*>(smem_raw + Cfg::template smem_bytes<STAGE>());
+  if constexpr (Sys::NSCRATCH > 0) {
+    static_assert(NSLOW == 1, "batch functors: the only slow dim is the batch index");
+    Sys::fill_scratch(scratch, slow_flat, ks, tid, NTHREADS);
+  }
+  const double dt = st.dt_arr ? __ldg(st.dt_arr + slow_flat) : st.dt;
   __syncthreads();
 
   // plane with ring position k -> slot s: TMA load, or a bare arrival for a computed ghost plane
@@ -296,9 +303,9 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   idx[DZ] = z0;
   idx[DY] = min(iy, NY - 1);                                 // clamp: masked threads must not read past the axis tables
   idx[DX] = min(ix, NX - 1);
-  typename Sys::Pt ptA = Sys::load(idx, g, ks);
+  typename Sys::Pt ptA = Sys::load(idx, g, ks, scratch);
   idx[DX] = min(ix + 1, NX - 1);
-  typename Sys::Pt ptB = Sys::load(idx, g, ks);
+  typename Sys::Pt ptB = Sys::load(idx, g, ks, scratch);
 
   const int myoff = (ty + 3) * BW + 4 + 2 * tp;              // my pair inside a slot (doubles); 16-byte aligned
   // does any node of this tile have an X / Y stencil that leaves the grid?  (CTA-uniform)
@@ -485,13 +492,13 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     // RK stage algebra + driver epilogue (see stage_update in hj_common.cuh), on the pair
     double oA, oB;
     if (STAGE == 0) { oA = ydA; oB = ydB; }
-    else if (STAGE == 1) { oA = ctr.x + st.dt * ydA; oB = ctr.y + st.dt * ydB; }
+    else if (STAGE == 1) { oA = ctr.x + dt * ydA; oB = ctr.y + dt * ydB; }
     else if (STAGE == 2) {
-      oA = 0.25 * (3.0 * y0v.x + (ctr.x + st.dt * ydA));
-      oB = 0.25 * (3.0 * y0v.y + (ctr.y + st.dt * ydB));
+      oA = 0.25 * (3.0 * y0v.x + (ctr.x + dt * ydA));
+      oB = 0.25 * (3.0 * y0v.y + (ctr.y + dt * ydB));
     } else {
-      oA = (1.0 / 3.0) * (y0v.x + 2.0 * (ctr.x + st.dt * ydA));
-      oB = (1.0 / 3.0) * (y0v.y + 2.0 * (ctr.y + st.dt * ydB));
+      oA = (1.0 / 3.0) * (y0v.x + 2.0 * (ctr.x + dt * ydA));
+      oB = (1.0 / 3.0) * (y0v.y + 2.0 * (ctr.y + dt * ydB));
       switch (st.comp) {
         case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
         case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;

@@ -215,6 +215,15 @@ def workload_name(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def committed_traffic():
+    """dram bytes per stage launch from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            return float(json.load(fh)["avg_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import levelsetpy_b200 as lsp
@@ -367,7 +376,9 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": args.traffic, "peak_source": peak_src, "kernel": "k_stage_* (fused RHS + RK stage)",
+                     "traffic": args.traffic if args.traffic is not None else (
+                         committed_traffic() if (args.workload == "air3d" and world == 1 and n == 512) else None),
+                     "peak_source": peak_src, "kernel": "k_stage_* (fused RHS + RK stage)",
                      "algorithmic_bytes_per_launch": (points / world) * ALG_BYTES_PER_POINT_STEP / 3.0,
                      "avg_launch_ms": 1e3 * avg_launch_s},
     }

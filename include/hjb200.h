@@ -186,6 +186,17 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
 int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
                        double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out);
 
+/* termRestrictUpdate (ExplicitIntegration/Term/term_restrict_update.py:56-96): restrict the sign of the update,
+ * ydot = max(ydot, 0) (sign > 0, schemeData.positive true) or min(ydot, 0) (sign < 0), fused into every stage kernel
+ * and into hj_rhs; sign = 0 switches it off. */
+int hj_set_restrict(hj_ctx* ctx, int sign);
+
+/* odeCFL2 (ExplicitIntegration/Integration/ode_cfl_2.py): one step of the second-order TVD Runge-Kutta scheme on the
+ * resident state, y1 = y + dt f(y); y = 0.5 (y + (y1 + dt f(y1))), as two fused stage kernels; arguments as hj_step
+ * (stage_params: 2 parameter blocks or NULL). */
+int hj_step_rk2(hj_ctx* ctx, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,
+                int want_reduce);
+
 /* Batch contexts (many small independent grids, e.g. one 101^3 grid per Flock).
  * nbatch grids of identical shape / dx / boundary kinds share one context: fields are [nbatch, N0, N1, N2]
  * (hj_upload / hj_download move all of them at once), every grid has its own system parameter block and its own

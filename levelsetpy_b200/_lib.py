@@ -54,6 +54,8 @@ SIGNATURES = {
     "hj_memcpy": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
     "hj_stream_sync": (_i, [_vp]),
     "hj_ode_cfl3_single": (_i, [_vp, _vp, _d, _d, _d, _d, _vp, _i, _i, _i, _pd, _pd]),
+    "hj_set_restrict": (_i, [_vp, _i]),
+    "hj_step_rk2": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_create_batch": (_i, [C.POINTER(_vp), _i, _i, _i, _pi64, _pd, _pi, _pi, _i]),
     "hj_step_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "hj_batch_size": (_i, [_vp]),

@@ -52,6 +52,7 @@ struct hj_ctx {
   bool have_state = false, alpha_valid = false;
   double alpha_cache[HJ_MAX_DIM] = {};
   double step_bound_cache = 0.0;
+  int restrict_sign = 0;         // termRestrictUpdate: 0 off, +1 / -1
   int nbatch = 0;                // > 0: batch context (dim 0 of the internal grid is the batch index)
   double* batch_dt = nullptr;    // [nbatch] per-element dt of the current step
   double* batch_params = nullptr;// [3][nbatch][nparams] per-stage parameter blocks
@@ -376,6 +377,7 @@ int hj_rhs(hj_ctx* c, void* stream, double t, const double* y_dev, double* ydot_
   KStage st{};
   st.stage = 0;
   st.want_reduce = 1;
+  st.restrict_sign = c->restrict_sign;
   st.in = y_dev;
   st.out = ydot_dev;
   for (int d = 0; d < c->D; ++d) st.out_stride[d] = c->gd.stride[d];
@@ -481,32 +483,39 @@ static bool use_tma(hj_ctx* c) {
   return c->plan != nullptr;
 }
 
+// stage 1..3: the TVD-RK3 stages (ode_cfl_3.py:151,184-193,226-241); stage 4: the final stage of the RK2 scheme
+// (ode_cfl_2.py: y = 0.5 (y + (y1 + dt f(y1)))), which is the stage-3 kernel reading buffer 1
 static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
                       int want_reduce, bool run_prepass, bool batch = false) {
-  static const int in_[4] = {0, 0, 1, 2}, out_[4] = {0, 1, 2, 0};
+  static const int in_[5] = {0, 0, 1, 2, 1}, out_[5] = {0, 1, 2, 0, 0};
+  const bool final_stage = stage >= 3;
+  const int slot = stage == 4 ? 1 : stage - 1;   // reduction record / batch parameter set of this stage
   KSys ks = c->ks;
   if (params) std::memcpy(ks.p, params, c->nparams * sizeof(double));
   KStage st{};
   if (batch) {                    // per-element parameter blocks of this stage + per-element dt
     ks.p[0] = (double)c->nparams;
-    ks.tab[HJ_BATCH_TABLE] = c->batch_params + (size_t)(stage - 1) * c->nbatch * c->nparams;
+    ks.tab[HJ_BATCH_TABLE] = c->batch_params + (size_t)slot * c->nbatch * c->nparams;
     st.dt_arr = c->batch_dt;
   }
-  st.stage = stage;
-  st.comp = (stage == 3) ? comp : HJ_COMP_NONE;
-  st.use_obs = (stage == 3) ? use_obs : 0;
+  st.stage = final_stage ? 3 : stage;
+  st.comp = final_stage ? comp : HJ_COMP_NONE;
+  st.use_obs = final_stage ? use_obs : 0;
   st.want_reduce = want_reduce;
+  st.restrict_sign = c->restrict_sign;
+  st.fin_a = stage == 4 ? 0.5 : 1.0 / 3.0;
+  st.fin_b = stage == 4 ? 1.0 : 2.0;
   st.dt = dt;
   st.in = c->buf[in_[stage]] + c->origin;
   st.y0 = c->buf[0] + c->origin;
-  // dimension-split path: pass 1 parks in + dt F_B(in) in the stage's output buffer (stage 3: buffer 1, which is
-  // free by then -- buffer 0 still holds y0)
-  st.tmp = (stage == 3 ? c->buf[1] : c->buf[out_[stage]]) + c->origin;
+  // dimension-split path: pass 1 parks F_B(in) in the stage's output buffer (stage 3: buffer 1, which is free by
+  // then -- buffer 0 still holds y0; RK2 final stage: buffer 2)
+  st.tmp = (stage == 3 ? c->buf[1] : (stage == 4 ? c->buf[2] : c->buf[out_[stage]])) + c->origin;
   st.aux = c->aux ? c->aux + c->origin : nullptr;
   st.obs = c->obs ? c->obs + c->origin : nullptr;
   st.out = c->buf[out_[stage]] + c->origin;
   for (int d = 0; d < c->D; ++d) st.out_stride[d] = c->gp.stride[d];
-  st.red = c->red + (stage - 1) * RED_STRIDE;
+  st.red = c->red + slot * RED_STRIDE;
   st.epsmax = c->eps;
   if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX)
     if (!st.aux) return fail(HJ_ERR_STATE, "Need to define target function l(x)!");   // hji_solver.py:584
@@ -553,6 +562,29 @@ int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_pa
   for (int stage = 1; stage <= 3; ++stage) {
     const double* p = stage_params ? stage_params + (stage - 1) * c->nparams : nullptr;
     r = stage_impl(c, (cudaStream_t)stream, stage, dt, p, comp, use_obstacle, want_reduce, true);
+    if (r) return r;
+  }
+  return HJ_OK;
+}
+
+int hj_set_restrict(hj_ctx* c, int sign) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  c->restrict_sign = sign > 0 ? 1 : (sign < 0 ? -1 : 0);
+  return HJ_OK;
+}
+
+int hj_step_rk2(hj_ctx* c, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,
+                int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_step_rk2: not available on a batch context");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_step_rk2: no resident state (hj_upload first)");
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_step_rk2: slab contexts drive hj_stage (RK3)");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < 2; ++k) {
+    const double* p = stage_params ? stage_params + k * c->nparams : nullptr;
+    r = stage_impl(c, (cudaStream_t)stream, k == 0 ? 1 : 4, dt, p, comp, use_obstacle, want_reduce, true);
     if (r) return r;
   }
   return HJ_OK;

@@ -39,6 +39,8 @@ struct KStage {
   int comp;         // hj_comp (stage 3 only)
   int use_obs;      // stage 3 only
   int want_reduce;
+  int restrict_sign;  // termRestrictUpdate (term_restrict_update.py:91-94): +1 ydot = max(ydot,0), -1 min(ydot,0), 0 off
+  double fin_a, fin_b;  // final-stage combination y = fin_a*(y0 + fin_b*yLast): RK3 (1/3, 2) ode_cfl_3.py:241, RK2 (1/2, 1) ode_cfl_2.py
   double dt;
   const double* dt_arr; // batch contexts: one dt per batch element (dim 0), else nullptr
   const double* in;   // field the stencil reads
@@ -196,7 +198,12 @@ HJ_DEV double inv_eps_from_max(unsigned long long enc) {
 
 // ---------------------------------------------------------------- RK3 stage algebra + driver epilogue
 // ode_cfl_3.py:151 (y1), :184,:193 (y2, yHalf), :226,:241 (yThreeHalf, y); hji_solver.py:571-599, :641-644.
+HJ_DEV double restrict_update(double ydot, int sign) {
+  return sign > 0 ? fmax(ydot, 0.0) : (sign < 0 ? fmin(ydot, 0.0) : ydot);
+}
+
 HJ_DEV double stage_update(const KStage& st, double yin, double ydot, long long oidx) {
+  ydot = restrict_update(ydot, st.restrict_sign);
   if (st.stage == 0) return ydot;
   if (st.stage == 1) return yin + st.dt * ydot;
   const double y0 = st.y0[oidx];
@@ -205,7 +212,7 @@ HJ_DEV double stage_update(const KStage& st, double yin, double ydot, long long 
     return 0.25 * (3.0 * y0 + y2);
   }
   const double y32 = yin + st.dt * ydot;
-  double y = (1.0 / 3.0) * (y0 + 2.0 * y32);
+  double y = st.fin_a * (y0 + st.fin_b * y32);
   switch (st.comp) {
     case HJ_COMP_MIN_OVER_TIME: y = fmin(y, y0); break;
     case HJ_COMP_MAX_OVER_TIME: y = fmax(y, y0); break;

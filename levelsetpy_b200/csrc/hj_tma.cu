@@ -109,17 +109,18 @@ struct TmaLauncher {
       default: return cudaErrorNotSupported;
     }
   }
-  // product system: pass 1 (trailing block, tmp = in + dt F_B(in)) then pass 2 (leading block + stage algebra)
+  // product system: pass 1 (trailing block, tmp = F_B(in)) then pass 2 (leading block + stage algebra)
   template <class Sys, int WENO, bool RED>
   cudaError_t split_by_stage() {
     using P1 = typename SplitCfg<Sys>::P1;
     using P2 = typename SplitCfg<Sys>::P2;
     KStage s1 = st;
-    s1.stage = 1;
+    s1.stage = 0;                 // ydot of the trailing block only
     s1.comp = HJ_COMP_NONE;
     s1.use_obs = 0;
+    s1.restrict_sign = 0;         // termRestrictUpdate acts on the total ydot, in pass 2
     s1.out = const_cast<double*>(st.tmp);
-    cudaError_t e = launch_one<typename Sys::Second, Sys::ND, WENO, RED, 1, P1>(p, p->tmap[in_buf], g, ks, s1, s);
+    cudaError_t e = launch_one<typename Sys::Second, Sys::ND, WENO, RED, 0, P1>(p, p->tmap[in_buf], g, ks, s1, s);
     if (e != cudaSuccess) return e;
     launches = 2;
     const CUtensorMap& vm = p->vmap[in_buf];

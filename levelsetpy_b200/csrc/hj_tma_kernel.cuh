@@ -198,7 +198,7 @@ HJ_DEV void patch_y(double2& ym3, double2& ym2, double2& ym1, double2& yp1, doub
 // `Sys` is the functor of the dim block [BASE_DIM, BASE_DIM + ND) of a GD-dimensional grid and the kernel
 // differentiates along those dims only.  A whole system has BASE = 0, ND = GD.  The trailing block of a product
 // system (BASE + ND == GD, dimension-split path, see hj_vec_kernel.cuh) makes this kernel the first of two passes:
-// out = in + dt * F_B(in) with STAGE = 1.
+// out = F_B(in) with STAGE = 0.
 template <class Sys, int GD, int WENO, bool RED, int STAGE, class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB)
 k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y0, const KGrid g,
@@ -489,6 +489,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       }
     }
 
+    ydA = restrict_update(ydA, st.restrict_sign);
+    ydB = restrict_update(ydB, st.restrict_sign);
     // RK stage algebra + driver epilogue (see stage_update in hj_common.cuh), on the pair
     double oA, oB;
     if (STAGE == 0) { oA = ydA; oB = ydB; }
@@ -497,8 +499,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       oA = 0.25 * (3.0 * y0v.x + (ctr.x + dt * ydA));
       oB = 0.25 * (3.0 * y0v.y + (ctr.y + dt * ydB));
     } else {
-      oA = (1.0 / 3.0) * (y0v.x + 2.0 * (ctr.x + dt * ydA));
-      oB = (1.0 / 3.0) * (y0v.y + 2.0 * (ctr.y + dt * ydB));
+      oA = st.fin_a * (y0v.x + st.fin_b * (ctr.x + dt * ydA));
+      oB = st.fin_a * (y0v.y + st.fin_b * (ctr.y + dt * ydB));
       switch (st.comp) {
         case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
         case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;

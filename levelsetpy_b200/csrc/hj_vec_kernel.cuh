@@ -5,8 +5,8 @@
 // so one RHS is  F(y) = F_A(y) + F_B(y)  where F_A only differentiates along the leading dim block A and F_B along
 // the trailing (contiguous) block B.  A star stencil of radius 3 in 6 dims has no tile that fits shared memory or L2
 // with useful reuse in all dims, but each block alone is a 2-D/3-D stencil.  The stage is therefore two kernels:
-//     pass 1 (k_stage_tma on block B):  tmp = in + dt * F_B(in)                                   8 B r + 8 B w
-//     pass 2 (this kernel, block A):    out = RK_s(y0, tmp + dt * F_A(in))  [+ driver epilogue]   16(24) B r + 8 B w
+//     pass 1 (k_stage_tma on block B):  tmp = F_B(in)                                             8 B r + 8 B w
+//     pass 2 (this kernel, block A):    out = RK_s(y0, in + dt * (tmp + F_A(in)))  [+ epilogue]   16(24) B r + 8 B w
 // i.e. 40 / 48 / 48 B per node for the three stages instead of the 16 / 24 / 24 B of a (hypothetical) fully fused
 // 6-D tile, but every byte is streamed once, coalesced, at HBM speed.
 //
@@ -183,7 +183,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   int z = z0;
   double2 raw_next = Blk::template fetch<MD>(z0, g, ks);
   const double2 zero2 = make_double2(0.0, 0.0);
-  double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;       // pass-1 result: fetched one plane ahead
+  double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;       // pass-1 result F_B(in): fetched one plane ahead
 
   auto plane = [&]<bool FAST>() {
     if constexpr (FAST) {
@@ -286,14 +286,16 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
       if (red && ok0) acc.amax[d] = fmax(acc.amax[d], a);
     }
 
-    // tmp already holds in + dt * F_B(in): add this block's share, then the RK algebra + driver epilogue
-    const double vA = tmpv.x + st.dt * ydA, vB = tmpv.y + st.dt * ydB;
+    // tmp holds F_B(in) from pass 1: total ydot, termRestrictUpdate, then the RK algebra + driver epilogue
+    ydA = restrict_update(tmpv.x + ydA, st.restrict_sign);
+    ydB = restrict_update(tmpv.y + ydB, st.restrict_sign);
+    const double vA = ctr.x + st.dt * ydA, vB = ctr.y + st.dt * ydB;
     double oA, oB;
     if (STAGE == 1) { oA = vA; oB = vB; }
     else if (STAGE == 2) { oA = 0.25 * (3.0 * y0v.x + vA); oB = 0.25 * (3.0 * y0v.y + vB); }
     else {
-      oA = (1.0 / 3.0) * (y0v.x + 2.0 * vA);
-      oB = (1.0 / 3.0) * (y0v.y + 2.0 * vB);
+      oA = st.fin_a * (y0v.x + st.fin_b * vA);
+      oB = st.fin_a * (y0v.y + st.fin_b * vB);
       switch (st.comp) {
         case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
         case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;

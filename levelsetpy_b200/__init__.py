@@ -10,8 +10,8 @@ from .grids import createGrid, processGrid, flockGrid  # noqa: F401
 from .initial_conditions import *  # noqa: F401,F403
 from .spatial import upwindFirstWENO5, upwindFirstWENO5a  # noqa: F401
 from .dissipation import artificialDissipationGLF  # noqa: F401
-from .term import termLaxFriedrichs  # noqa: F401
-from .integration import odeCFL3, odeCFLset  # noqa: F401
+from .term import termLaxFriedrichs, termRestrictUpdate  # noqa: F401
+from .integration import odeCFL3, odeCFL2, odeCFLset  # noqa: F401
 from .systems import DubinsVehicleRel, DoubleIntegrator, Bird, Flock, ProductSystem  # noqa: F401
 from .solver import HJIPDE_solve  # noqa: F401
 from .engine import Engine, engine_for_grid, clear_engine_cache  # noqa: F401

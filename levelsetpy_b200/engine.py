@@ -268,6 +268,20 @@ class Engine:
         L.check(self.lib.hj_stage(self.h, self.stream(), int(stage), float(t), float(dt), p, int(comp),
                                   int(bool(use_obstacle)), int(bool(want_reduce))))
 
+    def set_restrict(self, sign):
+        """termRestrictUpdate: +1 -> ydot = max(ydot, 0); -1 -> min(ydot, 0); 0 -> off."""
+        L.check(self.lib.hj_set_restrict(self.h, int(sign)))
+
+    def step_rk2(self, t, dt, stage_params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False):
+        p = None
+        if stage_params is not None:
+            sp = np.ascontiguousarray(stage_params, dtype=np.float64).reshape(-1)
+            assert sp.size == 2 * self.nparams
+            p = sp.ctypes.data
+            self._sp_keep = sp
+        L.check(self.lib.hj_step_rk2(self.h, self.stream(), float(t), float(dt), p, int(comp), int(bool(use_obstacle)),
+                                     int(bool(want_reduce))))
+
     def step_reductions(self):
         n = 3 * self.D + 1
         buf = (C.c_double * (3 * n))()

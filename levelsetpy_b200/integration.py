@@ -1,12 +1,12 @@
-"""ExplicitIntegration/Integration call surface: ``odeCFLset`` and ``odeCFL3``."""
+"""ExplicitIntegration/Integration call surface: ``odeCFLset``, ``odeCFL3`` and ``odeCFL2``."""
 import numpy as np
 
 from . import _lib as L
 from .engine import is_torch_tensor
-from .term import eng_grid, prepare_scheme
+from .term import eng_grid, prepare_scheme, unwrap_scheme
 from .utilities import Bundle, cputime, eps, info, isbundle, iscell, isfield, realmax, strcmp, warn
 
-__all__ = ["odeCFLset", "odeCFL3", "rk3_times"]
+__all__ = ["odeCFLset", "odeCFL3", "odeCFL2", "rk3_times", "rk2_times"]
 
 
 def odeCFLset(kwargs=None):
@@ -61,8 +61,16 @@ def _step_bound(eng, ad, block):
     return 1 / inv
 
 
-def rk3_step_resident(eng, ad, grid, t, t_end, factorCFL, maxStep, comp=L.COMP_NONE, use_obstacle=False):
-    """One CFL-limited TVD-RK3 step on the engine's resident state.  Returns (t_new, dt)."""
+def rk2_times(t, dt):
+    """New time of one odeCFL2 step, arithmetic verbatim from ode_cfl_2.py (t1 = t+dt; t2 = t1+dt; t = 0.5 (t+t2))."""
+    t1 = t + dt
+    t2 = t1 + dt
+    return 0.5 * (t + t2)
+
+
+def rk3_step_resident(eng, ad, grid, t, t_end, factorCFL, maxStep, comp=L.COMP_NONE, use_obstacle=False, order=3):
+    """One CFL-limited TVD-RK3 (``order=3``, odeCFL3) or TVD-RK2 (``order=2``, odeCFL2) step on the engine's
+    resident state.  Returns (t_new, dt)."""
     safetyFactorCFL = min(1.0, 1.2 * factorCFL)                         # ode_cfl_3.py:95
     tables = list(enumerate(ad.tables(grid)))
     blocks = [ad.block()]
@@ -72,32 +80,25 @@ def rk3_step_resident(eng, ad, grid, t, t_end, factorCFL, maxStep, comp=L.COMP_N
     if ad.time_varying:
         # the reference's hamFunc mutates the system on each of the three RHS evaluations (flock.py:213)
         bounds = [stepBound]
-        for _ in range(2):
+        for _ in range(order - 1):
             b = ad.block()
             blocks.append(b)
             bounds.append(_step_bound(eng, ad, b))
-        for k, name in ((1, "Second"), (2, "Third")):
+        for k, name in ((1, "Second"), (2, "Third"))[:order - 1]:
             if deltaT > safetyFactorCFL * bounds[k]:                    # ode_cfl_3.py:173-175, :215-217
                 warn("%s substep violated CFL effective number %s" % (name, deltaT / bounds[k]))
-        eng.step(t, deltaT, np.concatenate(blocks), comp, use_obstacle)
+        (eng.step if order == 3 else eng.step_rk2)(t, deltaT, np.concatenate(blocks), comp, use_obstacle)
     else:
-        # state-only alpha: the stage-2/3 bounds equal the stage-1 bound, the CFL check cannot fire
-        eng.step(t, deltaT, None, comp, use_obstacle)
-    return rk3_times(t, deltaT)[2], deltaT
+        # state-only alpha: the later stages' bounds equal the stage-1 bound, the CFL check cannot fire
+        (eng.step if order == 3 else eng.step_rk2)(t, deltaT, None, comp, use_obstacle)
+    return (rk3_times(t, deltaT)[2] if order == 3 else rk2_times(t, deltaT)), deltaT
 
 
-def odeCFL3(schemeFunc, tspan, y0, options=None, schemeData=None):
-    """[t, y, schemeData] = odeCFL3(schemeFunc, tspan, y0, options, schemeData)
-    -- ExplicitIntegration/Integration/ode_cfl_3.py:11-277: third-order TVD Runge-Kutta with a CFL-limited step.
-
-    Each step is three fused sm_100a stage kernels on a field that stays resident in HBM; ``y0`` is uploaded once
-    and ``y`` downloaded once per call (numpy in -> numpy out; torch CUDA tensor in -> tensor out, no host copy).
-    ``schemeFunc`` must be ``termLaxFriedrichs`` (this package's or the reference's own object)."""
-    small = 100 * eps                                                   # ode_cfl_3.py:81
+def _ode_cfl(order, schemeFunc, tspan, y0, options, schemeData):
+    small = 100 * eps                                                   # ode_cfl_3.py:81 / ode_cfl_2.py
     if not options:
         options = odeCFLset()                                           # raises, like the reference (:85-86)
-    if getattr(schemeFunc, "__name__", None) != "termLaxFriedrichs":
-        raise NotImplementedError("schemeFunc=%r: only termLaxFriedrichs is compiled for the device" % (schemeFunc,))
+    inner, sign = unwrap_scheme(schemeFunc, schemeData)                 # termLaxFriedrichs | termRestrictUpdate(LF)
     if iscell(y0):
         raise NotImplementedError("vector level sets (cell y0) are outside the hot path")
     if isfield(options, "postTimeStep") and options.postTimeStep:
@@ -107,20 +108,42 @@ def odeCFL3(schemeFunc, tspan, y0, options=None, schemeData=None):
     numT = len(tspan)
     if numT != 2:
         raise NotImplementedError("tspan must have exactly two entries (odeCFLmultipleSteps is outside the hot path)")
-    eng, ad = prepare_scheme(schemeData)
-    grid = eng_grid(schemeData)
+    eng, ad = prepare_scheme(inner)
+    grid = eng_grid(inner)
     t = tspan[0]
     steps = 0
     startTime = cputime()
     eng.upload(y0)
-    while tspan[1] - t >= small * np.abs(tspan[1]):                     # ode_cfl_3.py:125
-        t, _ = rk3_step_resident(eng, ad, grid, t, tspan[1], options.factorCFL, options.maxStep)
-        steps += 1
-        if isfield(options, "singleStep") and strcmp(options.singleStep, "on"):
-            break                                                       # :250-251
+    eng.set_restrict(sign)
+    try:
+        while tspan[1] - t >= small * np.abs(tspan[1]):                 # ode_cfl_3.py:125
+            t, _ = rk3_step_resident(eng, ad, grid, t, tspan[1], options.factorCFL, options.maxStep, order=order)
+            steps += 1
+            if isfield(options, "singleStep") and strcmp(options.singleStep, "on"):
+                break                                                   # :250-251
+    finally:
+        eng.set_restrict(0)
     shape = tuple(y0.shape)
     y = eng.download(like=y0, shape=shape)
     endTime = cputime()
     if isfield(options, "stats") and strcmp(options.stats, "on"):
         info("%d steps in %.2g seconds from  %.2f to %.2f." % (steps, endTime - startTime, tspan[0], t))
     return t, y, schemeData
+
+
+def odeCFL3(schemeFunc, tspan, y0, options=None, schemeData=None):
+    """[t, y, schemeData] = odeCFL3(schemeFunc, tspan, y0, options, schemeData)
+    -- ExplicitIntegration/Integration/ode_cfl_3.py:11-277: third-order TVD Runge-Kutta with a CFL-limited step.
+
+    Each step is three fused sm_100a stage kernels on a field that stays resident in HBM; ``y0`` is uploaded once
+    and ``y`` downloaded once per call (numpy in -> numpy out; torch CUDA tensor in -> tensor out, no host copy).
+    ``schemeFunc`` must be ``termLaxFriedrichs`` or ``termRestrictUpdate`` around it (this package's or the
+    reference's own function objects)."""
+    return _ode_cfl(3, schemeFunc, tspan, y0, options, schemeData)
+
+
+def odeCFL2(schemeFunc, tspan, y0, options=None, schemeData=None):
+    """[t, y, schemeData] = odeCFL2(schemeFunc, tspan, y0, options, schemeData)
+    -- ExplicitIntegration/Integration/ode_cfl_2.py: second-order TVD Runge-Kutta (two forward-Euler substeps with the
+    CFL step of the first, then the average), two fused stage kernels per step.  Same argument rules as odeCFL3."""
+    return _ode_cfl(2, schemeFunc, tspan, y0, options, schemeData)

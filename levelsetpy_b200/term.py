@@ -6,7 +6,7 @@ from .engine import engine_for_grid, weno_mode_of
 from .functors import resolve
 from .utilities import iscell, isfield
 
-__all__ = ["termLaxFriedrichs", "prepare_scheme"]
+__all__ = ["termLaxFriedrichs", "termRestrictUpdate", "prepare_scheme", "unwrap_scheme"]
 
 _COSTATE = ("upwindFirstWENO5", "upwindFirstWENO5a")
 
@@ -51,6 +51,44 @@ def termLaxFriedrichs(t, y, schemeData):
     if iscell(schemeData):
         schemeData[0] = copy.copy(schemeData[0])
     return ydot, step_bound, schemeData
+
+
+def unwrap_scheme(schemeFunc, schemeData):
+    """(Lax-Friedrichs schemeData, restrict sign) for the two term functions the device path runs:
+    ``termLaxFriedrichs`` (sign 0) and ``termRestrictUpdate`` wrapped around it (term_restrict_update.py:68-94:
+    .innerFunc / .innerData / optional .positive, default True -> +1, False -> -1)."""
+    name = getattr(schemeFunc, "__name__", None)
+    if name == "termLaxFriedrichs":
+        return schemeData, 0
+    if name == "termRestrictUpdate":
+        sd = schemeData[0] if iscell(schemeData) else schemeData
+        assert isfield(sd, "innerFunc"), "innerFunc not in schemeData"     # term_restrict_update.py:65-66
+        assert isfield(sd, "innerData"), "innerData not in schemeData"
+        if getattr(sd.innerFunc, "__name__", None) != "termLaxFriedrichs":
+            raise NotImplementedError("termRestrictUpdate.innerFunc=%r: only termLaxFriedrichs is compiled for the device"
+                                      % (sd.innerFunc,))
+        positive = sd.positive if isfield(sd, "positive") else True         # :85-88
+        return sd.innerData, (1 if positive else -1)
+    raise NotImplementedError("schemeFunc=%r: only termLaxFriedrichs / termRestrictUpdate(termLaxFriedrichs) are "
+                              "compiled for the device" % (schemeFunc,))
+
+
+def termRestrictUpdate(t, y, schemeData):
+    """[ydot, stepBound, schemeData] = termRestrictUpdate(t, y, schemeData)
+    -- ExplicitIntegration/Term/term_restrict_update.py:9-96: the inner term's update with its sign restricted,
+    ``max(ydot, 0)`` (schemeData.positive, default) or ``min(ydot, 0)``; the restriction is fused into the same
+    kernel launch as the inner termLaxFriedrichs.  ``ydot`` is returned squeezed to (n,) like the reference (:92,:94)."""
+    inner, sign = unwrap_scheme(termRestrictUpdate, schemeData)
+    eng, ad = prepare_scheme(inner)
+    if iscell(y):
+        y = y[0]
+    eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(eng_grid(inner)))))
+    eng.set_restrict(sign)
+    try:
+        ydot, step_bound, _ = eng.rhs(t, y)
+    finally:
+        eng.set_restrict(0)
+    return ydot.reshape(-1), step_bound, schemeData
 
 
 def eng_grid(schemeData):

@@ -273,6 +273,74 @@ def ode_cfl3(tspan, y0, sd, factor_cfl=0.5, max_step=REALMAX, single_step=False,
     return t, y, dts
 
 
+def term_restrict_update(t, y, sd, positive=True, weno="as_shipped"):
+    """termRestrictUpdate around termLaxFriedrichs: ExplicitIntegration/Term/term_restrict_update.py:79-96.
+    ydot = max(inner, 0) if positive else min(inner, 0), squeezed to (n,) like the reference (:92,:94)."""
+    unrestricted, step_bound = term_lax_friedrichs(t, y, sd, weno)         # :79
+    if positive:
+        ydot = np.maximum(unrestricted, 0).squeeze()                       # :92
+    else:
+        ydot = np.minimum(unrestricted, 0).squeeze()                       # :94
+    return ydot, step_bound
+
+
+def ode_cfl2(tspan, y0, sd, factor_cfl=0.5, max_step=REALMAX, single_step=False, weno="as_shipped", restrict=None):
+    """ExplicitIntegration/Integration/ode_cfl_2.py (two-entry tspan, no hooks): forward Euler to t+dt, forward Euler
+    to t+2dt with the same dt, then the average.  ``restrict``: None -> schemeFunc = termLaxFriedrichs (y of shape
+    (n,1)); True/False -> schemeFunc = termRestrictUpdate(positive=restrict) (y of shape (n,), because the restricted
+    ydot is squeezed).  Returns (t, y, dts)."""
+    small = 100 * EPS
+    t = tspan[0]
+    y = np.array(y0, dtype=np.float64, copy=True)
+
+    def f(tt, yy):
+        if restrict is None:
+            return term_lax_friedrichs(tt, yy, sd, weno)
+        return term_restrict_update(tt, yy, sd, restrict, weno)
+    dts = []
+    while tspan[1] - t >= small * np.abs(tspan[1]):
+        ydot, sb = f(t, y)
+        dt = float(np.min(np.hstack((factor_cfl * sb, tspan[1] - t, max_step))))
+        t1 = t + dt
+        y1 = y + dt * ydot
+        ydot, sb = f(t1, y1)
+        t2 = t1 + dt
+        y2 = y1 + dt * ydot
+        t = 0.5 * (t + t2)
+        y = 0.5 * (y + y2)
+        dts.append(dt)
+        if single_step:
+            break
+    return t, y, dts
+
+
+def ode_cfl3_restricted(tspan, y0, sd, positive, factor_cfl=0.5, max_step=REALMAX, single_step=False, weno="as_shipped"):
+    """odeCFL3 (ode_cfl_3.py:125-251) with schemeFunc = termRestrictUpdate(positive); y of shape (n,)."""
+    small = 100 * EPS
+    t = tspan[0]
+    y = np.array(y0, dtype=np.float64, copy=True)
+    dts = []
+    while tspan[1] - t >= small * np.abs(tspan[1]):
+        ydot, sb = term_restrict_update(t, y, sd, positive, weno)
+        dt = float(np.min(np.hstack((factor_cfl * sb, tspan[1] - t, max_step))))
+        t1 = t + dt
+        y1 = y + dt * ydot
+        ydot, sb = term_restrict_update(t1, y1, sd, positive, weno)
+        t2 = t1 + dt
+        y2 = y1 + dt * ydot
+        t_half = 0.25 * (3 * t + t2)
+        y_half = 0.25 * (3 * y + y2)
+        ydot, sb = term_restrict_update(t_half, y_half, sd, positive, weno)
+        t_three_half = t_half + dt
+        y_three_half = y_half + dt * ydot
+        t = (1 / 3) * (t + 2 * t_three_half)
+        y = (1 / 3) * (y + 2 * y_three_half)
+        dts.append(dt)
+        if single_step:
+            break
+    return t, y, dts
+
+
 def hji_solve(data0, tau, sd, comp_method="minVOverTime", obstacle=None, target=None, weno="as_shipped",
               factor_cfl=0.8):
     """The driver loop of ValueFuncs/hji_solver.py:509-656 in ``keepLast`` mode (the only storage mode

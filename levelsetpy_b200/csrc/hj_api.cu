@@ -56,6 +56,10 @@ struct hj_ctx {
   int nbatch = 0;                // > 0: batch context (dim 0 of the internal grid is the batch index)
   double* batch_dt = nullptr;    // [nbatch] per-element dt of the current step
   double* batch_params = nullptr;// [3][nbatch][nparams] per-stage parameter blocks
+  // pipelined host <-> device stepping (hj_ode_cfl3_single with host buffers)
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_up, ev_done;
+  cudaEvent_t ev_start = nullptr;
   HjTmaPlan* plan = nullptr;
   bool plan_tried = false;
   std::string plan_err;
@@ -136,6 +140,11 @@ int hj_destroy(hj_ctx* c) {
   if (!c) return HJ_OK;
   cudaSetDevice(c->device);
   if (c->plan) hj_tma_plan_destroy(c->plan);
+  for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   for (int b = 0; b < 3; ++b) cudaFree(c->buf[b]);
   for (int d = 0; d < HJ_MAX_DIM; ++d) cudaFree(c->vs_dev[d]);
   for (int t = 0; t < HJ_MAX_TABLES; ++t) cudaFree(c->tab_dev[t]);
@@ -486,7 +495,7 @@ static bool use_tma(hj_ctx* c) {
 // stage 1..3: the TVD-RK3 stages (ode_cfl_3.py:151,184-193,226-241); stage 4: the final stage of the RK2 scheme
 // (ode_cfl_2.py: y = 0.5 (y + (y1 + dt f(y1)))), which is the stage-3 kernel reading buffer 1
 static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
-                      int want_reduce, bool run_prepass, bool batch = false) {
+                      int want_reduce, bool run_prepass, bool batch = false, int zbeg = 0, int zend = 0) {
   static const int in_[5] = {0, 0, 1, 2, 1}, out_[5] = {0, 1, 2, 0, 0};
   const bool final_stage = stage >= 3;
   const int slot = stage == 4 ? 1 : stage - 1;   // reduction record / batch parameter set of this stage
@@ -526,7 +535,7 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
     CK(hj_launch_maxd1sq(c->gp, st.in, c->eps, -1, s));
   }
   if (use_tma(c)) {
-    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s));
+    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s, zbeg, zend));
   } else if (c->nbatch) {
     return fail(HJ_ERR_UNSUPPORTED, "batch contexts run on the TMA backend only: %s", c->plan_err.c_str());
   } else {
@@ -601,6 +610,70 @@ int hj_step_reductions(hj_ctx* c, void* stream, double* reduce_host) {
   return HJ_OK;
 }
 
+// Host-buffer stepping as a software pipeline (3-D grids whose dim 0 is the marched Z dim): dim 0 is cut into chunks;
+// chunk k+1 is on its way up while the stage kernels of chunks <= k run as a wavefront S1(w), S2(w-1), S3(w-2) on the
+// compute stream (stream order satisfies every +-3-plane stencil dependency, and stage 3's in-place write of chunk k
+// comes after every stage-1 read of it), and chunk w-2 goes down on a third stream as soon as its stage 3 is done.
+// With pinned host memory the two PCIe directions overlap each other and the compute.
+static bool can_pipeline(hj_ctx* c, int is_host) {
+  if (!is_host || c->D != 3 || c->halo0 || c->nbatch || c->weno != HJ_WENO_AS_SHIPPED) return false;
+  if (c->pitch != c->gp.N[2] || c->gp.bc[0] == HJ_BC_PERIODIC || c->gp.N[0] < 64) return false;
+  if (ensure_buffers(c) != HJ_OK) return false;
+  return use_tma(c) && !hj_tma_plan_is_split(c->plan);
+}
+
+static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, double* y_host, int comp, int use_obs) {
+  const int N0 = c->gp.N[0];
+  int P = (N0 + 15) / 16;
+  if (P < 32) P = 32;
+  const int C = (N0 + P - 1) / P;
+  if (!c->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  }
+  while ((int)c->ev_up.size() < C) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_up.push_back(e);
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_done.push_back(e);
+  }
+  // copies start after whatever the caller queued on its stream before this call
+  CK(cudaEventRecord(c->ev_start, s));
+  CK(cudaStreamWaitEvent(c->s_h2d, c->ev_start, 0));
+  CK(cudaStreamWaitEvent(c->s_d2h, c->ev_start, 0));
+  const size_t plane = (size_t)c->plane;
+  auto lo = [&](int k) { return k * P; };
+  auto hi = [&](int k) { return (k + 1) * P < N0 ? (k + 1) * P : N0; };
+  for (int k = 0; k < C; ++k) {
+    CK(cudaMemcpyAsync(c->buf[0] + lo(k) * plane, y_host + lo(k) * plane, (hi(k) - lo(k)) * plane * sizeof(double),
+                       cudaMemcpyHostToDevice, c->s_h2d));
+    CK(cudaEventRecord(c->ev_up[k], c->s_h2d));
+  }
+  c->have_state = true;
+  for (int w = 0; w < C + 2; ++w) {
+    int r;
+    if (w < C) {
+      CK(cudaStreamWaitEvent(s, c->ev_up[w + 1 < C ? w + 1 : C - 1], 0));     // the +3-plane halo lives in chunk w+1
+      if ((r = stage_impl(c, s, 1, dt, nullptr, comp, use_obs, 0, false, false, lo(w), hi(w)))) return r;
+    }
+    if (w >= 1 && w - 1 < C)
+      if ((r = stage_impl(c, s, 2, dt, nullptr, comp, use_obs, 0, false, false, lo(w - 1), hi(w - 1)))) return r;
+    if (w >= 2) {
+      const int k = w - 2;
+      if ((r = stage_impl(c, s, 3, dt, nullptr, comp, use_obs, 0, false, false, lo(k), hi(k)))) return r;
+      CK(cudaEventRecord(c->ev_done[k], s));
+      CK(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
+      CK(cudaMemcpyAsync(y_host + lo(k) * plane, c->buf[0] + lo(k) * plane, (hi(k) - lo(k)) * plane * sizeof(double),
+                         cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+  }
+  CK(cudaStreamSynchronize(c->s_d2h));
+  CK(cudaStreamSynchronize(s));
+  return HJ_OK;
+}
+
 int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double factor_cfl, double max_step,
                        double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out) {
   int r = check_ready(c, true);
@@ -609,8 +682,6 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab / batch context");
   if (factor_cfl < 0.0) return fail(HJ_ERR_INVALID, "FactorCFL must be a positive scalar double value");   // ode_cfl_set.py:104
   if (max_step < 0.0) return fail(HJ_ERR_INVALID, "MaxStep must be a positive scalar double value");       // ode_cfl_set.py:106
-  r = hj_upload(c, stream, HJ_FIELD_STATE, y_inout, is_host);
-  if (r) return r;
   double sb = 0;
   r = hj_alpha_max(c, stream, t, nullptr, &sb);
   if (r) return r;
@@ -618,11 +689,18 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   double dt = factor_cfl * sb;
   if (t_end - t < dt) dt = t_end - t;
   if (max_step < dt) dt = max_step;
-  r = hj_step(c, stream, t, dt, nullptr, comp, use_obstacle, 0);
-  if (r) return r;
-  r = hj_download(c, stream, HJ_FIELD_STATE, y_inout, is_host);
-  if (r) return r;
-  if (!is_host) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (can_pipeline(c, is_host)) {
+    r = pipelined_step(c, (cudaStream_t)stream, dt, y_inout, comp, use_obstacle);
+    if (r) return r;
+  } else {
+    r = hj_upload(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+    if (r) return r;
+    r = hj_step(c, stream, t, dt, nullptr, comp, use_obstacle, 0);
+    if (r) return r;
+    r = hj_download(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+    if (r) return r;
+    if (!is_host) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  }
   // ode_cfl_3.py:145,178,187,220,236 -- time arithmetic kept verbatim
   const double t1 = t + dt;
   const double t2 = t1 + dt;

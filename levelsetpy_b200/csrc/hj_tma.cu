@@ -204,6 +204,9 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   p->geo.nslow = nslow;
   p->geo.zcoord0 = zcoord0;
   p->geo.NZ = NZ;
+  p->geo.zbeg = 0;
+  p->geo.zend = NZ;
+  p->tiles = tiles;
   p->nblocks = tiles * p->geo.nzc;
   if (p->nblocks > 0x7fffffffLL) { delete p; snprintf(err, errlen, "grid too large"); return nullptr; }
   for (int bidx = 0; bidx < 4; ++bidx) {                    // 0..2: haloed boxes on the RK buffers; 3: y0 tile on buffer 0
@@ -274,9 +277,20 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
 }
 
 void hj_tma_plan_destroy(HjTmaPlan* p) { delete p; }
+bool hj_tma_plan_is_split(const HjTmaPlan* p) { return p && p->split; }
 
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
-                                const KStage& st, int in_buf, cudaStream_t s) {
+                                const KStage& st, int in_buf, cudaStream_t s, int zbeg, int zend) {
+  HjTmaPlan sub;
+  if (zend > zbeg) {               // advance only planes [zbeg, zend) of Z (pipelined host <-> device stepping)
+    if (plan->split) return cudaErrorNotSupported;
+    sub = *plan;
+    sub.geo.zbeg = zbeg;
+    sub.geo.zend = zend;
+    sub.geo.nzc = (zend - zbeg + sub.geo.cz - 1) / sub.geo.cz;
+    sub.nblocks = sub.tiles * sub.geo.nzc;
+    plan = &sub;
+  }
   TmaLauncher l{plan, in_buf, weno, g, ks, st, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
   hj_count_launch(l.launches);

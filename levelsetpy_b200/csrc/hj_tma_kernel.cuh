@@ -31,6 +31,7 @@ struct TmaGeom {
   long long nslow;            // product of slow dims
   long long zcoord0;          // TMA dim-2 coordinate of (slow = 0, z = 0)  (halo planes on dim 0 shift it)
   int NZ;
+  int zbeg, zend;             // planes [zbeg, zend) of Z are advanced by this launch (whole dim: 0, NZ)
 };
 
 // tuning knobs of the plane-ring kernel
@@ -235,8 +236,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   const int zc = (int)(b % geo.nzc); b /= geo.nzc;
   const long long slow_flat = b;
   const int NX = g.N[DX], NY = g.N[DY], NZ = g.N[DZ];
-  const int x0 = xt * TX, y0 = yt * TY, z0 = zc * geo.cz;
-  const int z1 = min(z0 + geo.cz, NZ);
+  const int x0 = xt * TX, y0 = yt * TY, z0 = geo.zbeg + zc * geo.cz;
+  const int z1 = min(z0 + geo.cz, geo.zend);
   const int bcx = g.bc[DX], bcy = g.bc[DY], bcz = g.bc[DZ];
   const unsigned klast = (unsigned)((z1 - 1 + 3) - (z0 - 3));   // ring position of the last plane this chunk needs
   const int zcoord_base = (int)(geo.zcoord0 + slow_flat * NZ);

@@ -11,6 +11,7 @@ struct HjTmaPlan {
   TmaGeom geo;
   int tx, ty;
   long long nblocks;
+  long long tiles;         // (X, Y, slow) tiles: nblocks = tiles * geo.nzc
   // dimension-split path (product systems): pass 2 tensor maps + geometry
   bool split = false;
   CUtensorMap vmap[3];

@@ -243,3 +243,32 @@ def test_step_reductions_match_oracle(lsp):
         assert np.allclose(rec["derivMax"], info["derivMax"], rtol=1e-11, atol=1e-12)
         assert not rec["nan"]
         eng.set_backend(L.BACKEND_AUTO)
+
+
+@pytest.mark.parametrize("N,pd", [([70, 40, 50], [2]), ([131, 36, 34], [1, 2]), ([64, 33, 40], [])])
+def test_pipelined_host_step_is_bit_identical(lsp, N, pd):
+    """hj_ode_cfl3_single with a HOST buffer runs as a chunked H2D / wavefront-of-stages / D2H pipeline (3-D grids with
+    N0 >= 64 and an even innermost extent); it must give the bits of the resident three-launch step, for every
+    compMethod epilogue, and the oracle's t."""
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.term import prepare_scheme
+    g, d0 = _air_case(lsp, N, pd)
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    sd = scheme(lsp, g, s)
+    eng, ad = prepare_scheme(sd)
+    eng.set_backend(L.BACKEND_TMA)
+    eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g))))
+    o = osys.DubinsVehicleRel(g, 5, 1)
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    to, yo, _ = orc.ode_cfl3([0.0, 1.0], d0.reshape(-1, 1), osd, factor_cfl=0.8, single_step=True)
+    for comp in (L.COMP_NONE, L.COMP_MIN_OVER_TIME):
+        y = np.ascontiguousarray(d0.reshape(-1)).copy()
+        t1, _, dt = eng.ode_cfl3_single(0.0, 1.0, 0.8, np.finfo(np.float64).max, y, comp)
+        eng.upload(d0)
+        eng.step(0.0, dt, None, comp, False)
+        want = eng.download().reshape(-1)
+        assert t1 == to
+        assert np.array_equal(y, want), "comp=%d: max diff %.3e" % (comp, np.max(np.abs(y - want)))
+        if comp == L.COMP_NONE:
+            assert_close(y.reshape(-1, 1), yo, FIELD_TOL, "pipelined step vs oracle")
+    eng.set_backend(L.BACKEND_AUTO)

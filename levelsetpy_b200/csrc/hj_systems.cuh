@@ -25,7 +25,9 @@ template <int BASE, int PB, int TB>
 struct DubinsRelF {
   static constexpr int ND = 3, BASE_DIM = BASE, NSCRATCH = 0;
   // x1, x2 and the two x3-only coefficients of dubins_relative.py:81-82, evaluated un-fused like numpy does
-  struct Pt { double x1, x2, p1c, p2c; };
+  // awx1/awx2 = |w x1|, |w x2| (the state-only parts of alpha_1 / alpha_0) are kept per node so that the marched
+  // plane body adds them instead of re-multiplying
+  struct Pt { double x1, x2, p1c, p2c, awx1, awx2; };
   HJ_DEV static void set3(Pt& q, int i3, const KSys& k) {
     q.p1c = __dsub_rn(k.p[PB + 0], __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 0] + i3)));   // v_e - v_p cos x3
     q.p2c = __dmul_rn(k.p[PB + 1], __ldg(k.tab[TB + 1] + i3));                          // v_p sin x3
@@ -34,6 +36,8 @@ struct DubinsRelF {
     Pt q;
     q.x1 = __ldg(g.vs[BASE + 0] + idx[BASE + 0]);
     q.x2 = __ldg(g.vs[BASE + 1] + idx[BASE + 1]);
+    q.awx1 = fabs(__dmul_rn(k.p[PB + 2], q.x1));
+    q.awx2 = fabs(__dmul_rn(k.p[PB + 2], q.x2));
     set3(q, idx[BASE + 2], k);
     return q;
   }
@@ -48,8 +52,8 @@ struct DubinsRelF {
   }
   template <int GD>
   HJ_DEV static void apply(Pt& q, const double2 r, const KSys& k) {
-    if (GD == BASE + 0) q.x1 = r.x;
-    if (GD == BASE + 1) q.x2 = r.x;
+    if (GD == BASE + 0) { q.x1 = r.x; q.awx1 = fabs(__dmul_rn(k.p[PB + 2], r.x)); }
+    if (GD == BASE + 1) { q.x2 = r.x; q.awx2 = fabs(__dmul_rn(k.p[PB + 2], r.x)); }
     if (GD == BASE + 2) {
       q.p1c = __dsub_rn(k.p[PB + 0], __dmul_rn(k.p[PB + 1], r.x));
       q.p2c = __dmul_rn(k.p[PB + 1], r.y);
@@ -61,9 +65,8 @@ struct DubinsRelF {
     return p1 * q.p1c - p2 * q.p2c - w * fabs(p1 * q.x2 - p2 * q.x1 - p3) + w * fabs(p3);
   }
   HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
-    const double w = k.p[PB + 2];
-    if (dl == 0) return __dadd_rn(fabs(q.p1c), fabs(__dmul_rn(w, q.x2)));
-    if (dl == 1) return __dadd_rn(fabs(q.p2c), fabs(__dmul_rn(w, q.x1)));
+    if (dl == 0) return __dadd_rn(fabs(q.p1c), q.awx2);
+    if (dl == 1) return __dadd_rn(fabs(q.p2c), q.awx1);
     return __dadd_rn(k.p[PB + 3], k.p[PB + 4]);
   }
 };

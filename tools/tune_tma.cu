@@ -170,13 +170,11 @@ int main(int argc, char** argv) {
   P.only = argc > 4 ? argv[4] : nullptr;
   printf("N=%d reps=%d\n", N, reps);
   unsigned long long ref[3] = {0, 0, 0};
-#define V(R, MINB, U, TY, SEQ) run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ, reps, ref)
-  V(8, 2, 1, 16, false);
-  V(8, 2, 1, 16, true);
-  V(6, 3, 1, 16, true);
-  V(6, 3, 1, 16, false);
-  V(8, 3, 1, 12, true);
-  V(6, 5, 1, 8, true);
-  V(8, 4, 1, 8, true);
+#define V(R, MINB, U, TY, SEQ, OPT) \
+  run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ, OPT>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ "_opt" #OPT, reps, ref)
+  V(8, 2, 1, 16, false, 7);
+  V(8, 2, 1, 16, false, 135);
+  V(8, 2, 1, 16, false, 128);
+  V(8, 2, 1, 16, false, 143);
   return 0;
 }

@@ -167,6 +167,13 @@ int hj_step_reductions(hj_ctx* ctx, void* stream, double* reduce_host);
  * hj_step == hj_stage(1); hj_stage(2); hj_stage(3) on a single device.                                  */
 int hj_stage(hj_ctx* ctx, void* stream, int stage, double t, double dt, const double* params, int comp,
              int use_obstacle, int want_reduce);
+/* Product systems on the dimension-split path: a stage is two kernels.  Pass 1 (trailing dim block)
+ * reads no dim-0 halo plane, so a slab job posts its halo exchange, runs pass 1 under it, and runs pass 2 (leading
+ * dim block + stage algebra) once the halos have landed.  hj_stage == hj_stage_pass(1); hj_stage_pass(2).
+ * hj_is_split: 1 if this context (system and state set) advances its system that way, else 0.                 */
+int hj_stage_pass(hj_ctx* ctx, void* stream, int stage, int which_pass, double t, double dt, const double* params,
+                  int comp, int use_obstacle, int want_reduce);
+int hj_is_split(const hj_ctx* ctx);
 /* Which internal buffer (0..2) stage `stage` reads with its stencil (needs valid halos) / writes. */
 int hj_stage_io(const hj_ctx* ctx, int stage, int* in_buffer, int* out_buffer);
 /* intended-WENO only: per-dim max(D1^2) prepass of buffer `buf` into the context's eps record

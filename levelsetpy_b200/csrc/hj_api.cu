@@ -495,7 +495,8 @@ static bool use_tma(hj_ctx* c) {
 // stage 1..3: the TVD-RK3 stages (ode_cfl_3.py:151,184-193,226-241); stage 4: the final stage of the RK2 scheme
 // (ode_cfl_2.py: y = 0.5 (y + (y1 + dt f(y1)))), which is the stage-3 kernel reading buffer 1
 static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
-                      int want_reduce, bool run_prepass, bool batch = false, int zbeg = 0, int zend = 0) {
+                      int want_reduce, bool run_prepass, bool batch = false, int zbeg = 0, int zend = 0,
+                      int which_pass = 0) {
   static const int in_[5] = {0, 0, 1, 2, 1}, out_[5] = {0, 1, 2, 0, 0};
   const bool final_stage = stage >= 3;
   const int slot = stage == 4 ? 1 : stage - 1;   // reduction record / batch parameter set of this stage
@@ -529,13 +530,15 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
   if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX)
     if (!st.aux) return fail(HJ_ERR_STATE, "Need to define target function l(x)!");   // hji_solver.py:584
   if (st.use_obs && !st.obs) return fail(HJ_ERR_STATE, "obstacle field not uploaded");
-  if (want_reduce) CK(hj_launch_init_reduce(st.red, c->D, s));
-  if (c->weno == HJ_WENO_INTENDED && run_prepass) {
+  if (which_pass && !(use_tma(c) && hj_tma_plan_is_split(c->plan)))
+    return fail(HJ_ERR_UNSUPPORTED, "hj_stage_pass: this context does not advance a product system on the dimension-split path");
+  if (want_reduce && which_pass != 2) CK(hj_launch_init_reduce(st.red, c->D, s));
+  if (c->weno == HJ_WENO_INTENDED && run_prepass && which_pass != 2) {
     CK(hj_launch_init_eps(c->eps, c->D, s));
     CK(hj_launch_maxd1sq(c->gp, st.in, c->eps, -1, s));
   }
   if (use_tma(c)) {
-    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s, zbeg, zend));
+    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s, zbeg, zend, which_pass));
   } else if (c->nbatch) {
     return fail(HJ_ERR_UNSUPPORTED, "batch contexts run on the TMA backend only: %s", c->plan_err.c_str());
   } else {
@@ -557,6 +560,27 @@ int hj_stage(hj_ctx* c, void* stream, int stage, double t, double dt, const doub
   CK(cudaSetDevice(c->device));
   // on a slab the caller runs hj_eps_prepass + allreduce itself before each stage
   return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0);
+}
+
+int hj_is_split(const hj_ctx* c) {
+  if (!c) return 0;
+  hj_ctx* m = const_cast<hj_ctx*>(c);
+  if (m->system_id == HJ_SYS_NONE || !m->buf[0]) return 0;
+  return use_tma(m) && hj_tma_plan_is_split(m->plan) ? 1 : 0;
+}
+
+int hj_stage_pass(hj_ctx* c, void* stream, int stage, int which_pass, double t, double dt, const double* params,
+                  int comp, int use_obstacle, int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_stage_pass: use hj_step_batch on a batch context");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage_pass: no resident state (hj_upload first)");
+  if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage_pass: stage must be 1..3");
+  if (which_pass < 1 || which_pass > 2) return fail(HJ_ERR_INVALID, "hj_stage_pass: pass must be 1 or 2");
+  CK(cudaSetDevice(c->device));
+  return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0, false, 0, 0,
+                    which_pass);
 }
 
 int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,

@@ -32,7 +32,8 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g_pitched, int system_id, int weno, d
                               char* err, int errlen, int tile_y = 0);
 void hj_tma_plan_destroy(HjTmaPlan* p);
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
-                                const KStage& st, int in_buf, cudaStream_t s, int zbeg = 0, int zend = 0);
+                                const KStage& st, int in_buf, cudaStream_t s, int zbeg = 0, int zend = 0,
+                                int which_pass = 0);
 bool hj_tma_plan_is_split(const HjTmaPlan* p);
 
 void hj_count_launch(int n);

@@ -95,6 +95,7 @@ struct TmaLauncher {
   const KSys& ks;
   const KStage& st;
   cudaStream_t s;
+  int which_pass = 0;            // product systems: 0 = both passes, 1 = pass 1 only, 2 = pass 2 only
   cudaError_t err = cudaSuccess;
   int launches = 0;
   // whole system: one fused kernel per stage
@@ -120,9 +121,13 @@ struct TmaLauncher {
     s1.use_obs = 0;
     s1.restrict_sign = 0;         // termRestrictUpdate acts on the total ydot, in pass 2
     s1.out = const_cast<double*>(st.tmp);
-    cudaError_t e = launch_one<typename Sys::Second, Sys::ND, WENO, RED, 0, P1>(p, p->tmap[in_buf], g, ks, s1, s);
-    if (e != cudaSuccess) return e;
-    launches = 2;
+    if (which_pass != 2) {
+      cudaError_t e = launch_one<typename Sys::Second, Sys::ND, WENO, RED, 0, P1>(p, p->tmap[in_buf], g, ks, s1, s);
+      if (e != cudaSuccess) return e;
+      ++launches;
+      if (which_pass == 1) return cudaSuccess;
+    }
+    ++launches;
     const CUtensorMap& vm = p->vmap[in_buf];
     switch (st.stage) {
       case 1: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 1, P2>(p, vm, g, ks, st, s);
@@ -280,7 +285,7 @@ void hj_tma_plan_destroy(HjTmaPlan* p) { delete p; }
 bool hj_tma_plan_is_split(const HjTmaPlan* p) { return p && p->split; }
 
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
-                                const KStage& st, int in_buf, cudaStream_t s, int zbeg, int zend) {
+                                const KStage& st, int in_buf, cudaStream_t s, int zbeg, int zend, int which_pass) {
   HjTmaPlan sub;
   if (zend > zbeg) {               // advance only planes [zbeg, zend) of Z (pipelined host <-> device stepping)
     if (plan->split) return cudaErrorNotSupported;
@@ -292,6 +297,10 @@ cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const 
     plan = &sub;
   }
   TmaLauncher l{plan, in_buf, weno, g, ks, st, s};
+  if (which_pass) {
+    if (!plan->split) return cudaErrorNotSupported;
+    l.which_pass = which_pass;
+  }
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
   hj_count_launch(l.launches);
   return l.err;

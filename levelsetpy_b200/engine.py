@@ -259,14 +259,24 @@ class Engine:
         L.check(self.lib.hj_step(self.h, self.stream(), float(t), float(dt), p, int(comp), int(bool(use_obstacle)),
                                  int(bool(want_reduce))))
 
-    def stage(self, stage, t, dt, params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False):
+    def stage(self, stage, t, dt, params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False, which_pass=0):
+        """One RK stage.  which_pass = 1 / 2: only the first / second kernel of a product system's stage on the
+        dimension-split path (pass 1 reads no dim-0 halo: a slab job runs it under its halo exchange)."""
         p = None
         if params is not None:
             sp = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
             p = sp.ctypes.data
             self._sp_keep = sp
-        L.check(self.lib.hj_stage(self.h, self.stream(), int(stage), float(t), float(dt), p, int(comp),
-                                  int(bool(use_obstacle)), int(bool(want_reduce))))
+        if which_pass:
+            L.check(self.lib.hj_stage_pass(self.h, self.stream(), int(stage), int(which_pass), float(t), float(dt), p,
+                                           int(comp), int(bool(use_obstacle)), int(bool(want_reduce))))
+        else:
+            L.check(self.lib.hj_stage(self.h, self.stream(), int(stage), float(t), float(dt), p, int(comp),
+                                      int(bool(use_obstacle)), int(bool(want_reduce))))
+
+    def is_split(self):
+        """True if this context advances its (product) system as two kernels per stage (system and state set)."""
+        return bool(self.lib.hj_is_split(self.h))
 
     def set_restrict(self, sign):
         """termRestrictUpdate: +1 -> ydot = max(ydot, 0); -1 -> min(ydot, 0); 0 -> off."""

@@ -50,15 +50,23 @@ class DistComm:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
-    def exchange(self, sends, recvs):
-        """sends/recvs: lists of (tensor, peer, tag).  Posted as one batch; returns after local completion is
-        ordered on the current stream (NCCL) / finished (gloo)."""
+    def post(self, sends, recvs):
+        """sends/recvs: lists of (tensor, peer, tag), posted as one batch.  Returns the requests: work launched on
+        the current stream afterwards runs under the transfer until ``wait`` orders the stream behind it."""
         dist = self.dist
         ops = [dist.P2POp(dist.irecv, t, p, self.group, tag) for t, p, tag in recvs]
         ops += [dist.P2POp(dist.isend, t, p, self.group, tag) for t, p, tag in sends]
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def wait(reqs):
+        for req in reqs:
+            req.wait()
+
+    def exchange(self, sends, recvs):
+        """Posted as one batch; returns after local completion is ordered on the current stream (NCCL) /
+        finished (gloo)."""
+        self.wait(self.post(sends, recvs))
 
     def allreduce_max(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
@@ -99,6 +107,7 @@ class SlabSolver:
         self.plane = self.eng.plane_elems
         self.bufs = [self.eng.buffer_tensor(b) for b in range(3)]
         self._alpha = None
+        self._overlap = None
         self._tables = list(enumerate(self.adapter.tables(g)))
         self.shape = (self.n0,) + tuple(int(x) for x in np.asarray(g.N).reshape(-1)[1:])
 
@@ -199,21 +208,41 @@ class SlabSolver:
         self._step = (t, dt, blocks)
         return dt
 
-    def run_stage(self, stage, comp=L.COMP_NONE, use_obstacle=False):
-        """Stage kernel on this slab; the halos of the buffer it reads must already be current."""
+    def run_stage(self, stage, comp=L.COMP_NONE, use_obstacle=False, which_pass=0):
+        """Stage kernel(s) on this slab; the halos of the buffer it reads must already be current (pass 1 of a
+        product system's stage reads none)."""
         t, dt, blocks = self._step
-        if self.weno == "intended":
+        if self.weno == "intended" and which_pass != 2:
             eps = self.eng.eps_prepass(self.eng.stage_io(stage)[0])
             if self.world > 1:
                 self.comm.allreduce_max(eps)
-        self.eng.stage(stage, t, dt, blocks[stage - 1], comp, use_obstacle)
+        kw = {"which_pass": which_pass} if which_pass else {}
+        self.eng.stage(stage, t, dt, blocks[stage - 1], comp, use_obstacle, **kw)
+
+    def overlapped(self):
+        """Product systems on the dimension-split path under as_shipped WENO: the halo exchange of a stage runs
+        under its first kernel.  ('intended' needs the halos for the WENO eps pre-pass, so it exchanges first.)"""
+        return self.two_pass() and hasattr(self.comm, "post")
+
+    def two_pass(self):
+        if self._overlap is None:
+            self._overlap = bool(self.weno != "intended" and getattr(self.eng, "is_split", lambda: False)())
+        return self._overlap
 
     def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
         """One CFL-limited TVD-RK3 step of the distributed field.  Returns (t_new, dt)."""
         dt = self.begin_step(t, t_end, factorCFL, maxStep)
         for stage in (1, 2, 3):
-            self.exchange(self.eng.stage_io(stage)[0])
-            self.run_stage(stage, comp, use_obstacle)
+            b = self.eng.stage_io(stage)[0]
+            if self.overlapped():
+                reqs = self.comm.post(*self.halo_ops(b))
+                self.run_stage(stage, comp, use_obstacle, which_pass=1)
+                self.comm.wait(reqs)
+                self.finish_halos(b)
+                self.run_stage(stage, comp, use_obstacle, which_pass=2)
+            else:
+                self.exchange(b)
+                self.run_stage(stage, comp, use_obstacle)
         return rk3_times(t, dt)[2], dt
 
 
@@ -221,6 +250,8 @@ class LocalWorld:
     """``world`` slabs driven in lock-step inside ONE process (all on one device): exercises exactly the halo,
     edge-fill and reduction code of the multi-process path, with tensor copies standing in for send/recv and an
     element-wise maximum over the slabs standing in for the max-allreduce."""
+
+    poison_halos = False     # tests: NaN the halo planes a stage will receive before its pass 1 runs
 
     def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None):
         self.world = int(world)
@@ -256,12 +287,22 @@ class LocalWorld:
                 s._alpha = [float(x) for x in amax]
         dts = [s.begin_step(t, t_end, factorCFL, maxStep) for s in self.slabs]
         assert all(d == dts[0] for d in dts), "dt must be identical on every rank"
+        two = self.slabs[0].two_pass()        # product systems: pass 1 runs before the halos arrive (as under NCCL)
         for stage in (1, 2, 3):
             b = self.slabs[0].eng.stage_io(stage)[0]
+            if two:
+                for s in self.slabs:
+                    if self.poison_halos:
+                        _, _, rlo, rhi = s._faces(b)
+                        rlo.fill_(float("nan"))
+                        rhi.fill_(float("nan"))
+                    t_, dt_, blocks = s._step
+                    s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, which_pass=1)
             self._exchange(b)
             if self.slabs[0].weno == "intended":
                 self._max_over([s.eng.eps_prepass(b) for s in self.slabs])
             for s in self.slabs:
                 t_, dt_, blocks = s._step
-                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                kw = {"which_pass": 2} if two else {}
+                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, **kw)
         return rk3_times(t, dts[0])[2], dts[0]

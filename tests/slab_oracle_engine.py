@@ -123,6 +123,30 @@ class OracleSlabEngine:
         self._interior(self._buf[o])[...] = out
 
 
+class TwoPassOracleSlabEngine(OracleSlabEngine):
+    """Stands in for a product-system context on the dimension-split path: a stage is two calls.  Pass 1 must not
+    depend on the dim-0 halo planes (it poisons them to prove it), pass 2 evaluates the stage and therefore needs
+    the halos the exchange posted BEFORE pass 1 has delivered by then."""
+
+    def is_split(self):
+        return True
+
+    def stage(self, stage, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=False, which_pass=0):
+        if which_pass == 1:
+            self.log.append(("pass1", stage))
+            return
+        if which_pass == 2:
+            assert self.log and self.log[-1] == ("pass1", stage), "pass 2 without its pass 1"
+        self.log.append(("pass2" if which_pass else "both", stage))
+        OracleSlabEngine.stage(self, stage, t, dt, params, comp, use_obstacle, want_reduce)
+
+    log = None
+
+    def __init__(self, *a, **k):
+        OracleSlabEngine.__init__(self, *a, **k)
+        self.log = []
+
+
 def _extrap(*a, **k):
     raise RuntimeError("token only")
 

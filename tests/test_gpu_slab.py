@@ -100,9 +100,47 @@ def test_slabs_6d_pair_split_path(lsp):
     want = yo.reshape(g.shape)
     for be in (L.BACKEND_GATHER, L.BACKEND_TMA):
         w = LocalWorld(sd, 2, backend=be)
+        w.poison_halos = True        # pass 1 (hj_stage_pass) runs on NaN halos: it must not read them
         w.upload(d0)
         t = 0.0
         for _ in range(2):
             t, dt = w.step(t, 1.0, 0.8, comp=L.COMP_MIN_OVER_TIME)
+        assert w.slabs[0].two_pass() == (be == L.BACKEND_TMA)   # the two-kernel protocol is what ran on the TMA backend
         assert t == to
         assert np.max(np.abs(w.download() - want)) <= 1e-9 * (want.max() - want.min())
+
+
+def test_stage_pass_equals_stage(lsp):
+    """hj_stage == hj_stage_pass(1); hj_stage_pass(2), bit for bit, on a product system; other contexts refuse."""
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.term import prepare_scheme
+    g = lsp.createGrid(-np.ones(4), np.ones(4), np.array([12, 9, 18, 34]))
+    x = np.meshgrid(*[np.asarray(v).reshape(-1) for v in g.vs], indexing="ij")
+    d0 = np.sqrt((x[0] - x[2]) ** 2 + (x[1] - x[3]) ** 2) - 0.2 + 0.1 * np.sin(3 * x[1] + x[3])
+    s = lsp.ProductSystem(g, [lsp.DoubleIntegrator(g, 1.0), lsp.DoubleIntegrator(g, 0.6)])
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+    outs = []
+    for two in (False, True):
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(L.BACKEND_TMA)
+        eng.upload(d0)
+        eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g))))
+        assert eng.is_split()
+        for stage in (1, 2, 3):
+            if two:
+                eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, which_pass=1)
+                eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, which_pass=2)
+            else:
+                eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME)
+        outs.append(eng.download(shape=g.shape))
+    assert np.array_equal(outs[0], outs[1])
+    g3, d3 = _grid3(lsp, [26, 37, 34], [2])
+    s3 = lsp.DubinsVehicleRel(g3, 5, 1)
+    eng, ad = prepare_scheme(lsp.Bundle(dict(grid=g3, hamFunc=s3.hamiltonian, partialFunc=s3.dissipation,
+                                             dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a)))
+    eng.upload(d3)
+    eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g3))))
+    assert not eng.is_split()
+    with pytest.raises(Exception):
+        eng.stage(1, 0.0, 1e-3, None, which_pass=1)

@@ -55,31 +55,36 @@ def _oracle(g, d0, nsteps, comp):
     return ts, y.reshape(g.shape)
 
 
-def _worker(rank, world, port, periodic0, q):
+def _worker(rank, world, port, periodic0, q, two_pass=False):
     import torch.distributed as dist
-    from slab_oracle_engine import OracleSlabEngine
+    from slab_oracle_engine import OracleSlabEngine, TwoPassOracleSlabEngine
     from levelsetpy_b200.slab import SlabSolver
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
         lsp, g, d0, sd = _case(periodic0)
-        sol = SlabSolver(sd, device=0, engine_factory=OracleSlabEngine)
+        sol = SlabSolver(sd, device=0, engine_factory=TwoPassOracleSlabEngine if two_pass else OracleSlabEngine)
         sol.upload(d0[sol.lo:sol.hi])
         t, ts = 0.0, []
         for _ in range(2):
             t, dt = sol.step(t, 1.0, 0.8, comp=1)
             ts.append(t)
+        if two_pass:      # the exchange of every stage was posted before pass 1 and awaited before pass 2
+            assert sol.overlapped()
+            assert sol.eng.log == [(p, s) for _ in range(2) for s in (1, 2, 3) for p in ("pass1", "pass2")]
         q.put((rank, sol.lo, sol.hi, ts, sol.download()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,periodic0", [(2, False), (2, True), (3, False)])
-def test_slab_solver_over_gloo_matches_single_domain_oracle(world, periodic0):
+@pytest.mark.parametrize("world,periodic0,two_pass", [(2, False, False), (2, True, False), (3, False, False),
+                                                      (2, False, True), (2, True, True)])
+def test_slab_solver_over_gloo_matches_single_domain_oracle(world, periodic0, two_pass):
+    """two_pass: the overlapped protocol of product systems (halo exchange posted, pass 1, wait, pass 2)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, periodic0, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, periodic0, q, two_pass)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)])

@@ -248,7 +248,7 @@ def run_ours(args):
     backend = {"auto": L.BACKEND_AUTO, "gather": L.BACKEND_GATHER, "tma": L.BACKEND_TMA}[args.backend]
 
     scaling = "weak"
-    slab0 = None
+    slab0 = data0 = None
     if world > 1 and args.workload in ("dint4d", "dubins6d"):
         # configs[2] / [3]: the FIXED product grid slab-decomposed along dim 0 (strong scaling), state made on the device
         import torch.distributed as dist

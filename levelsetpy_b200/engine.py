@@ -202,8 +202,14 @@ class Engine:
         L.check(self.lib.hj_upload(self.h, self.stream(), field, ptr, is_host))
         self._keep = flat
 
-    def download(self, like=None, field=L.FIELD_STATE, shape=None):
+    def download(self, like=None, field=L.FIELD_STATE, shape=None, out=None):
+        """The dense field; ``out``: a C-contiguous float64 numpy array (e.g. pinned) that receives it in place."""
         shape = (self.nodes, 1) if shape is None else shape
+        if out is not None:
+            o = np.asarray(out)
+            assert o.dtype == np.float64 and o.flags.c_contiguous and o.size == self.nodes
+            L.check(self.lib.hj_download(self.h, self.stream(), field, o.ctypes.data, 1))
+            return o.reshape(shape)
         if is_torch_tensor(like):
             t = _torch()
             out = t.empty(self.nodes, dtype=t.float64, device=like.device)

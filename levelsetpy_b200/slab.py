@@ -117,11 +117,14 @@ class SlabSolver:
         self.eng.upload(slab, field)
 
     def download(self, out=None):
-        y = self.eng.download(shape=self.shape)
         if out is not None:
-            np.copyto(np.asarray(out).reshape(self.shape), y)
+            o = np.asarray(out)
+            if o.dtype == np.float64 and o.flags.c_contiguous and hasattr(self.eng, "lib"):
+                self.eng.download(shape=self.shape, out=o)      # straight into the caller's (pinned) buffer
+            else:
+                np.copyto(o.reshape(self.shape), self.eng.download(shape=self.shape))
             return out
-        return y
+        return self.eng.download(shape=self.shape)
 
     # ------------------------------------------------------------------ halos
     def _faces(self, b):

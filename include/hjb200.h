@@ -174,6 +174,13 @@ int hj_stage(hj_ctx* ctx, void* stream, int stage, double t, double dt, const do
 int hj_stage_pass(hj_ctx* ctx, void* stream, int stage, int which_pass, double t, double dt, const double* params,
                   int comp, int use_obstacle, int want_reduce);
 int hj_is_split(const hj_ctx* ctx);
+/* Whole (non-product) systems on the plane-ring backend: run stage `stage` on planes [z_begin, z_end) of the marched
+ * dim D-3 only (dim 0 of a 3-D grid, i.e. the slab dim).  A slab job posts its halo exchange, advances the planes
+ * whose stencil stays inside the slab ([3, N0-3)) under it, and advances the two 3-plane edge ranges once the halos
+ * have landed.  The union of disjoint ranges covering [0, N[D-3]) equals hj_stage bit for bit.  as_shipped WENO only.
+ * want_reduce: 0 none, 1 reset the stage's reduction record then accumulate, 2 accumulate into it.             */
+int hj_stage_range(hj_ctx* ctx, void* stream, int stage, int64_t z_begin, int64_t z_end, double t, double dt,
+                   const double* params, int comp, int use_obstacle, int want_reduce);
 /* Which internal buffer (0..2) stage `stage` reads with its stencil (needs valid halos) / writes. */
 int hj_stage_io(const hj_ctx* ctx, int stage, int* in_buffer, int* out_buffer);
 /* intended-WENO only: per-dim max(D1^2) prepass of buffer `buf` into the context's eps record

@@ -47,6 +47,7 @@ SIGNATURES = {
     "hj_stage": (_i, [_vp, _vp, _i, _d, _d, _vp, _i, _i, _i]),
     "hj_stage_pass": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _i, _i, _i]),
     "hj_is_split": (_i, [_vp]),
+    "hj_stage_range": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _i, _i, _i]),
     "hj_stage_io": (_i, [_vp, _i, _pi, _pi]),
     "hj_eps_prepass": (_i, [_vp, _vp, _i, C.POINTER(_vp)]),
     "hj_fill_edge_halo": (_i, [_vp, _vp, _i, _i]),

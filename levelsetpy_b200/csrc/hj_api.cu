@@ -532,7 +532,7 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
   if (st.use_obs && !st.obs) return fail(HJ_ERR_STATE, "obstacle field not uploaded");
   if (which_pass && !(use_tma(c) && hj_tma_plan_is_split(c->plan)))
     return fail(HJ_ERR_UNSUPPORTED, "hj_stage_pass: this context does not advance a product system on the dimension-split path");
-  if (want_reduce && which_pass != 2) CK(hj_launch_init_reduce(st.red, c->D, s));
+  if (want_reduce == 1 && which_pass != 2) CK(hj_launch_init_reduce(st.red, c->D, s));   // 2: accumulate only
   if (c->weno == HJ_WENO_INTENDED && run_prepass && which_pass != 2) {
     CK(hj_launch_init_eps(c->eps, c->D, s));
     CK(hj_launch_maxd1sq(c->gp, st.in, c->eps, -1, s));
@@ -560,6 +560,25 @@ int hj_stage(hj_ctx* c, void* stream, int stage, double t, double dt, const doub
   CK(cudaSetDevice(c->device));
   // on a slab the caller runs hj_eps_prepass + allreduce itself before each stage
   return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0);
+}
+
+int hj_stage_range(hj_ctx* c, void* stream, int stage, int64_t z_begin, int64_t z_end, double t, double dt,
+                   const double* params, int comp, int use_obstacle, int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_stage_range: use hj_step_batch on a batch context");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage_range: no resident state (hj_upload first)");
+  if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage_range: stage must be 1..3");
+  if (c->D < 3) return fail(HJ_ERR_UNSUPPORTED, "hj_stage_range: needs a grid of >= 3 dims");
+  if (c->weno == HJ_WENO_INTENDED) return fail(HJ_ERR_UNSUPPORTED, "hj_stage_range: the intended-WENO eps pre-pass needs the whole field");
+  CK(cudaSetDevice(c->device));
+  if (!use_tma(c) || hj_tma_plan_is_split(c->plan))
+    return fail(HJ_ERR_UNSUPPORTED, "hj_stage_range: whole-system plane-ring (TMA) contexts only");
+  const int64_t NZ = c->gp.N[c->D - 3];
+  if (z_begin < 0 || z_end > NZ || z_begin >= z_end) return fail(HJ_ERR_INVALID, "hj_stage_range: need 0 <= z_begin < z_end <= N[D-3]");
+  return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, false, false, (int)z_begin,
+                    (int)z_end);
 }
 
 int hj_is_split(const hj_ctx* c) {

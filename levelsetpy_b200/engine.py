@@ -280,6 +280,22 @@ class Engine:
             L.check(self.lib.hj_stage(self.h, self.stream(), int(stage), float(t), float(dt), p, int(comp),
                                       int(bool(use_obstacle)), int(bool(want_reduce))))
 
+    def stage_range(self, stage, z_begin, z_end, t, dt, params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=0):
+        """Stage ``stage`` on planes [z_begin, z_end) of the marched dim only (whole systems, plane-ring backend)."""
+        p = None
+        if params is not None:
+            sp = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+            p = sp.ctypes.data
+            self._sp_keep = sp
+        L.check(self.lib.hj_stage_range(self.h, self.stream(), int(stage), int(z_begin), int(z_end), float(t), float(dt),
+                                        p, int(comp), int(bool(use_obstacle)), int(want_reduce)))
+
+    def supports_range(self):
+        """True if hj_stage_range can advance this context (probed with an empty-range call that must fail as INVALID,
+        not as UNSUPPORTED)."""
+        rc = self.lib.hj_stage_range(self.h, self.stream(), 1, 0, 0, 0.0, 0.0, None, 0, 0, 0)
+        return rc == L.HJ_ERR_INVALID
+
     def is_split(self):
         """True if this context advances its (product) system as two kernels per stage (system and state set)."""
         return bool(self.lib.hj_is_split(self.h))

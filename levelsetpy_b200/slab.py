@@ -108,6 +108,7 @@ class SlabSolver:
         self.bufs = [self.eng.buffer_tensor(b) for b in range(3)]
         self._alpha = None
         self._overlap = None
+        self._ranged = None
         self._tables = list(enumerate(self.adapter.tables(g)))
         self.shape = (self.n0,) + tuple(int(x) for x in np.asarray(g.N).reshape(-1)[1:])
 
@@ -227,6 +228,14 @@ class SlabSolver:
         under its first kernel.  ('intended' needs the halos for the WENO eps pre-pass, so it exchanges first.)"""
         return self.two_pass() and hasattr(self.comm, "post")
 
+    def ranged(self):
+        """Whole 3-D systems on the plane-ring backend under as_shipped WENO: the planes whose dim-0 stencil stays
+        inside the slab are advanced under the halo exchange, the two 3-plane edge ranges after it (hj_stage_range)."""
+        if self._ranged is None:
+            self._ranged = bool(self.weno != "intended" and self.eng.D == 3 and self.n0 > 2 * GHOST
+                                and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
+        return self._ranged
+
     def two_pass(self):
         if self._overlap is None:
             self._overlap = bool(self.weno != "intended" and getattr(self.eng, "is_split", lambda: False)())
@@ -243,6 +252,14 @@ class SlabSolver:
                 self.comm.wait(reqs)
                 self.finish_halos(b)
                 self.run_stage(stage, comp, use_obstacle, which_pass=2)
+            elif self.ranged() and hasattr(self.comm, "post"):
+                t_, dt_, blocks = self._step
+                reqs = self.comm.post(*self.halo_ops(b))
+                self.eng.stage_range(stage, GHOST, self.n0 - GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                self.comm.wait(reqs)
+                self.finish_halos(b)
+                self.eng.stage_range(stage, 0, GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                self.eng.stage_range(stage, self.n0 - GHOST, self.n0, t_, dt_, blocks[stage - 1], comp, use_obstacle)
             else:
                 self.exchange(b)
                 self.run_stage(stage, comp, use_obstacle)
@@ -291,8 +308,23 @@ class LocalWorld:
         dts = [s.begin_step(t, t_end, factorCFL, maxStep) for s in self.slabs]
         assert all(d == dts[0] for d in dts), "dt must be identical on every rank"
         two = self.slabs[0].two_pass()        # product systems: pass 1 runs before the halos arrive (as under NCCL)
+        ranged = all(s.ranged() for s in self.slabs)   # whole 3-D systems: interior planes before, edge planes after
         for stage in (1, 2, 3):
             b = self.slabs[0].eng.stage_io(stage)[0]
+            if ranged:
+                for s in self.slabs:
+                    if self.poison_halos:
+                        _, _, rlo, rhi = s._faces(b)
+                        rlo.fill_(float("nan"))
+                        rhi.fill_(float("nan"))
+                    t_, dt_, blocks = s._step
+                    s.eng.stage_range(stage, GHOST, s.n0 - GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                self._exchange(b)
+                for s in self.slabs:
+                    t_, dt_, blocks = s._step
+                    s.eng.stage_range(stage, 0, GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                    s.eng.stage_range(stage, s.n0 - GHOST, s.n0, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                continue
             if two:
                 for s in self.slabs:
                     if self.poison_halos:

@@ -36,6 +36,7 @@ def test_slabs_match_single_domain(lsp, world, pd, weno, backend):
     osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
     be = L.BACKEND_GATHER if backend == "gather" else L.BACKEND_TMA
     w = LocalWorld(sd, world, backend=be)
+    w.poison_halos = True     # ranged mode (TMA, as_shipped): the interior range runs on NaN halos and must not read them
     w.upload(d0)
     t, to, yo = 0.0, 0.0, d0.reshape(-1, 1)
     for _ in range(2):
@@ -45,8 +46,44 @@ def test_slabs_match_single_domain(lsp, world, pd, weno, backend):
         yo = np.minimum(yo, y_last)
         assert t == to
     got, want = w.download(), yo.reshape(g.shape)
+    assert all(s.ranged() for s in w.slabs) == (backend == "tma" and weno == "as_shipped")
     assert np.max(np.abs(got - want)) <= 1e-9 * (want.max() - want.min())
     assert np.mean(np.sign(got) == np.sign(want)) >= 0.9999
+
+
+def test_stage_range_union_equals_stage(lsp):
+    """hj_stage_range over disjoint ranges covering the marched dim == hj_stage, bit for bit (incl. in-place stage 3
+    and the accumulate-only reduction mode); refused on gather / product / intended contexts."""
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.term import prepare_scheme
+    g, d0 = _grid3(lsp, [41, 37, 34], [2])
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+    outs, reds = [], []
+    for ranged in (False, True):
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(L.BACKEND_TMA)
+        eng.upload(d0)
+        eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g))))
+        for stage in (1, 2, 3):
+            if ranged:
+                assert eng.supports_range()
+                eng.stage_range(stage, 3, 38, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, False, 1)
+                eng.stage_range(stage, 0, 3, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, False, 2)
+                eng.stage_range(stage, 38, 41, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, False, 2)
+            else:
+                eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, want_reduce=True)
+        reds.append(eng.step_reductions())
+        outs.append(eng.download(shape=g.shape))
+    assert np.array_equal(outs[0], outs[1])
+    for a, b in zip(reds[0], reds[1]):
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    with pytest.raises(Exception):
+        eng.stage_range(1, 5, 5, 0.0, 1e-3)
+    eng.set_backend(L.BACKEND_GATHER)
+    assert not eng.supports_range()
 
 
 def test_slabs_4d_pair_with_obstacle(lsp):

@@ -3,7 +3,9 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "hj_internal.h"
 #include "hj_tma_kernel.cuh"
@@ -37,8 +39,23 @@ template <class Sys> struct SplitCfg;
 #endif
 #define HJ_P2_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, HJ_P2_TA, HJ_P2_TB>
 #define HJ_P1_6D TmaCfg<8, HJ_P1_MINB, 1, HJ_P1_TY, HJ_P1_TXP>
-template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; };
-template <> struct SplitCfg<SysDoubleIntPair> { using P1 = TmaCfg<8, 2, 1, 9, 27>;  using P2 = VecCfg<2, 8, 2, 16, 16, 1>; };
+// P2T: pass-2 tile for THIN dim-0 extents (slabs of a multi-GPU job: 41 planes over 8 ranks are 5..6 planes each, of
+// which a 4-row tile wastes a third); chosen per context by pick_thin() below
+#define HJ_P2T_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, 6, 5>
+template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; using P2T = HJ_P2T_6D; };
+template <> struct SplitCfg<SysDoubleIntPair> {
+  using P1 = TmaCfg<8, 2, 1, 9, 27>;
+  using P2 = VecCfg<2, 8, 2, 16, 16, 1>;
+  using P2T = P2;
+};
+// rows of dim 0 a tiling of height `ta` processes per useful row
+static double tile_waste(int n0, int ta) { return (double)((n0 + ta - 1) / ta * ta) / n0; }
+template <class P2, class P2T>
+static bool pick_thin(int n0) {
+  if (const char* e = getenv("HJ_P2_THIN")) return atoi(e) != 0;       // developer override
+  if (P2::TA == P2T::TA) return false;
+  return tile_waste(n0, P2T::TA) < 0.9 * tile_waste(n0, P2::TA);
+}
 
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -129,6 +146,15 @@ struct TmaLauncher {
     }
     ++launches;
     const CUtensorMap& vm = p->vmap[in_buf];
+    using P2T = typename SplitCfg<Sys>::P2T;
+    if constexpr (!std::is_same<P2, P2T>::value) {
+      if (p->thin) switch (st.stage) {
+        case 1: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 1, P2T>(p, vm, g, ks, st, s);
+        case 2: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 2, P2T>(p, vm, g, ks, st, s);
+        case 3: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 3, P2T>(p, vm, g, ks, st, s);
+        default: return cudaErrorNotSupported;
+      }
+    }
     switch (st.stage) {
       case 1: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 1, P2>(p, vm, g, ks, st, s);
       case 2: return launch_vec<typename Sys::First, Sys::ND, WENO, RED, 2, P2>(p, vm, g, ks, st, s);
@@ -154,16 +180,19 @@ struct TmaLauncher {
 // tile shapes of a system's kernels, for the plan
 struct PlanShape {
   int txp = ProdCfg::TXP, ty = ProdCfg::TY;
-  bool split = false;
+  bool split = false, thin = false;
+  int n0 = 0;
   int ns = 0, vb = 0, ta = 0, tb = 0;
   template <class Sys>
   void operator()() {
     if constexpr (SysSplit<Sys>::value) {
       using P1 = typename SplitCfg<Sys>::P1;
       using P2 = typename SplitCfg<Sys>::P2;
+      using P2T = typename SplitCfg<Sys>::P2T;
       txp = P1::TXP; ty = P1::TY;
       split = true;
-      ns = P2::NS; vb = P2::VB; ta = P2::TA; tb = P2::TB;
+      thin = pick_thin<P2, P2T>(n0);
+      ns = P2::NS; vb = P2::VB; ta = thin ? P2T::TA : P2::TA; tb = thin ? P2T::TB : P2::TB;
     }
   }
 };
@@ -173,6 +202,7 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   (void)weno;
   const int D = g.D;
   PlanShape shape;
+  shape.n0 = g.N[0];
   if (!hj_dispatch_system(system_id, shape)) { snprintf(err, errlen, "unknown system"); return nullptr; }
   const int TY = tile_y > 0 ? tile_y : shape.ty;
   const int TX = 2 * shape.txp;
@@ -230,6 +260,7 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
     }
   }
   p->split = shape.split;
+  p->thin = shape.thin;
   if (shape.split) {
     // pass 2: [V, (N2,) N1, N0 (+ halo planes)] with V = the flattened trailing dims; the block's last dim is marched
     // (box extent 1), the others are tiled with a 3-cell halo

@@ -14,6 +14,7 @@ struct HjTmaPlan {
   long long tiles;         // (X, Y, slow) tiles: nblocks = tiles * geo.nzc
   // dimension-split path (product systems): pass 2 tensor maps + geometry
   bool split = false;
+  bool thin = false;      // pass 2 runs the thin-slab tile (SplitCfg::P2T)
   CUtensorMap vmap[3];
   VecGeom vgeo;
   long long vblocks = 0;

@@ -49,7 +49,10 @@ typedef enum hj_bc { HJ_BC_EXTRAPOLATE = 0, HJ_BC_PERIODIC = 1, HJ_BC_HALO = 2 }
 /* SpatialDerivative/upwind_first_weno5a.py:13-196 semantics. */
 typedef enum hj_weno {
   HJ_WENO_AS_SHIPPED = 0, /* bug-compatible: aliasing at :97 => fixed-weight 5th-order upwind      */
-  HJ_WENO_INTENDED = 1    /* true WENO5 smoothness indicators + weights (ENO3bHelper.py:136-160)   */
+  HJ_WENO_INTENDED = 1,   /* true WENO5 smoothness indicators + weights (ENO3bHelper.py:136-160)   */
+  /* the other CoStateCalc functors of the reference, gather backend:                */
+  HJ_SCHEME_ENO3A = 2,    /* upwindFirstENO3a / upwindFirstENO3  SpatialDerivative/upwind_first_eno3a.py:87-142 */
+  HJ_SCHEME_ENO2 = 3      /* upwindFirstENO2                     SpatialDerivative/upwind_first_eno2.py:50-150  */
 } hj_weno;
 
 /* Compiled device functors for schemeData.hamFunc / schemeData.partialFunc.  Parameter blocks: see

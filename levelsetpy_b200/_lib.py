@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "_hjb200.so")
 HJ_MAX_DIM, HJ_MAX_PARAMS, HJ_MAX_TABLES, HJ_GHOST = 6, 96, 8, 3
 HJ_OK, HJ_ERR_INVALID, HJ_ERR_CUDA, HJ_ERR_UNSUPPORTED, HJ_ERR_STATE, HJ_ERR_NAN = 0, -1, -2, -3, -4, -5
 BC_EXTRAPOLATE, BC_PERIODIC, BC_HALO = 0, 1, 2
-WENO_AS_SHIPPED, WENO_INTENDED = 0, 1
+WENO_AS_SHIPPED, WENO_INTENDED, SCHEME_ENO3A, SCHEME_ENO2 = 0, 1, 2, 3
 SYS_DUBINS_REL, SYS_DOUBLE_INT, SYS_FLOCK, SYS_DUBINS_REL_PAIR, SYS_DOUBLE_INT_PAIR = 1, 2, 3, 4, 5
 COMP_NONE, COMP_MIN_OVER_TIME, COMP_MAX_OVER_TIME, COMP_MIN_WITH_AUX, COMP_MAX_WITH_AUX = 0, 1, 2, 3, 4
 FIELD_STATE, FIELD_AUX, FIELD_OBSTACLE = 0, 1, 2

@@ -79,7 +79,7 @@ int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double
               const int* bc_toward_zero, int weno_mode) {
   if (!out || !N || !dx || !bc_kind) return fail(HJ_ERR_INVALID, "hj_create: null argument");
   if (ndim < 2 || ndim > HJ_MAX_DIM) return fail(HJ_ERR_UNSUPPORTED, "hj_create: grid.dim must be 2..%d, got %d", HJ_MAX_DIM, ndim);
-  if (weno_mode != HJ_WENO_AS_SHIPPED && weno_mode != HJ_WENO_INTENDED) return fail(HJ_ERR_INVALID, "hj_create: bad weno_mode");
+  if (weno_mode < HJ_WENO_AS_SHIPPED || weno_mode > HJ_SCHEME_ENO2) return fail(HJ_ERR_INVALID, "hj_create: bad weno_mode");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(HJ_ERR_CUDA, "hj_create: no CUDA device (this library has no CPU fallback)");
@@ -483,6 +483,10 @@ int hj_device_count(void) {
 
 static bool use_tma(hj_ctx* c) {
   if (c->backend == HJ_BACKEND_GATHER) return false;
+  if (c->weno == HJ_SCHEME_ENO3A || c->weno == HJ_SCHEME_ENO2) {      // the ENO functors run on the gather backend
+    c->plan_err = "upwindFirstENO2 / upwindFirstENO3a are compiled for the gather backend only";
+    return false;
+  }
   if (!c->plan_tried) {
     c->plan_tried = true;
     char err[256] = {0};

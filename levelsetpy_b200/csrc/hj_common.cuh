@@ -169,10 +169,66 @@ HJ_DEV void upwind5_weno(const double v[7], double dxinv, double inv_eps, double
   R = weno_combine(c1, c2, c3, sr0, sr1, sr2, 0.3, 0.6, 0.1, inv_eps);
 }
 
+// ENO divided differences around node i from v[0..6] = phi[i-3..i+3], with the reference's operation order
+// (ENO3aHelper.py:76-88: scalar products first) and un-fused arithmetic, so that the tables -- hence the
+// minimum-modulus choices, which are discontinuous in them -- are bit-identical to numpy's:
+//   a[k] = dxInv (v[k+1]-v[k])                 a[2] = D1[i], a[3] = D1[i+1]
+//   b[k] = (0.5 dxInv)(a[k+1]-a[k])            b[1], b[2], b[3] = D2[i], D2[i+1], D2[i+2]  (centred at i-1, i, i+1)
+//   c[k] = ((1/3) dxInv)(b[k+1]-b[k])          c[0..3] = D3[i..i+3]                         (centred at i-3/2 ..)
+struct EnoTables { double a[6], b[5], c[4]; };
+HJ_DEV void eno_tables(const double v[7], double dxinv, EnoTables& T, bool third) {
+  const double h2 = __dmul_rn(0.5, dxinv), h3 = __dmul_rn(1.0 / 3.0, dxinv);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) T.a[k] = __dmul_rn(dxinv, __dsub_rn(v[k + 1], v[k]));
+#pragma unroll
+  for (int k = 0; k < 5; ++k) T.b[k] = __dmul_rn(h2, __dsub_rn(T.a[k + 1], T.a[k]));
+  if (third) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) T.c[k] = __dmul_rn(h3, __dsub_rn(T.b[k + 1], T.b[k]));
+  }
+}
+
+// upwindFirstENO3a (upwind_first_eno3a.py:87-142): candidates of ENO3aHelper.py:116-189, the one built on the
+// minimum-modulus D2 and then D3 neighbours is taken (:104-140).
+HJ_DEV void upwind_eno3a(const double v[7], double dx, double dxinv, double& L, double& R) {
+  EnoTables T;
+  eno_tables(v, dxinv, T, true);
+  const double dx2 = __dmul_rn(dx, dx), cLL = __dmul_rn(2.0, dx2), cLR = -dx2;
+  const double l01 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[1])), l2 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[2]));
+  const double r01 = __dadd_rn(T.a[3], __dmul_rn(-dx, T.b[2])), r2 = __dadd_rn(T.a[3], __dmul_rn(-dx, T.b[3]));
+  const double dL0 = __dadd_rn(l01, __dmul_rn(cLL, T.c[0])), dL1 = __dadd_rn(l01, __dmul_rn(cLL, T.c[1])),
+               dL2 = __dadd_rn(l2, __dmul_rn(cLR, T.c[2]));
+  const double dR0 = __dadd_rn(r01, __dmul_rn(cLR, T.c[1])), dR1 = __dadd_rn(r01, __dmul_rn(cLR, T.c[2])),
+               dR2 = __dadd_rn(r2, __dmul_rn(cLL, T.c[3]));
+  const bool t0 = fabs(T.c[0]) < fabs(T.c[1]), t1 = fabs(T.c[1]) < fabs(T.c[2]), t2 = fabs(T.c[2]) < fabs(T.c[3]);
+  {  // left: index i of the masks
+    const bool sL = fabs(T.b[1]) < fabs(T.b[2]);
+    const bool LL = t0 && sL, RR = !t1 && !sL;
+    L = LL ? dL0 : (RR ? dL2 : dL1);
+  }
+  {  // right: index i+1 of the masks
+    const bool sL = fabs(T.b[2]) < fabs(T.b[3]);
+    const bool LL = t1 && sL, RR = !t2 && !sL;
+    R = LL ? dR0 : (RR ? dR2 : dR1);
+  }
+}
+
+// upwindFirstENO2 (upwind_first_eno2.py:50-150): two ghost cells (v[1..5]), minimum-modulus second-order term.
+HJ_DEV void upwind_eno2(const double v[7], double dx, double dxinv, double& L, double& R) {
+  EnoTables T;
+  eno_tables(v, dxinv, T, false);
+  const double dL0 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[1])), dL1 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[2]));
+  const double dR0 = __dsub_rn(T.a[3], __dmul_rn(dx, T.b[2])), dR1 = __dsub_rn(T.a[3], __dmul_rn(dx, T.b[3]));
+  L = fabs(T.b[1]) < fabs(T.b[2]) ? dL0 : dL1;
+  R = fabs(T.b[2]) < fabs(T.b[3]) ? dR0 : dR1;
+}
+
 template <int WENO>
-HJ_DEV void upwind5(const double v[7], double dxinv, double inv_eps, double& L, double& R) {
+HJ_DEV void upwind5(const double v[7], double dxinv, double inv_eps, double& L, double& R, double dx = 0.0) {
   if (WENO == HJ_WENO_AS_SHIPPED) upwind5_linear(v, dxinv, L, R);
-  else upwind5_weno(v, dxinv, inv_eps, L, R);
+  else if (WENO == HJ_WENO_INTENDED) upwind5_weno(v, dxinv, inv_eps, L, R);
+  else if (WENO == HJ_SCHEME_ENO3A) upwind_eno3a(v, dx, dxinv, L, R);
+  else upwind_eno2(v, dx, dxinv, L, R);
 }
 
 // max over the D1 entries this node is responsible for (unstripped table: node pairs (-3,-2)..(N+1,N+2)):

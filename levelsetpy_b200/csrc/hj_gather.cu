@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(BX* BY) k_stage_gather(const KGrid g, const KS
     for (int d = 0; d < D; ++d) {
       double v[7], L, R;
       load_stencil(st.in + off, idx[d], g.N[d], g.stride[d], g.bc[d], g.slope_mult[d], v);
-      upwind5<WENO>(v, g.dxinv[d], inv_eps[d], L, R);
+      upwind5<WENO>(v, g.dxinv[d], inv_eps[d], L, R, g.dx[d]);
       pc[d] = 0.5 * (L + R);           // term_lax_friedrich.py:108
       dd[d] = R - L;                   // artificial_diss_glf.py:90
       if (d == 0) yin = v[3];
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_deriv(const KGrid g, const double* __re
     const int i = (int)((e / g.stride[dim]) % g.N[dim]);
     double v[7], L, R;
     load_stencil(in + e, i, g.N[dim], g.stride[dim], g.bc[dim], g.slope_mult[dim], v);
-    upwind5<WENO>(v, g.dxinv[dim], inv_eps, L, R);
+    upwind5<WENO>(v, g.dxinv[dim], inv_eps, L, R, g.dx[dim]);
     dl[e] = L;
     dr[e] = R;
   }
@@ -267,8 +267,13 @@ struct StageLauncher {
       constexpr int D = Sys::ND;
       const long long no = outer_count<D>(g);
       const dim3 grid = tile_grid(g, D, no), block(BX, BY);
-      if (weno == HJ_WENO_AS_SHIPPED) k_stage_gather<Sys, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, ks, st, no);
-      else k_stage_gather<Sys, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, ks, st, no);
+      switch (weno) {
+        case HJ_WENO_AS_SHIPPED: k_stage_gather<Sys, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, ks, st, no); break;
+        case HJ_WENO_INTENDED: k_stage_gather<Sys, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, ks, st, no); break;
+        case HJ_SCHEME_ENO3A: k_stage_gather<Sys, HJ_SCHEME_ENO3A><<<grid, block, 0, s>>>(g, ks, st, no); break;
+        case HJ_SCHEME_ENO2: k_stage_gather<Sys, HJ_SCHEME_ENO2><<<grid, block, 0, s>>>(g, ks, st, no); break;
+        default: ok = false;
+      }
     } else {
       ok = false;    // batch functors only exist for the plane-ring kernel
     }
@@ -308,10 +313,13 @@ cudaError_t hj_launch_deriv(int weno, const KGrid& g, const double* in, int dim,
                             const unsigned long long* epsmax, cudaStream_t s) {
   long long n = 1;
   for (int d = 0; d < g.D; ++d) n *= g.N[d];
-  if (weno == HJ_WENO_AS_SHIPPED)
-    k_deriv<HJ_WENO_AS_SHIPPED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n);
-  else
-    k_deriv<HJ_WENO_INTENDED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n);
+  switch (weno) {
+    case HJ_WENO_AS_SHIPPED: k_deriv<HJ_WENO_AS_SHIPPED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n); break;
+    case HJ_WENO_INTENDED: k_deriv<HJ_WENO_INTENDED><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n); break;
+    case HJ_SCHEME_ENO3A: k_deriv<HJ_SCHEME_ENO3A><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n); break;
+    case HJ_SCHEME_ENO2: k_deriv<HJ_SCHEME_ENO2><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n); break;
+    default: return cudaErrorInvalidValue;
+  }
   hj_count_launch(1);
   return cudaGetLastError();
 }

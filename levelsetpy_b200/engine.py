@@ -14,8 +14,10 @@ from . import _lib as L
 
 __all__ = ["Engine", "engine_for_grid", "DeviceBuffer", "current_stream", "weno_mode_of", "clear_engine_cache"]
 
-_WENO = {"as_shipped": L.WENO_AS_SHIPPED, "intended": L.WENO_INTENDED,
+_WENO = {"as_shipped": L.WENO_AS_SHIPPED, "intended": L.WENO_INTENDED, "eno3a": L.SCHEME_ENO3A, "eno2": L.SCHEME_ENO2,
          L.WENO_AS_SHIPPED: L.WENO_AS_SHIPPED, L.WENO_INTENDED: L.WENO_INTENDED}
+# schemeData.CoStateCalc (by name) -> derivative scheme of the context; the WENO5 names take schemeData.wenoMode
+_COSTATE_SCHEME = {"upwindFirstENO3a": "eno3a", "upwindFirstENO3": "eno3a", "upwindFirstENO2": "eno2"}
 
 
 def _torch():
@@ -38,8 +40,12 @@ def current_stream(device=None):
 def weno_mode_of(scheme_data=None, default="as_shipped"):
     """``schemeData.wenoMode`` ('as_shipped' | 'intended'); the reference has no such switch, so the default is
     its shipped behaviour."""
+    if scheme_data is not None:
+        name = getattr(getattr(scheme_data, "CoStateCalc", None), "__name__", None)
+        if name in _COSTATE_SCHEME:
+            return _COSTATE_SCHEME[name]
     mode = getattr(scheme_data, "wenoMode", default) if scheme_data is not None else default
-    if mode not in _WENO:
+    if mode not in ("as_shipped", "intended"):
         raise ValueError("wenoMode must be 'as_shipped' or 'intended', got %r" % (mode,))
     return mode
 

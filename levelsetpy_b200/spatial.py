@@ -1,7 +1,7 @@
 """SpatialDerivative call surface: ``schemeData.CoStateCalc`` tokens + standalone GPU operators."""
 from .engine import engine_for_grid
 
-__all__ = ["upwindFirstWENO5a", "upwindFirstWENO5"]
+__all__ = ["upwindFirstWENO5a", "upwindFirstWENO5", "upwindFirstENO3a", "upwindFirstENO3", "upwindFirstENO2"]
 
 
 def upwindFirstWENO5a(grid, data, dim, generateAll=False, wenoMode="as_shipped"):
@@ -19,3 +19,28 @@ def upwindFirstWENO5a(grid, data, dim, generateAll=False, wenoMode="as_shipped")
 def upwindFirstWENO5(grid, data, dim, generateAll=False, wenoMode="as_shipped"):
     """Alias of upwindFirstWENO5a -- SpatialDerivative/upwind_first_weno5.py:11-48."""
     return upwindFirstWENO5a(grid, data, dim, generateAll, wenoMode)
+
+
+def _eno(grid, data, dim, generateAll, scheme):
+    if dim < 0 or dim > grid.dim:
+        raise ValueError("Illegal dim parameter")           # upwind_first_eno2.py:52-53, upwind_first_eno3a.py:77-78
+    if generateAll:
+        raise NotImplementedError("generateAll=True (the raw ENO candidates) is outside the hot path")
+    return engine_for_grid(grid, scheme).deriv(data, dim)
+
+
+def upwindFirstENO3a(grid, data, dim, generateAll=False):
+    """[derivL, derivR] = upwindFirstENO3a(grid, data, dim) -- SpatialDerivative/upwind_first_eno3a.py:13: third-order
+    ENO, the candidate on the minimum-modulus D2 / D3 neighbours."""
+    return _eno(grid, data, dim, generateAll, "eno3a")
+
+
+def upwindFirstENO3(grid, data, dim, generateAll=False):
+    """Alias of upwindFirstENO3a -- SpatialDerivative/upwind_first_eno3.py."""
+    return _eno(grid, data, dim, generateAll, "eno3a")
+
+
+def upwindFirstENO2(grid, data, dim, generateAll=False):
+    """[derivL, derivR] = upwindFirstENO2(grid, data, dim) -- SpatialDerivative/upwind_first_eno2.py:13: second-order
+    ENO (two ghost cells), minimum-modulus second-order term."""
+    return _eno(grid, data, dim, generateAll, "eno2")

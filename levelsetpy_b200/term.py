@@ -8,7 +8,7 @@ from .utilities import iscell, isfield
 
 __all__ = ["termLaxFriedrichs", "termRestrictUpdate", "prepare_scheme", "unwrap_scheme"]
 
-_COSTATE = ("upwindFirstWENO5", "upwindFirstWENO5a")
+_COSTATE = ("upwindFirstWENO5", "upwindFirstWENO5a", "upwindFirstENO3a", "upwindFirstENO3", "upwindFirstENO2")
 
 
 def prepare_scheme(schemeData):
@@ -19,7 +19,7 @@ def prepare_scheme(schemeData):
         assert isfield(sd, f), "%s not in bundle thisschemeData" % f      # same messages as the reference
     name = getattr(sd.CoStateCalc, "__name__", None)
     if name not in _COSTATE:
-        raise NotImplementedError("CoStateCalc=%r: only upwindFirstWENO5 / upwindFirstWENO5a run on the device" % (sd.CoStateCalc,))
+        raise NotImplementedError("CoStateCalc=%r: only upwindFirstWENO5(a) / upwindFirstENO3(a) / upwindFirstENO2 run on the device" % (sd.CoStateCalc,))
     if getattr(sd.dissFunc, "__name__", None) != "artificialDissipationGLF":
         raise NotImplementedError("dissFunc=%r: only artificialDissipationGLF is fused into the stage kernel" % (sd.dissFunc,))
     adapter = sd.__dict__.get("_hjb200_adapter")

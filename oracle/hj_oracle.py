@@ -35,6 +35,7 @@ REALMAX = sys.float_info.max
 
 __all__ = [
     "add_ghost_extrapolate", "add_ghost_periodic", "add_ghost", "eno3a_helper", "upwind_first_weno5a",
+    "upwind_first_eno3a", "upwind_first_eno2", "upwind_first",
     "artificial_dissipation_glf", "term_lax_friedrichs", "ode_cfl3_step", "ode_cfl3", "hji_solve",
     "bc_kind_of", "OracleSchemeData",
 ]
@@ -178,6 +179,72 @@ def upwind_first_weno5a(grid, data, dim, weno="as_shipped"):
     return derivL, derivR
 
 
+def upwind_first_eno3a(grid, data, dim):
+    """(derivL, derivR) of the third-order ENO scheme.  Follows SpatialDerivative/upwind_first_eno3a.py:87-142
+    (upwindFirstENO3, upwind_first_eno3.py, is an alias).  The helper's DD tables are always the stripped ones
+    (ENO3aHelper.py:109 overwrites :92): D2 has N+2 entries, D3 N+3.  The choice is applied the way the reference
+    applies it, as a sum of candidate * boolean mask (:134-141)."""
+    n = data.shape[dim]
+    dx = float(np.asarray(grid.dx).reshape(-1)[dim])
+    dx_inv = 1 / dx
+    dL, dR, _, d1u = eno3a_helper(grid, data, dim)
+    d2u = 0.5 * dx_inv * (_ax(d1u, dim, slice(1, None)) - _ax(d1u, dim, slice(0, -1)))
+    d3 = (1 / 3) * dx_inv * (_ax(d2u, dim, slice(1, None)) - _ax(d2u, dim, slice(0, -1)))
+    d2 = _ax(d2u, dim, slice(1, d2u.shape[dim] - 1))
+    d2abs = np.abs(d2)                                                                     # :104
+    smallerL = _ax(d2abs, dim, slice(0, n + 1)) < _ax(d2abs, dim, slice(1, n + 2))          # :108  N+1
+    smallerR = np.logical_not(smallerL)
+    d3abs = np.abs(d3)                                                                     # :114
+    temp = _ax(d3abs, dim, slice(0, n + 2)) < _ax(d3abs, dim, slice(1, n + 3))              # :117  N+2
+    lo, hi = slice(0, n + 1), slice(1, n + 2)
+    smallerLL = np.logical_and(_ax(temp, dim, lo), smallerL)                               # :121-122
+    smallerRL = np.logical_and(_ax(temp, dim, hi), smallerR)
+    ntemp = np.logical_not(temp)
+    smallerLR = np.logical_and(_ax(ntemp, dim, lo), smallerL)                              # :124-125
+    smallerRR = np.logical_and(_ax(ntemp, dim, hi), smallerR)
+    smallerM = np.logical_or(smallerRL, smallerLR)                                         # :127
+    a, b = slice(0, n), slice(1, n + 1)
+    derivL = dL[0] * _ax(smallerLL, dim, a) + dL[1] * _ax(smallerM, dim, a) + dL[2] * _ax(smallerRR, dim, a)   # :132-135
+    derivR = dR[0] * _ax(smallerLL, dim, b) + dR[1] * _ax(smallerM, dim, b) + dR[2] * _ax(smallerRR, dim, b)   # :137-140
+    return derivL, derivR
+
+
+def upwind_first_eno2(grid, data, dim):
+    """(derivL, derivR) of the second-order ENO scheme.  Follows SpatialDerivative/upwind_first_eno2.py:50-150:
+    two ghost cells, D1 (N+3) / D2 (N+2) tables, minimum-modulus choice of the second-order term, applied as a sum
+    of candidate * boolean mask (:145-148)."""
+    n = data.shape[dim]
+    dx = float(np.asarray(grid.dx).reshape(-1)[dim])
+    dx_inv = 1 / dx
+    g = add_ghost(grid, data, dim, 2)                                                       # :66
+    d1 = dx_inv * (_ax(g, dim, slice(1, None)) - _ax(g, dim, slice(0, -1)))                 # :82  N+3
+    d2 = 0.5 * dx_inv * (_ax(d1, dim, slice(1, None)) - _ax(d1, dim, slice(0, -1)))         # :86  N+2
+    d1 = _ax(d1, dim, slice(1, d1.shape[dim] - 1))                                          # :92-93  N+1
+    dL = [_ax(d1, dim, slice(0, n)).copy() for _ in range(2)]                               # :99-100
+    dR = [_ax(d1, dim, slice(1, n + 1)).copy() for _ in range(2)]                           # :103-104
+    dL[0] += dx * _ax(d2, dim, slice(0, n))                                                 # :111-112
+    dL[1] += dx * _ax(d2, dim, slice(1, n + 1))
+    dR[0] -= dx * _ax(d2, dim, slice(1, n + 1))                                             # :117-118
+    dR[1] -= dx * _ax(d2, dim, slice(2, n + 2))
+    d2abs = np.abs(d2)                                                                      # :137
+    smallerL = _ax(d2abs, dim, slice(0, n + 1)) < _ax(d2abs, dim, slice(1, n + 2))          # :140
+    smallerR = np.logical_not(smallerL)
+    a, b = slice(0, n), slice(1, n + 1)
+    derivL = dL[0] * _ax(smallerL, dim, a) + dL[1] * _ax(smallerR, dim, a)                  # :145
+    derivR = dR[0] * _ax(smallerL, dim, b) + dR[1] * _ax(smallerR, dim, b)                  # :148
+    return derivL, derivR
+
+
+def upwind_first(grid, data, dim, scheme="as_shipped"):
+    """schemeData.CoStateCalc by name: 'as_shipped' / 'intended' (upwindFirstWENO5a), 'eno3a' (upwindFirstENO3a /
+    upwindFirstENO3), 'eno2' (upwindFirstENO2)."""
+    if scheme == "eno3a":
+        return upwind_first_eno3a(grid, data, dim)
+    if scheme == "eno2":
+        return upwind_first_eno2(grid, data, dim)
+    return upwind_first_weno5a(grid, data, dim, scheme)
+
+
 # --------------------------------------------------------------------------------------
 # ExplicitIntegration / Dissipation, Term, Integration
 # --------------------------------------------------------------------------------------
@@ -219,7 +286,7 @@ def term_lax_friedrichs(t, y, sd, weno="as_shipped", full=False):
     data = np.asarray(y).reshape(grid.shape)                               # :97
     derivL, derivR, derivC = [], [], []
     for i in range(grid.dim):                                              # :106-108
-        L, R = upwind_first_weno5a(grid, data, i, weno)
+        L, R = upwind_first(grid, data, i, weno)
         derivL.append(L)
         derivR.append(R)
         derivC.append(0.5 * (L + R))

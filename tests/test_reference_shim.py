@@ -59,3 +59,28 @@ def test_reference_weno5a_is_fixed_weight_as_shipped(ref):
         dL, dR, _ = ref["SD"].upwindFirstENO3aHelper(g, data, d, False, False)
         wL = 0.1 * np.asarray(dL[0]) + 0.6 * np.asarray(dL[1]) + 0.3 * np.asarray(dL[2])
         assert np.max(np.abs(np.asarray(L) - wL)) <= 16 * np.finfo(float).eps * np.max(np.abs(wL))
+
+
+def test_oracle_eno_matches_reference_on_fresh_inputs(ref):
+    """upwindFirstENO2 / upwindFirstENO3a, incl. towardZero ghost cells and the fused RHS."""
+    from oracle import hj_oracle as orc
+    from oracle import systems as osys
+    N = [16, 12, 10]
+    g = ref["G"].createGrid(col([-4, -7, 0]), col([9, 6, 2 * np.pi * (1 - 1 / N[2])]), col(N, np.int64), pdDims=2)
+    rng = np.random.default_rng(77)
+    data = np.ascontiguousarray(np.sqrt(g.xs[0] ** 2 + g.xs[1] ** 2) - 3 + 0.5 * np.sin(2 * g.xs[2]) + 0.2 * rng.standard_normal(g.shape))
+    pairs = ((ref["SD"].upwindFirstENO2, orc.upwind_first_eno2, "eno2"), (ref["SD"].upwindFirstENO3a, orc.upwind_first_eno3a, "eno3a"))
+    for rfn, ofn, tag in pairs:
+        for d in range(3):
+            L, R = rfn(g, data, d)
+            oL, oR = ofn(g, data, d)
+            assert np.array_equal(np.asarray(L), oL) and np.array_equal(np.asarray(R), oR), (tag, d)
+        B = ref["U"].Bundle
+        rs = ref["DS"].DubinsVehicleRel(g, 3, 1.5)
+        sd = B(dict(grid=g, hamFunc=rs.hamiltonian, partialFunc=rs.dissipation,
+                    dissFunc=ref["EI"].artificialDissipationGLF, CoStateCalc=rfn))
+        os_ = osys.DubinsVehicleRel(g, 3, 1.5)
+        osd = orc.OracleSchemeData(grid=g, hamFunc=os_.hamiltonian, partialFunc=os_.dissipation)
+        ydot, sb, _ = ref["EI"].termLaxFriedrichs(0.0, data.reshape(-1, 1), sd)
+        oydot, osb = orc.term_lax_friedrichs(0.0, data.reshape(-1, 1), osd, tag)
+        assert sb == osb and np.array_equal(np.asarray(ydot), oydot)

@@ -16,7 +16,7 @@ from .engine import current_stream, grid_signature, weno_mode_of
 from .functors import resolve
 from .integration import rk3_times
 
-__all__ = ["BatchSolver", "batch_step_plan"]
+__all__ = ["BatchSolver", "batch_step_plan", "FlockBatchPlanner"]
 
 
 def batch_step_plan(adapters, dxs, t, t_end, factorCFL, maxStep=np.finfo(np.float64).max):
@@ -45,6 +45,132 @@ def batch_step_plan(adapters, dxs, t, t_end, factorCFL, maxStep=np.finfo(np.floa
         for j in range(nb):
             params[k, j, :blocks[k][j].size] = blocks[k][j]
     return params, dts, t_new
+
+
+class FlockBatchPlanner:
+    """The host side of a batched step for flocks that all have the same shape -- same number of birds, labels and
+    neighbour radii, hence the same neighbour lists (the flock-of-flocks case of SURVEY.md 8d config 5) -- evaluated
+    for the whole batch at once with numpy instead of one Python pass per flock.  Arithmetic and its ORDER are those
+    of ``Flock._housekeeping`` (flock.py:147-188: the headings are updated agent by agent, each update seeing the
+    already-updated headings of lower-indexed neighbours) and of the per-flock parameter block
+    (functors._Flock.block), element for element, so blocks, dt and the birds' ``w_e`` are bit-identical to
+    ``batch_step_plan``.  ``build`` returns None when the flocks are not uniform; the caller then takes the per-flock
+    path."""
+
+    MAX_NEIGH = 7       # np.sum adds fewer than 8 terms left to right; longer lists are summed pairwise
+
+    def __init__(self, flocks, nbrs):
+        self.flocks, self.nbrs = flocks, nbrs
+        self.nb, self.N = len(flocks), flocks[0].N
+        self._trig = {}
+
+    @classmethod
+    def build(cls, adapters):
+        from .functors import _Flock
+        if not adapters or any(not isinstance(ad, _Flock) or ad.mode != "flock" for ad in adapters):
+            return None
+        flocks = [ad.o for ad in adapters]
+        N = flocks[0].N
+        if N < 3 or 10 + 3 * (N - 1) > L.HJ_MAX_PARAMS:
+            return None
+        sig0 = None
+        for f in flocks:
+            if f.N != N or len(f.vehicles) != N:
+                return None
+            index = {id(b): i for i, b in enumerate(f.vehicles)}
+            nbrs = []
+            for i, b in enumerate(f.vehicles):
+                try:
+                    lst = [index[id(n)] for n in b.neighbors]
+                except KeyError:
+                    return None                       # a neighbour that is not a member of this flock
+                if not 1 <= len(lst) <= cls.MAX_NEIGH:
+                    return None
+                # the neighbour lists must already be what _housekeeping would make them (it only ever adds)
+                want = [j for j in list(range(i + 1, N)) + list(range(i - 1, -1, -1))
+                        if np.abs(b.label - f.vehicles[j].label) < b.neigh_rad]
+                if sorted(want) != sorted(lst):
+                    return None
+                nbrs.append(tuple(lst))
+            sig = tuple(nbrs)
+            if sig0 is None:
+                sig0 = sig
+            elif sig != sig0:
+                return None
+        return cls(flocks, sig0)
+
+    def _cos_sin(self, th):
+        out = np.empty(th.shape + (2,))
+        cache = self._trig
+        for idx, v in np.ndenumerate(th):
+            v = float(v)
+            cs = cache.get(v)
+            if cs is None:
+                cs = cache[v] = (float(np.cos(v)), float(np.sin(v)))      # the scalar calls the per-flock path makes
+            out[idx] = cs
+        return out[..., 0], out[..., 1]
+
+    def plan(self, dxs, t, t_end, factorCFL, maxStep=np.finfo(np.float64).max):
+        nb, N, nbrs = self.nb, self.N, self.nbrs
+        fl = self.flocks
+        W = np.array([[b.w_e for b in f.vehicles] for f in fl], dtype=np.float64).reshape(nb, N)
+        cs = np.array([[np.asarray(b.cur_state, dtype=np.float64)[:3, 0] for b in f.vehicles] for f in fl]).reshape(nb, N, 3)
+        ve = np.array([[b.v_e for b in f.vehicles] for f in fl], dtype=np.float64).reshape(nb, N)
+        vp = np.array([[b.v_p for b in f.vehicles] for f in fl], dtype=np.float64).reshape(nb, N)
+        wp0 = np.array([f.vehicles[0].w_p for f in fl], dtype=np.float64)
+        X, Y, TH = cs[..., 0], cs[..., 1], cs[..., 2]
+        C_, S_ = self._cos_sin(TH)
+        K = N - 1
+        npar = 10 + 3 * K
+        params = np.zeros((3, nb, npar))
+        # state-only parts of the block (the birds do not move during the solve)
+        th_low = np.stack([np.min(TH[:, list(nbrs[i])], axis=1) for i in range(N)], axis=1)    # min neighbour heading
+        th_up0 = np.max(TH[:, list(nbrs[0])], axis=1)
+        a_abs0 = np.abs(vp * C_)                     # functors._Flock._abs_alpha
+        a_abs1 = np.abs(ve * S_)
+        a1 = ve[:, 0] - vp[:, 0] * C_[:, 0]          # functors._Flock._att
+        a2 = vp[:, 0] * S_[:, 0]
+        al_att = [np.abs(ve[:, 0] - vp[:, 0] * C_[:, 0]) + np.abs(th_up0 * Y[:, 0]),
+                  np.abs(vp[:, 0] * S_[:, 0]) + np.abs(th_up0 * X[:, 0]),
+                  wp0 + th_up0]
+        amax = []
+        for d, per_other in enumerate((a_abs0, a_abs1, th_low)):
+            m = per_other[:, 1]
+            for i in range(2, N):
+                m = np.maximum(m, per_other[:, i])
+            amax.append(np.maximum(m, al_att[d]))
+        for k in range(3):
+            for i in range(N):                       # Flock._update_headings, agent by agent (flock.py:170-188)
+                lst = nbrs[i]
+                ssum = W[:, lst[0]].copy()
+                for j in lst[1:]:
+                    ssum += W[:, j]
+                W[:, i] = (1 / (1 + len(lst))) * (W[:, i] + ssum)
+            P = params[k]
+            P[:, 0] = float(K)
+            P[:, 1] = 1.0
+            wmax = W[:, nbrs[0][0]]
+            for j in nbrs[0][1:]:
+                wmax = np.maximum(wmax, W[:, j])
+            P[:, 2] = wmax
+            P[:, 3], P[:, 4], P[:, 5], P[:, 6] = a1, a2, X[:, 0], Y[:, 0]
+            P[:, 7], P[:, 8], P[:, 9] = amax
+            for i in range(1, N):
+                c0 = 10 + 3 * (i - 1)
+                P[:, c0], P[:, c0 + 1], P[:, c0 + 2] = -C_[:, i], -S_[:, i], -W[:, i]
+            if k == 0:
+                dx = np.asarray(dxs, dtype=np.float64).reshape(nb, 3)
+                inv = 0
+                for d in range(3):
+                    inv = inv + (amax[d] / dx[:, d])                     # artificial_diss_glf.py:107, dims in order
+                step_bound = 1 / inv
+        for f, row in zip(fl, W):                    # the flocks keep their mutated headings, like the reference's do
+            f.attacked_idx = 0
+            for b, w in zip(f.vehicles, row):
+                b.w_e = np.float64(w)
+        t = np.asarray(t, dtype=np.float64)
+        dts = np.minimum(np.minimum(factorCFL * step_bound, np.asarray(t_end, dtype=np.float64) - t), maxStep)
+        return params, dts, rk3_times(t, dts)[2]
 
 
 class BatchSolver:
@@ -85,6 +211,7 @@ class BatchSolver:
             L.check(self.lib.hj_set_axis(self.h, d, vs[d].ctypes.data, vs[d].size))
         self.t = np.zeros(self.nb)
         self._npar = None
+        self.planner = FlockBatchPlanner.build(self.adapters)     # None: flocks of different shapes -> per-flock host pass
 
     def upload(self, data, field=L.FIELD_STATE):
         """``data``: array [nbatch, N0, N1, N2] (or a list of per-grid arrays)."""
@@ -101,7 +228,10 @@ class BatchSolver:
     def step(self, t_end, factorCFL=0.8, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
         """One CFL-limited TVD-RK3 step of every grid (each with its own dt).  Returns (t_new[nbatch], dt[nbatch])."""
         t_end = np.broadcast_to(np.asarray(t_end, dtype=np.float64), (self.nb,))
-        params, dts, t_new = batch_step_plan(self.adapters, self.dxs, self.t, t_end, factorCFL, maxStep)
+        if self.planner is not None:
+            params, dts, t_new = self.planner.plan(self.dxs, self.t, t_end, factorCFL, maxStep)
+        else:
+            params, dts, t_new = batch_step_plan(self.adapters, self.dxs, self.t, t_end, factorCFL, maxStep)
         if self._npar != params.shape[2]:
             L.check(self.lib.hj_set_system(self.h, L.SYS_FLOCK, None, int(params.shape[2])))
             self._npar = params.shape[2]

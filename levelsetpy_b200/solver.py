@@ -27,7 +27,8 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
     TVD-RK3 at factorCFL 0.8, single-stepping until ``tau[i] - 1e-4`` (hji_solver.py:185,445,536-542).
 
     compMethod: None/'set'/'none', 'minVOverTime', 'maxVOverTime', 'minVWithV0', 'maxVWithV0',
-                'minVWithTarget'/'minVWithL', 'maxVWithTarget'/'maxVWithL'  (:566-599), fused into RK stage 3.
+                'minVWithTarget'/'minVWithL', 'maxVWithTarget'/'maxVWithL'  (:566-599), fused into RK stage 3;
+                'zero'/'minWithZero': termRestrictUpdate with positive = 0 (:438-442), fused into every stage.
     extraArgs : Bundle with optional ``quiet``, ``keepLast``, ``obstacleFunction`` (pointwise max(V, -obstacle),
                 the intended semantics of :641-644), ``targetFunction``, ``stopConverge`` + ``convergeThreshold``.
                 Time-varying obstacles/targets, discounting, SDModFunc, visualisation: NotImplementedError.
@@ -41,8 +42,12 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
                 "ignoreBoundary", "stopInit", "stopSetInclude", "stopSetIntersect", "saveFilename"):
         if isfield(extraArgs, bad) and getattr(extraArgs, bad):
             raise NotImplementedError("extraArgs.%s is outside the accelerated hot path" % bad)
-    if compMethod in ("zero", "minWithZero"):
-        raise NotImplementedError("compMethod %r needs termRestrictUpdate (SURVEY.md 8f, not built yet)" % compMethod)
+    # 'zero' / 'minWithZero': the driver swaps the term for termRestrictUpdate with positive = 0, i.e. ydot = min(ydot, 0)
+    # (hji_solver.py:438-442), and applies no epilogue (:566-570).  Intended semantics: as shipped, the restricted
+    # term returns ydot squeezed to (n,) while the driver's y is (n,1), so y + dt*ydot broadcasts to (n,n).
+    restrict_sign = -1 if compMethod in ("zero", "minWithZero") else 0
+    if restrict_sign:
+        compMethod = "set"
     if compMethod not in _COMP:
         error("Check which compMethod you are using")                   # hji_solver.py:599
     comp = _COMP[compMethod]
@@ -88,6 +93,20 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
     last = data0
     extraOuts = Bundle(dict(dts=[], steps=0))
     i_end = len(tau) - 1
+    eng.set_restrict(restrict_sign)
+    try:
+        i_end, last = _march(eng, ad, grid, g, tau, comp, use_obs, quiet, keepLast, stopConverge, convergeThreshold,
+                             frames, last, extraOuts, small)
+    finally:
+        eng.set_restrict(0)
+    data = last if keepLast else np.stack(frames, axis=0)
+    return data, tau[: i_end + 1], extraOuts
+
+
+def _march(eng, ad, grid, g, tau, comp, use_obs, quiet, keepLast, stopConverge, convergeThreshold, frames, last,
+           extraOuts, small):
+    """The time loop of hji_solver.py:509-672 on the resident state; returns (index of the last tau reached, field)."""
+    i_end = len(tau) - 1
     for i in range(1, len(tau)):
         if not quiet:
             info("Computing value function at time tau[%d]: %.4f" % (i, tau[i]))
@@ -112,5 +131,4 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
                     i_end = i
                     break
             last = cur
-    data = last if keepLast else np.stack(frames, axis=0)
-    return data, tau[: i_end + 1], extraOuts
+    return i_end, last

@@ -145,3 +145,33 @@ def test_device_restrict_on_split_path(lsp):
             assert t == to
             assert np.max(np.abs(y - yo)) <= 1e-9 * float(yo.max() - yo.min())
     lsp.engine_for_grid(g, "as_shipped").set_backend(L.BACKEND_AUTO)
+
+
+@pytest.mark.gpu
+def test_device_hjipde_solve_comp_zero(lsp):
+    """HJIPDE_solve(compMethod='zero'): the driver's termRestrictUpdate(positive=0) swap (hji_solver.py:438-442) on the
+    resident state, against the oracle's restricted odeCFL3 driven by the same time loop."""
+    gold = load_golden("restrict_rk2")
+    g, mk, d0 = _case(lsp, gold, "air3d")
+    s = mk(lsp)
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation))
+    tau = np.array([0.0, 0.05, 0.1])
+    data, tau_out, extra = lsp.HJIPDE_solve(d0, tau, sd, "zero", lsp.Bundle(dict(quiet=True, keepLast=True)))
+    o = mk(osys)
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    y, dts = d0.flatten(), []
+    for i in range(1, len(tau)):
+        t = float(tau[i - 1])
+        while t < tau[i] - 1e-4:
+            t_new, y, _ = orc.ode_cfl3_restricted([t, float(tau[i])], y, osd, False, factor_cfl=0.8, single_step=True)
+            dts.append(t_new - t)
+            t = t_new
+    want = y.reshape(g.shape)
+    assert extra.steps == len(dts)
+    assert np.max(np.abs(data - want)) <= 1e-9 * float(want.max() - want.min())
+    assert (data <= d0 + 1e-12).all()          # ydot <= 0 everywhere: the value function can only decrease
+    # the restriction does not leak into later calls on the same context
+    yd, _, _ = lsp.termLaxFriedrichs(0.0, np.expand_dims(d0.flatten(), 1), lsp.Bundle(dict(
+        grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation, dissFunc=lsp.artificialDissipationGLF,
+        CoStateCalc=lsp.upwindFirstWENO5a)))
+    assert (yd > 0).any() and (yd < 0).any()

@@ -27,6 +27,8 @@ from .utilities import isfield, warn
 __all__ = ["partition", "SlabSolver", "DistComm", "LocalWorld"]
 
 GHOST = L.HJ_GHOST
+# developer switch for attribution runs: exchange first, then compute (the protocol of the gather / intended paths)
+_NO_OVERLAP = bool(int(__import__("os").environ.get("HJ_SLAB_NO_OVERLAP", "0")))
 
 
 def partition(n0, world):
@@ -232,13 +234,14 @@ class SlabSolver:
         """Whole 3-D systems on the plane-ring backend under as_shipped WENO: the planes whose dim-0 stencil stays
         inside the slab are advanced under the halo exchange, the two 3-plane edge ranges after it (hj_stage_range)."""
         if self._ranged is None:
-            self._ranged = bool(self.weno != "intended" and self.eng.D == 3 and self.n0 > 2 * GHOST
+            self._ranged = bool(self.weno != "intended" and not _NO_OVERLAP and self.eng.D == 3 and self.n0 > 2 * GHOST
                                 and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
         return self._ranged
 
     def two_pass(self):
         if self._overlap is None:
-            self._overlap = bool(self.weno != "intended" and getattr(self.eng, "is_split", lambda: False)())
+            self._overlap = bool(self.weno != "intended" and not _NO_OVERLAP
+                                 and getattr(self.eng, "is_split", lambda: False)())
         return self._overlap
 
     def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):

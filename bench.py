@@ -377,6 +377,10 @@ def run_ours(args):
                "d2h_bytes_per_step": int(points * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * es / args.e2e_steps,
                "api": "SlabSolver.upload/step/download (pinned host slabs)"}
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     stage_launches = 3 * args.steps

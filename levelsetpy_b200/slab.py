@@ -51,19 +51,40 @@ class DistComm:
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._side = None
 
     def post(self, sends, recvs):
-        """sends/recvs: lists of (tensor, peer, tag), posted as one batch.  Returns the requests: work launched on
-        the current stream afterwards runs under the transfer until ``wait`` orders the stream behind it."""
+        """sends/recvs: lists of (tensor, peer, tag), posted as one batch.  Returns a handle for ``wait``: work
+        launched on the current stream after ``post`` runs under the transfer until ``wait`` orders the stream behind
+        it.  CUDA tensors: the batch is issued from a side stream (ordered after everything already on the current
+        stream), so that whichever stream the backend runs its copy kernels on, the caller's next kernel is not
+        queued behind them."""
         dist = self.dist
         ops = [dist.P2POp(dist.irecv, t, p, self.group, tag) for t, p, tag in recvs]
         ops += [dist.P2POp(dist.isend, t, p, self.group, tag) for t, p, tag in sends]
-        return dist.batch_isend_irecv(ops) if ops else []
+        if not ops:
+            return None
+        if ops[0].tensor.is_cuda:
+            import torch
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=ops[0].tensor.device)
+            cur = torch.cuda.current_stream(ops[0].tensor.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()                      # orders the side stream (not the host) behind the transfer
+            return ("stream", cur)
+        return ("reqs", dist.batch_isend_irecv(ops))
 
-    @staticmethod
-    def wait(reqs):
-        for req in reqs:
-            req.wait()
+    def wait(self, handle):
+        if handle is None:
+            return
+        kind, h = handle
+        if kind == "stream":
+            h.wait_stream(self._side)
+        else:
+            for req in h:
+                req.wait()
 
     def exchange(self, sends, recvs):
         """Posted as one batch; returns after local completion is ordered on the current stream (NCCL) /

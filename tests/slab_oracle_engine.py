@@ -147,6 +147,58 @@ class TwoPassOracleSlabEngine(OracleSlabEngine):
         self.log = []
 
 
+class RangedOracleSlabEngine(OracleSlabEngine):
+    """Stands in for a whole-system plane-ring context: ``stage_range`` advances only dim-0 planes [z0, z1) of the slab.
+    The stage is evaluated on a haloed sub-block holding exactly the planes that range may read (z0-3 .. z1+2), so an
+    interior range evaluated before the halos arrive provably does not depend on them (they are NaN-poisoned by the
+    test), and stage 3's in-place write of buffer 0 stays pointwise."""
+
+    def supports_range(self):
+        return True
+
+    def stage_range(self, stage, z0, z1, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=0):
+        self.log.append((stage, z0, z1))
+        i, o = self.stage_io(stage)
+        src = self._buf[i].reshape(self.hshape)
+        lo, hi = z0, z1 + 2 * G                     # haloed planes z0-3 .. z1+2 in buffer coordinates
+        sub = _SubGrid()
+        sub.__dict__.update(self.sub.__dict__)
+        sub.shape = (hi - lo,) + self.hshape[1:]
+        sub.N = np.array(sub.shape).reshape(-1, 1)
+        sub.vs = [np.asarray(self.sub.vs[0])[lo:hi]] + list(self.sub.vs[1:])
+        if hasattr(self.sys, "grid"):
+            pass
+        sysd = type(self.sys)(sub, *self._sys_args)
+        sd = orc.OracleSchemeData(grid=sub, hamFunc=sysd.hamiltonian, partialFunc=sysd.dissipation)
+        block = np.ascontiguousarray(src[lo:hi])
+        ydot, _ = orc.term_lax_friedrichs(t, block.reshape(-1, 1), sd, self.weno)
+        ydot = ydot.reshape(sub.shape)[G:G + (z1 - z0)]
+        yin = block[G:G + (z1 - z0)]
+        y0 = self._interior(self._buf[0])[z0:z1].copy()
+        if stage == 1:
+            out = yin + dt * ydot
+        elif stage == 2:
+            out = 0.25 * (3 * y0 + (yin + dt * ydot))
+        else:
+            out = (1 / 3) * (y0 + 2 * (yin + dt * ydot))
+            if comp == 1:
+                out = np.minimum(out, y0)
+            elif comp == 2:
+                out = np.maximum(out, y0)
+        self._interior(self._buf[o])[z0:z1] = out
+
+    def set_system(self, system_id, params, tables=()):
+        OracleSlabEngine.set_system(self, system_id, params, tables)
+        p = np.asarray(params, dtype=np.float64)
+        self._sys_args = (p[0], p[2]) if system_id == 1 else (p[0],)
+
+    log = None
+
+    def __init__(self, *a, **k):
+        OracleSlabEngine.__init__(self, *a, **k)
+        self.log = []
+
+
 def _extrap(*a, **k):
     raise RuntimeError("token only")
 

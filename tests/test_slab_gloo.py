@@ -57,18 +57,33 @@ def _oracle(g, d0, nsteps, comp):
 
 def _worker(rank, world, port, periodic0, q, two_pass=False):
     import torch.distributed as dist
-    from slab_oracle_engine import OracleSlabEngine, TwoPassOracleSlabEngine
+    from slab_oracle_engine import OracleSlabEngine, TwoPassOracleSlabEngine, RangedOracleSlabEngine
     from levelsetpy_b200.slab import SlabSolver
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
         lsp, g, d0, sd = _case(periodic0)
-        sol = SlabSolver(sd, device=0, engine_factory=TwoPassOracleSlabEngine if two_pass else OracleSlabEngine)
+        factory = {False: OracleSlabEngine, True: TwoPassOracleSlabEngine, "ranged": RangedOracleSlabEngine}[two_pass]
+        sol = SlabSolver(sd, device=0, engine_factory=factory)
+        if two_pass == "ranged":
+            # the interior range of every stage must not read the halo planes: poison them before each step's first use
+            orig_post = sol.comm.post
+
+            def poisoned_post(sends, recvs):
+                for t_, _, _ in recvs:
+                    t_.fill_(float("nan"))
+                return orig_post(sends, recvs)
+            sol.comm.post = poisoned_post
         sol.upload(d0[sol.lo:sol.hi])
         t, ts = 0.0, []
         for _ in range(2):
             t, dt = sol.step(t, 1.0, 0.8, comp=1)
             ts.append(t)
-        if two_pass:      # the exchange of every stage was posted before pass 1 and awaited before pass 2
+        if two_pass == "ranged":
+            n0 = sol.n0
+            assert sol.ranged() and not sol.overlapped()
+            assert sol.eng.log == [(s, a, b) for _ in range(2) for s in (1, 2, 3)
+                                   for a, b in ((3, n0 - 3), (0, 3), (n0 - 3, n0))]
+        elif two_pass:      # the exchange of every stage was posted before pass 1 and awaited before pass 2
             assert sol.overlapped()
             assert sol.eng.log == [(p, s) for _ in range(2) for s in (1, 2, 3) for p in ("pass1", "pass2")]
         q.put((rank, sol.lo, sol.hi, ts, sol.download()))
@@ -77,9 +92,12 @@ def _worker(rank, world, port, periodic0, q, two_pass=False):
 
 
 @pytest.mark.parametrize("world,periodic0,two_pass", [(2, False, False), (2, True, False), (3, False, False),
-                                                      (2, False, True), (2, True, True)])
+                                                      (2, False, True), (2, True, True),
+                                                      (2, False, "ranged"), (2, True, "ranged")])
 def test_slab_solver_over_gloo_matches_single_domain_oracle(world, periodic0, two_pass):
-    """two_pass: the overlapped protocol of product systems (halo exchange posted, pass 1, wait, pass 2)."""
+    """two_pass: the overlapped protocol of product systems (halo exchange posted, pass 1, wait, pass 2);
+    "ranged": the protocol of whole 3-D systems (exchange posted, interior planes, wait, the two 3-plane edge ranges),
+    with the receiving halo planes NaN-poisoned when the exchange is posted."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

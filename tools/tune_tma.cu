@@ -172,9 +172,14 @@ int main(int argc, char** argv) {
   unsigned long long ref[3] = {0, 0, 0};
 #define V(R, MINB, U, TY, SEQ, OPT) \
   run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ, OPT>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ "_opt" #OPT, reps, ref)
-  V(8, 2, 1, 16, false, 7);
-  V(8, 2, 1, 16, false, 135);
-  V(8, 2, 1, 16, false, 128);
-  V(8, 2, 1, 16, false, 143);
+  V(8, 2, 1, 16, false, 143);   // production
+  V(8, 2, 1, 16, false, 135);   // without the dim-pipelined load order
+  V(8, 2, 1, 16, false, 7);     // without the SIMPLE fast loop
+  V(8, 2, 1, 16, false, 0);     // round-start plane body
+  // bound-finding experiments: results differ by construction
+  V(8, 2, 1, 16, false, 23);    // no arithmetic
+  V(8, 2, 1, 16, false, 39);    // every load hits L2
+  V(8, 2, 1, 16, false, 103);   // every load hits L2, no store
+  V(8, 2, 1, 16, false, 119);   // nothing but the ring: no arithmetic, no DRAM traffic
   return 0;
 }

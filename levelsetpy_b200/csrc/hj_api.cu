@@ -90,7 +90,10 @@ int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double
   c->D = ndim;
   c->weno = weno_mode;
   for (int d = 0; d < ndim; ++d) {
-    if (N[d] < 2 * HJ_GHOST - 2 || N[d] > 0x7fffffff) { delete c; return fail(HJ_ERR_INVALID, "hj_create: N[%d]=%lld unsupported (need >= 4)", d, (long long)N[d]); }
+    // smallest extents the reference's ghost cells accept: addGhostExtrapolate reads the edge node and its neighbour
+    // (add_ghost_extrapolate.py:88-100), addGhostPeriodic copies `width` = 3 nodes (add_ghost_periodic.py:78-87)
+    const int64_t nmin = bc_kind[d] == HJ_BC_EXTRAPOLATE ? 2 : HJ_GHOST;
+    if (N[d] < nmin || N[d] > 0x7fffffff) { delete c; return fail(HJ_ERR_INVALID, "hj_create: N[%d]=%lld unsupported (need >= %lld)", d, (long long)N[d], (long long)nmin); }
     if (!(dx[d] > 0.0)) { delete c; return fail(HJ_ERR_INVALID, "hj_create: grid cell size dx must be strictly positive"); }
     if (bc_kind[d] != HJ_BC_EXTRAPOLATE && bc_kind[d] != HJ_BC_PERIODIC && !(bc_kind[d] == HJ_BC_HALO && d == 0)) {
       delete c;

@@ -211,7 +211,8 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   PFN_encodeTiled enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled not available from the driver"); return nullptr; }
   const int NX = g.N[D - 1], NY = g.N[D - 2], NZ = g.N[D - 3];
-  if (NZ < 4) { snprintf(err, errlen, "Z extent too small"); return nullptr; }
+  for (int d = 0; d < D; ++d)
+    if (g.N[d] < 4) { snprintf(err, errlen, "extent of dim %d too small for the plane-ring backend", d); return nullptr; }
   const long long pitch = g.stride[D - 2];
   if (pitch % 2) { snprintf(err, errlen, "row pitch must be even"); return nullptr; }
   long long nslow = 1;

@@ -1,0 +1,193 @@
+"""GPU parity at BASELINE.json's configured sizes.
+
+* configs[0] (air3D 101^3, the reference's own CPU-runnable case): direct comparison with the numpy oracle after two
+  TVD-RK3 steps -- identical t, fields within 1e-9 of the value range, sign mask >= 99.99 % (north_star).
+* configs[1] (air3D 512^3), where the oracle would need minutes and ~100 GB: size-independent properties of the
+  scheme -- dt equal to the closed-form CFL bound (bit for bit), the plane-ring backend against the gather backend,
+  minVOverTime monotonicity (bit-exact), a constant field staying constant (bit-exact: every derivative is 0), and the
+  y -> -y, theta -> -theta symmetry of the air3D problem.
+* configs[2] / [3] (4-D pair 161^4, 6-D pair at a 12-plane dim-0 extent of the 41^6 grid): the dimension-split path
+  against the single-pass gather backend on the device.
+* edge cases: the smallest grids the reference's ghost cells allow, ragged (odd, prime) extents.
+"""
+import numpy as np
+import pytest
+
+from oracle import hj_oracle as orc
+from oracle import systems as osys
+
+pytestmark = pytest.mark.gpu
+
+
+def _air3d(lsp, n):
+    g = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / n)]),
+                       np.array([n, n, n]), pdDims=2, low_mem=True)
+    x0 = np.asarray(g.vs[0]).reshape(-1, 1, 1)
+    x1 = np.asarray(g.vs[1]).reshape(1, -1, 1)
+    d0 = np.ascontiguousarray(np.broadcast_to(np.sqrt(x0 ** 2 + x1 ** 2) - 5.0, (n, n, n)))
+    s = lsp.DubinsVehicleRel(g, 5, 1)
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+    return g, d0, sd
+
+
+def _steps(lsp, sd, g, d0, nsteps, backend, comp):
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.integration import rk3_step_resident
+    from levelsetpy_b200.term import prepare_scheme
+    eng, ad = prepare_scheme(sd)
+    eng.set_backend(backend)
+    eng.upload(d0)
+    t, ts = 0.0, []
+    for _ in range(nsteps):
+        t, dt = rk3_step_resident(eng, ad, g, t, 1e9, 0.8, np.finfo(np.float64).max, comp)
+        ts.append(t)
+    out = eng.download(shape=tuple(g.shape))
+    eng.set_backend(L.BACKEND_AUTO)
+    return ts, out
+
+
+def test_config0_air3d_101_vs_oracle(lsp):
+    from levelsetpy_b200 import _lib as L
+    g, d0, sd = _air3d(lsp, 101)
+    ts, got = _steps(lsp, sd, g, d0, 2, L.BACKEND_AUTO, L.COMP_MIN_OVER_TIME)
+    go = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / 101)]),
+                        np.array([101, 101, 101]), pdDims=2)
+    o = osys.DubinsVehicleRel(go, 5, 1)
+    osd = orc.OracleSchemeData(grid=go, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    to, yo = 0.0, d0.reshape(-1, 1)
+    for k in range(2):
+        y_last = yo
+        to, yo, _ = orc.ode_cfl3([to, 1e9], yo, osd, factor_cfl=0.8, single_step=True)
+        yo = np.minimum(yo, y_last)
+        assert ts[k] == to
+    want = yo.reshape(g.shape)
+    assert np.max(np.abs(got - want)) <= 1e-9 * float(want.max() - want.min())
+    assert np.mean(np.sign(got) == np.sign(want)) >= 0.9999
+
+
+def test_config1_air3d_512_properties(lsp):
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.integration import rk3_times
+    n = 512
+    g, d0, sd = _air3d(lsp, n)
+    ts, y_tma = _steps(lsp, sd, g, d0, 2, L.BACKEND_TMA, L.COMP_MIN_OVER_TIME)
+    # (1) dt: alpha_0 = |v_e - v_p cos x3| + |w x2| and alpha_1 = |v_p sin x3| + |w x1| are sums of a function of x3 and
+    # a function of one other coordinate, and fl(a + b) is monotone in both, so the grid maximum of the sum is the sum
+    # of the 1-D maxima, bit for bit (dubins_relative.py:106-111, artificial_diss_glf.py:104-109)
+    v = [np.asarray(g.vs[d]).reshape(-1) for d in range(3)]
+    dx = np.asarray(g.dx).reshape(-1)
+    a0 = np.max(np.abs(5.0 - 5.0 * np.cos(v[2]))) + np.max(np.abs(1.0 * v[1]))
+    a1 = np.max(np.abs(5.0 * np.sin(v[2]))) + np.max(np.abs(1.0 * v[0]))
+    a2 = 1.0 + 1.0
+    inv = 0
+    for al, h in ((a0, dx[0]), (a1, dx[1]), (a2, dx[2])):
+        inv = inv + (al / h)
+    dt = 0.8 * (1 / inv)
+    t1 = rk3_times(0.0, dt)[2]
+    assert ts[0] == t1 and ts[1] == rk3_times(t1, dt)[2]
+    # (2) minVOverTime: the value function can only decrease, pointwise and exactly
+    assert np.all(y_tma <= d0)
+    rng = float(d0.max() - d0.min())
+    # (3) the plane-ring kernels against the one-thread-per-node gather kernels (different operation order)
+    _, y_g = _steps(lsp, sd, g, d0, 2, L.BACKEND_GATHER, L.COMP_MIN_OVER_TIME)
+    assert np.max(np.abs(y_tma - y_g)) <= 1e-10 * rng
+    assert np.mean(np.sign(y_tma) == np.sign(y_g)) >= 0.9999
+    del y_g
+    # (4) symmetry of the air3D problem: V(x, -y, -theta) = V(x, y, theta); node j <-> n-1-j in y, k <-> (n-k) % n in theta
+    mirror = y_tma[:, ::-1, :][:, :, (-np.arange(n)) % n]
+    assert np.max(np.abs(mirror - y_tma)) <= 1e-9 * rng
+    del mirror
+    # (5) a constant field has zero derivatives everywhere (extrapolated and periodic ghosts included): H(x, 0) = 0 and
+    # the dissipation vanishes, so the field is a fixed point, bit for bit
+    c = np.full((n, n, n), 0.375)
+    _, yc = _steps(lsp, sd, g, c, 1, L.BACKEND_TMA, L.COMP_NONE)
+    assert np.array_equal(yc, c)
+
+
+def _device_compare(lsp, g, system, fill, nsteps=1):
+    """One step of the dimension-split (TMA) path and of the single-pass gather path from the same device-made initial
+    data; returns (max |diff|, value range, t_tma, t_gather), compared on the device plane block by plane block."""
+    import torch
+    import sys as _sys
+    import os
+    _sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from levelsetpy_b200 import _lib as L
+    from levelsetpy_b200.integration import rk3_step_resident
+    from levelsetpy_b200.term import prepare_scheme
+    sd = lsp.Bundle(dict(grid=g, hamFunc=system.hamiltonian, partialFunc=system.dissipation,
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+    eng, ad = prepare_scheme(sd)
+    keep, ts = None, []
+    for be in (L.BACKEND_TMA, L.BACKEND_GATHER):
+        eng.set_backend(be)
+        bench.fill_resident(eng, g, fill)
+        t = 0.0
+        for _ in range(nsteps):
+            t, _ = rk3_step_resident(eng, ad, g, t, 1e9, 0.8, np.finfo(np.float64).max, L.COMP_MIN_OVER_TIME)
+        ts.append(t)
+        # valid columns only: the pad column of an odd innermost extent is never written
+        nx = int(np.asarray(g.N).reshape(-1)[-1])
+        pitch = (nx + 1) // 2 * 2
+        buf = eng.buffer_tensor(0).view(-1, pitch)[:, :nx]
+        if keep is None:
+            keep = buf.clone()
+        else:
+            err, lo, hi = 0.0, float("inf"), float("-inf")
+            step = 1 << 21
+            for a in range(0, buf.shape[0], step):
+                x, y = buf[a:a + step], keep[a:a + step]
+                err = max(err, float((x - y).abs().max()))
+                lo, hi = min(lo, float(x.min())), max(hi, float(x.max()))
+    eng.set_backend(L.BACKEND_AUTO)
+    del keep
+    torch.cuda.empty_cache()
+    return err, hi - lo, ts[0], ts[1]
+
+
+def test_config2_dint4d_161_split_vs_gather(lsp):
+    import bench
+    g, system, fill = bench.product_setup(lsp, "dint4d", 161)
+    err, rng, t_a, t_b = _device_compare(lsp, g, system, fill)
+    assert t_a == t_b
+    assert err <= 1e-10 * rng
+
+
+def test_config3_dubins6d_slab_of_41_split_vs_gather(lsp):
+    """12 of the 41 dim-0 planes of the 41^6 grid (11 GB per field; the full grid is exercised by bench.py): the
+    dimension-split kernels with their production tile shapes against the single-pass gather kernel."""
+    import bench
+    g, system, fill = bench.product_setup(lsp, "dubins6d", 41, 12)
+    err, rng, t_a, t_b = _device_compare(lsp, g, system, fill)
+    assert t_a == t_b
+    assert err <= 1e-10 * rng
+
+
+@pytest.mark.parametrize("N,pd", [([3, 3, 3], [2]), ([4, 5, 6], []), ([7, 3, 5], [0, 2]), ([2, 9, 4], []), ([13, 17, 19], [1]),
+                                  ([5, 8], [1]), ([3, 3], [])])
+def test_smallest_and_ragged_grids(lsp, N, pd):
+    """The smallest extents the reference's ghost cells allow (extrapolation reads 2 nodes, a periodic dim 3) and prime /
+    odd extents: every stencil is made of ghost cells on at least one side."""
+    D = len(N)
+    gmin = [-6.0, -10.0, 0.0][:D]
+    gmax = [20.0, 10.0, 2 * np.pi][:D]
+    for d in pd:
+        gmax[d] = gmin[d] + (gmax[d] - gmin[d]) * (1 - 1 / N[d])
+    g = lsp.createGrid(np.array(gmin), np.array(gmax), np.array(N), pdDims=pd if pd else None)
+    rng = np.random.default_rng(sum(N))
+    x = np.meshgrid(*[np.asarray(v).reshape(-1) for v in g.vs], indexing="ij")
+    d0 = np.ascontiguousarray(np.sqrt(x[0] ** 2 + x[1] ** 2) - 5 + 0.3 * rng.standard_normal(g.shape))
+    if D == 3:
+        s, o = lsp.DubinsVehicleRel(g, 5, 1), osys.DubinsVehicleRel(g, 5, 1)
+    else:
+        s, o = lsp.DoubleIntegrator(g, 0.7), osys.DoubleIntegrator(g, 0.7)
+    sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
+    osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
+    y0 = d0.reshape(-1, 1)
+    t, y, _ = lsp.odeCFL3(lsp.termLaxFriedrichs, [0.0, 1.0], y0, opts, sd)
+    to, yo, _ = orc.ode_cfl3([0.0, 1.0], y0, osd, factor_cfl=0.8, single_step=True)
+    assert t == to
+    assert np.max(np.abs(y - yo)) <= 1e-9 * float(yo.max() - yo.min())

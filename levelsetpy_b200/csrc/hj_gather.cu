@@ -23,7 +23,7 @@ HJ_DEV void decompose_outer(long long o, const KGrid& g, int* idx) {
 // (derivL, derivR) -> derivC, R-L; then H(x, derivC), GLF dissipation, stage algebra, and (optionally) the
 // derivative min/max, alpha max and NaN reductions.
 template <class Sys, int WENO>
-__global__ void __launch_bounds__(BX* BY) k_stage_gather(const KGrid g, const KSys ks, const KStage st,
+__global__ void __launch_bounds__(BX* BY, 2) k_stage_gather(const KGrid g, const KSys ks, const KStage st,
                                                           const long long nouter) {
   constexpr int D = Sys::ND;
   const int NX = g.N[D - 1], NY = g.N[D - 2];

@@ -211,8 +211,9 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   PFN_encodeTiled enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled not available from the driver"); return nullptr; }
   const int NX = g.N[D - 1], NY = g.N[D - 2], NZ = g.N[D - 3];
-  for (int d = 0; d < D; ++d)
-    if (g.N[d] < 4) { snprintf(err, errlen, "extent of dim %d too small for the plane-ring backend", d); return nullptr; }
+  // the tiled / marched dims of the plane-ring kernel (outer dims -- a batch index, the leading dims of a >= 4-D grid --
+  // carry no such limit)
+  if (NX < 4 || NY < 4 || NZ < 4) { snprintf(err, errlen, "X/Y/Z extent too small for the plane-ring backend"); return nullptr; }
   const long long pitch = g.stride[D - 2];
   if (pitch % 2) { snprintf(err, errlen, "row pitch must be even"); return nullptr; }
   long long nslow = 1;

@@ -7,7 +7,6 @@ and they are the *tokens* by which the engine recognises a dim's boundary condit
 """
 import numpy as np
 
-from . import _lib as L
 
 __all__ = ["addGhostExtrapolate", "addGhostPeriodic"]
 

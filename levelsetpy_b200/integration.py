@@ -2,7 +2,6 @@
 import numpy as np
 
 from . import _lib as L
-from .engine import is_torch_tensor
 from .term import eng_grid, prepare_scheme, unwrap_scheme
 from .utilities import Bundle, cputime, eps, info, isbundle, iscell, isfield, realmax, strcmp, warn
 

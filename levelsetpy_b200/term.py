@@ -1,7 +1,6 @@
 """ExplicitIntegration/Term call surface: ``termLaxFriedrichs``."""
 import copy
 
-from . import _lib as L
 from .engine import engine_for_grid, weno_mode_of
 from .functors import resolve
 from .utilities import iscell, isfield

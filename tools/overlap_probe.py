@@ -1,7 +1,6 @@
 """Developer probe (not product): on N ranks, time the halo exchange alone, pass 1 alone, and both posted together,
 for the 6-D pair on a thin slab.  torchrun --nproc-per-node 2 tools/overlap_probe.py"""
 import os, sys
-import numpy as np
 import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

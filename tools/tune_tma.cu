@@ -175,6 +175,9 @@ int main(int argc, char** argv) {
 #define V(R, MINB, U, TY, SEQ, OPT) \
   run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ, OPT>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ "_opt" #OPT, reps, ref)
   V(8, 2, 1, 16, false, 143);   // production
+  V(8, 3, 1, 12, false, 143);   // 3 CTAs of 192 threads (18 warps/SM, <= 112 registers)
+  V(6, 3, 1, 12, false, 143);
+  V(8, 2, 1, 16, true, 143);    // one dim at a time
   V(8, 2, 1, 16, false, 135);   // without the dim-pipelined load order
   V(8, 2, 1, 16, false, 7);     // without the SIMPLE fast loop
   V(8, 2, 1, 16, false, 0);     // round-start plane body

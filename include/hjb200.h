@@ -199,7 +199,9 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
 /* odeCFL3(schemeFunc, [t, t_end], y, options{factorCFL,maxStep,singleStep='on'}, schemeData)
  * ExplicitIntegration/Integration/ode_cfl_3.py:11 for one CFL-limited step on a dense array that may live
  * on the host (is_host) -- upload, dt = min(factorCFL*stepBound, t_end-t, maxStep) (:142-143), step,
- * download.  Synchronises.  This is the "host buffers in, host buffers out" call the e2e number times.     */
+ * download.  Synchronises.  This is the "host buffers in, host buffers out" call the e2e number times.
+ * Systems whose parameter block changes between the three RHS evaluations (HJ_SYS_FLOCK) are refused
+ * (HJ_ERR_UNSUPPORTED): step them with hj_upload + hj_step(stage_params) + hj_download.                    */
 int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
                        double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out);
 

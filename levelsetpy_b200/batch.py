@@ -5,6 +5,9 @@ The reference handles a flock of flocks with a Python loop -- one ``odeCFL3(term
 grids of identical shape in ONE resident field ``[nbatch, N0, N1, N2]`` and advances the whole batch with one fused
 kernel per RK stage (C-ABI: hj_create_batch / hj_step_batch).  Each grid keeps its own Flock parameter block (re-derived
 on each of the three RHS evaluations like flock.py:213) and its own CFL time step, exactly as the per-grid loop would.
+A grid that has already reached its ``t_end`` is FINISHED: the per-grid loop would not call odeCFL3 for it any more
+(ode_cfl_3.py:125), so its flock bookkeeping is not run, its dt is 0, its time does not move and the kernels skip
+its CTAs (the field is left bit for bit as it is).
 """
 import ctypes as C
 import weakref
@@ -27,6 +30,12 @@ def batch_step_plan(adapters, dxs, t, t_end, factorCFL, maxStep=np.finfo(np.floa
     blocks = [[None] * nb for _ in range(3)]
     dts, t_new = np.empty(nb), np.empty(nb)
     for j, ad in enumerate(adapters):
+        if not t_end[j] - t[j] > 0:                        # finished: no RHS evaluation, no bookkeeping, dt = 0
+            dts[j], t_new[j] = 0.0, t[j]
+            z = np.zeros(10)                               # header-only block; the kernels skip this element
+            for k in range(3):
+                blocks[k][j] = z
+            continue
         bs = [ad.block(), ad.block(), ad.block()]          # hamFunc re-runs the flock bookkeeping on every RHS
         al = ad.alphas(bs[0])
         inv = 0
@@ -113,6 +122,8 @@ class FlockBatchPlanner:
     def plan(self, dxs, t, t_end, factorCFL, maxStep=np.finfo(np.float64).max):
         nb, N, nbrs = self.nb, self.N, self.nbrs
         fl = self.flocks
+        t = np.asarray(t, dtype=np.float64)
+        active = (np.asarray(t_end, dtype=np.float64) - t) > 0           # finished grids take no RHS evaluation
         W = np.array([[b.w_e for b in f.vehicles] for f in fl], dtype=np.float64).reshape(nb, N)
         cs = np.array([[np.asarray(b.cur_state, dtype=np.float64)[:3, 0] for b in f.vehicles] for f in fl]).reshape(nb, N, 3)
         ve = np.array([[b.v_e for b in f.vehicles] for f in fl], dtype=np.float64).reshape(nb, N)
@@ -164,13 +175,15 @@ class FlockBatchPlanner:
                 for d in range(3):
                     inv = inv + (amax[d] / dx[:, d])                     # artificial_diss_glf.py:107, dims in order
                 step_bound = 1 / inv
-        for f, row in zip(fl, W):                    # the flocks keep their mutated headings, like the reference's do
+        for f, row, act in zip(fl, W, active):   # the flocks keep their mutated headings, like the reference's do
+            if not act:
+                continue                             # ... and a finished flock is not touched at all
             f.attacked_idx = 0
             for b, w in zip(f.vehicles, row):
                 b.w_e = np.float64(w)
-        t = np.asarray(t, dtype=np.float64)
         dts = np.minimum(np.minimum(factorCFL * step_bound, np.asarray(t_end, dtype=np.float64) - t), maxStep)
-        return params, dts, rk3_times(t, dts)[2]
+        dts = np.where(active, dts, 0.0)
+        return params, dts, np.where(active, rk3_times(t, dts)[2], t)
 
 
 class BatchSolver:

@@ -730,6 +730,10 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   if (r) return r;
   if (!y_inout) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_single: null y");
   if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab / batch context");
+  // a Flock re-derives its parameter block on each of the three RHS evaluations (flock.py:213) and its alphas are host
+  // scalars of those blocks: this entry point takes neither, so it must not step one with a frozen block
+  if (c->system_id == HJ_SYS_FLOCK)
+    return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: HJ_SYS_FLOCK needs per-stage parameter blocks; use hj_upload + hj_step(stage_params) + hj_download");
   if (factor_cfl < 0.0) return fail(HJ_ERR_INVALID, "FactorCFL must be a positive scalar double value");   // ode_cfl_set.py:104
   if (max_step < 0.0) return fail(HJ_ERR_INVALID, "MaxStep must be a positive scalar double value");       // ode_cfl_set.py:106
   double sb = 0;
@@ -777,9 +781,9 @@ int hj_create_batch(hj_ctx** out, int device, int nbatch, int ndim, const int64_
     Nb[d + 1] = N[d]; dxb[d + 1] = dx[d]; bcb[d + 1] = bc_kind[d]; tzb[d + 1] = bc_toward_zero ? bc_toward_zero[d] : 0;
   }
   hj_ctx* c = nullptr;
-  // hj_create wants N >= 4 per dim; the batch dim is never differentiated, so a batch of < 4 grids is legal:
-  // create with a padded extent and shrink it afterwards
-  const int64_t nb_create = nbatch < 4 ? 4 : nbatch;
+  // hj_create checks every dim against the smallest extent its ghost cells need (2 for an extrapolated dim); the
+  // batch dim is never differentiated, so a batch of 1 grid is legal: create with a padded extent and shrink it
+  const int64_t nb_create = nbatch < 2 ? 2 : nbatch;
   Nb[0] = nb_create;
   int r = hj_create(&c, device, ndim + 1, Nb, dxb, bcb, tzb, weno_mode);
   if (r) return r;

@@ -254,8 +254,24 @@ HJ_DEV double inv_eps_from_max(unsigned long long enc) {
 
 // ---------------------------------------------------------------- RK3 stage algebra + driver epilogue
 // ode_cfl_3.py:151 (y1), :184,:193 (y2, yHalf), :226,:241 (yThreeHalf, y); hji_solver.py:571-599, :641-644.
+// Driver epilogue and termRestrictUpdate min / max: hji_solver.py:571-599 and term_restrict_update.py:92-94 use
+// np.minimum / np.maximum, which PROPAGATE a NaN; fmin / fmax would return the other operand and silently repair a
+// blown-up node, so the NaN check of hji_solver.py:544 could never fire.  The second operands (y0 / target /
+// obstacle / 0) are finite inputs: propagate the NaN of the integrated value.
+HJ_DEV double nan_min(double y, double ref) { return (y == y) ? fmin(y, ref) : y; }
+HJ_DEV double nan_max(double y, double ref) { return (y == y) ? fmax(y, ref) : y; }
 HJ_DEV double restrict_update(double ydot, int sign) {
-  return sign > 0 ? fmax(ydot, 0.0) : (sign < 0 ? fmin(ydot, 0.0) : ydot);
+  return sign > 0 ? nan_max(ydot, 0.0) : (sign < 0 ? nan_min(ydot, 0.0) : ydot);
+}
+
+HJ_DEV double comp_epilogue(double y, int comp, double y0, double aux) {
+  switch (comp) {
+    case HJ_COMP_MIN_OVER_TIME: return nan_min(y, y0);
+    case HJ_COMP_MAX_OVER_TIME: return nan_max(y, y0);
+    case HJ_COMP_MIN_WITH_AUX: return nan_min(y, aux);
+    case HJ_COMP_MAX_WITH_AUX: return nan_max(y, aux);
+    default: return y;
+  }
 }
 
 HJ_DEV double stage_update(const KStage& st, double yin, double ydot, long long oidx) {
@@ -269,14 +285,9 @@ HJ_DEV double stage_update(const KStage& st, double yin, double ydot, long long 
   }
   const double y32 = yin + st.dt * ydot;
   double y = st.fin_a * (y0 + st.fin_b * y32);
-  switch (st.comp) {
-    case HJ_COMP_MIN_OVER_TIME: y = fmin(y, y0); break;
-    case HJ_COMP_MAX_OVER_TIME: y = fmax(y, y0); break;
-    case HJ_COMP_MIN_WITH_AUX: y = fmin(y, st.aux[oidx]); break;
-    case HJ_COMP_MAX_WITH_AUX: y = fmax(y, st.aux[oidx]); break;
-    default: break;
-  }
-  if (st.use_obs) y = fmax(y, -st.obs[oidx]);
+  if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) y = comp_epilogue(y, st.comp, y0, st.aux[oidx]);
+  else y = comp_epilogue(y, st.comp, y0, 0.0);
+  if (st.use_obs) y = nan_max(y, -st.obs[oidx]);
   return y;
 }
 

@@ -121,29 +121,28 @@ __global__ void __launch_bounds__(256) k_add_ghost(const KGrid g, const double* 
   }
 }
 
-// max_x alpha_d without a field (state-only partialFunc): artificial_diss_glf.py:104 evaluated once.
+// max_x alpha_d without a field (state-only partialFunc): artificial_diss_glf.py:104 evaluated once.  alpha_dl only
+// depends on the dims Sys::alpha_dims(dl) names (e.g. relative Dubins: alpha_0 = |v_e - v_p cos x3| + |w x2|), so the
+// maximum is taken over that sub-grid with every other index held at 0 -- the same set of alpha values, hence the
+// same maximum bit for bit, from N^2 evaluations instead of N^D (41^6: 0.8 s -> microseconds).
 template <class Sys>
-__global__ void __launch_bounds__(BX* BY) k_alpha_max(const KGrid g, const KSys ks, unsigned long long* red,
-                                                       const long long nouter) {
-  constexpr int D = Sys::ND;
-  const int NX = g.N[D - 1], NY = g.N[D - 2];
-  const int xt = (NX + BX - 1) / BX;
-  const int ix = (blockIdx.x % xt) * BX + threadIdx.x;
-  const int iy = (blockIdx.x / xt) * BY + threadIdx.y;
-  const bool active = ix < NX && iy < NY;
-  RedAcc<D> acc;
-  acc.init();
-  for (long long o = blockIdx.y; o < nouter; o += gridDim.y) {
-    if (!active) continue;
+__global__ void __launch_bounds__(256) k_alpha_max(const KGrid g, const KSys ks, unsigned long long* red, const int dl,
+                                                   const unsigned mask, const long long count) {
+  constexpr int D = Sys::BASE_DIM + Sys::ND;
+  double amax = -INFINITY;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
     int idx[D];
-    decompose_outer<D>(o, g, idx);
-    idx[D - 2] = iy;
-    idx[D - 1] = ix;
-    const typename Sys::Pt pt = Sys::load(idx, g, ks);
+    long long r = e;
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc.amax[d] = fmax(acc.amax[d], Sys::alpha(d, pt, ks));
+    for (int d = D - 1; d >= 0; --d) {
+      if (mask & (1u << d)) { idx[d] = (int)(r % g.N[d]); r /= g.N[d]; }
+      else idx[d] = 0;
+    }
+    const typename Sys::Pt pt = Sys::load(idx, g, ks);
+    amax = fmax(amax, Sys::alpha(dl, pt, ks));
   }
-  acc.flush(red);
+  amax = warp_max(amax);
+  if (threadIdx.x % 32 == 0) atomicMax(red + dl, enc_ordered(amax));
 }
 
 // intended WENO: eps_d = 1e-6 * max(D1_d^2) + 1e-99 over the unstripped D1 table (upwind_first_weno5a.py:154-156).
@@ -286,12 +285,18 @@ struct AlphaLauncher {
   unsigned long long* red;
   cudaStream_t s;
   bool ok = true;
+  int launches = 0;
   template <class Sys>
   void operator()() {
     if constexpr (Sys::BASE_DIM == 0) {
-      constexpr int D = Sys::ND;
-      const long long no = outer_count<D>(g);
-      k_alpha_max<Sys><<<tile_grid(g, D, no), dim3(BX, BY), 0, s>>>(g, ks, red, no);
+      for (int dl = 0; dl < Sys::ND; ++dl) {
+        const unsigned mask = Sys::alpha_dims(dl);
+        long long count = 1;
+        for (int d = 0; d < Sys::ND; ++d)
+          if (mask & (1u << d)) count *= g.N[d];
+        k_alpha_max<Sys><<<flat_blocks(count), 256, 0, s>>>(g, ks, red, dl, mask, count);
+        ++launches;
+      }
     } else {
       ok = false;
     }
@@ -337,7 +342,7 @@ cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, u
   AlphaLauncher l{g, ks, red, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
   if (!l.ok) return cudaErrorNotSupported;
-  hj_count_launch(1);
+  hj_count_launch(l.launches);
   return cudaGetLastError();
 }
 

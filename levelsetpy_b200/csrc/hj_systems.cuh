@@ -69,6 +69,10 @@ struct DubinsRelF {
     if (dl == 1) return __dadd_rn(fabs(q.p2c), q.awx1);
     return __dadd_rn(k.p[PB + 3], k.p[PB + 4]);
   }
+  // global dims alpha_dl depends on (bit d = dim d): max_x alpha_dl only needs that sub-grid (hj_alpha_max)
+  static constexpr unsigned alpha_dims(int dl) {
+    return dl == 0 ? (1u << (BASE + 1)) | (1u << (BASE + 2)) : (dl == 1 ? (1u << (BASE + 0)) | (1u << (BASE + 2)) : 0u);
+  }
 };
 
 template <int BASE, int PB>
@@ -95,6 +99,7 @@ struct DoubleIntF {
   HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
     return dl == 0 ? fabs(q.x2) : fabs(k.p[PB + 0]);
   }
+  static constexpr unsigned alpha_dims(int dl) { return dl == 0 ? (1u << (BASE + 1)) : 0u; }
 };
 
 struct FlockF {
@@ -121,6 +126,7 @@ struct FlockF {
     return h;
   }
   HJ_DEV static double alpha(int dl, const Pt&, const KSys& k) { return k.p[7 + dl]; }
+  static constexpr unsigned alpha_dims(int) { return 0u; }
 };
 
 // Batch of independent Flock grids: the field is [nbatch, N0, N1, N2], dim 0 is the batch
@@ -157,6 +163,7 @@ struct FlockBatchF {
     return h;
   }
   HJ_DEV static double alpha(int dl, const Pt& q, const KSys&) { return q.P[7 + dl]; }
+  static constexpr unsigned alpha_dims(int) { return 0u; }
 };
 
 template <class A, class B>
@@ -188,6 +195,7 @@ struct PairF {
   HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
     return dl < A::ND ? A::alpha(dl, q.a, k) : B::alpha(dl - A::ND, q.b, k);
   }
+  static constexpr unsigned alpha_dims(int dl) { return dl < A::ND ? A::alpha_dims(dl) : B::alpha_dims(dl - A::ND); }
 };
 
 // dimension-split trait: a product system is advanced as two passes, one per dim block (hj_vec_kernel.cuh)

@@ -2,6 +2,7 @@
 // kernel (device side: hj_tma_kernel.cuh).
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,12 +53,25 @@ template <> struct SplitCfg<SysDoubleIntPair> {
 static double tile_waste(int n0, int ta) { return (double)((n0 + ta - 1) / ta * ta) / n0; }
 template <class P2, class P2T>
 static bool pick_thin(int n0) {
-  if (const char* e = getenv("HJ_P2_THIN")) return atoi(e) != 0;       // developer override
   if (P2::TA == P2T::TA) return false;
   return tile_waste(n0, P2T::TA) < 0.9 * tile_waste(n0, P2::TA);
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute of a kernel: remember per device
+// whether this instantiation has it yet (a process may hold contexts on several devices; bit d = device d done)
+template <class K>
+static cudaError_t ensure_smem_attr(K kern, size_t smem, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -79,12 +93,8 @@ static cudaError_t launch_one(const HjTmaPlan* p, const CUtensorMap& tm, const K
                               const KStage& st, cudaStream_t s) {
   auto kern = k_stage_tma<Sys, GD, WENO, RED, STAGE, Cfg>;
   constexpr size_t smem = Cfg::template smem_bytes<STAGE>() + Sys::NSCRATCH * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_smem_attr(kern, smem, attr_done); e != cudaSuccess) return e;
   kern<<<(unsigned)p->nblocks, Cfg::NTHREADS, smem, s>>>(tm, p->tmap_y0, g, ks, st, p->geo);
   return cudaGetLastError();
 }
@@ -94,12 +104,8 @@ static cudaError_t launch_vec(const HjTmaPlan* p, const CUtensorMap& tm, const K
                               const KStage& st, cudaStream_t s) {
   auto kern = k_stage_vec<Blk, GD, WENO, RED, STAGE, Cfg>;
   constexpr size_t smem = Cfg::smem_bytes();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (cudaError_t e = ensure_smem_attr(kern, smem, attr_done); e != cudaSuccess) return e;
   kern<<<(unsigned)p->vblocks, Cfg::NTHREADS, smem, s>>>(tm, g, ks, st, p->vgeo);
   return cudaGetLastError();
 }

@@ -275,6 +275,10 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   }
   const double dt = st.dt_arr ? __ldg(st.dt_arr + slow_flat) : st.dt;
   __syncthreads();
+  // batch contexts: an element whose dt is 0 has reached its t_end -- the per-grid loop of the reference would not step
+  // it any more (ode_cfl_3.py:125), so its field stays bit for bit as it is (CTA-uniform exit; buffer 0 is untouched
+  // because all three stages skip)
+  if (st.dt_arr && dt == 0.0) return;
 
   // plane with ring position k -> slot s: TMA load, or a bare arrival for a computed ghost plane
   auto issue = [&](unsigned k, unsigned s) {
@@ -570,17 +574,13 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       oA = st.fin_a * (y0v.x + st.fin_b * (ctr.x + dt * ydA));
       oB = st.fin_a * (y0v.y + st.fin_b * (ctr.y + dt * ydB));
       if constexpr (SIMPLE) {
-        oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y);
+        oA = nan_min(oA, y0v.x); oB = nan_min(oB, y0v.y);
       } else {
-        switch (st.comp) {
-          case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
-          case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;
-          case HJ_COMP_MIN_WITH_AUX: oA = fmin(oA, auxv.x); oB = fmin(oB, auxv.y); break;
-          case HJ_COMP_MAX_WITH_AUX: oA = fmax(oA, auxv.x); oB = fmax(oB, auxv.y); break;
-          default: break;
-        }
+        const bool with_aux = st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX;
+        oA = comp_epilogue(oA, st.comp, y0v.x, with_aux ? auxv.x : 0.0);
+        oB = comp_epilogue(oB, st.comp, y0v.y, with_aux ? auxv.y : 0.0);
       }
-      if (!SIMPLE && st.use_obs) { oA = fmax(oA, -obsv.x); oB = fmax(oB, -obsv.y); }
+      if (!SIMPLE && st.use_obs) { oA = nan_max(oA, -obsv.x); oB = nan_max(oB, -obsv.y); }
     }
     if (FAST && (Cfg::OPT & 64)) { if (oA == 1.2345e300) st.out[off] = oB; }      // tuning harness only: no store
     else if (FAST && (Cfg::OPT & 4) && Cfg::NACTIVE == Cfg::NTHREADS) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);

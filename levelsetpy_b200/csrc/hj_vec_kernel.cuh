@@ -296,14 +296,9 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     else {
       oA = st.fin_a * (y0v.x + st.fin_b * vA);
       oB = st.fin_a * (y0v.y + st.fin_b * vB);
-      switch (st.comp) {
-        case HJ_COMP_MIN_OVER_TIME: oA = fmin(oA, y0v.x); oB = fmin(oB, y0v.y); break;
-        case HJ_COMP_MAX_OVER_TIME: oA = fmax(oA, y0v.x); oB = fmax(oB, y0v.y); break;
-        case HJ_COMP_MIN_WITH_AUX: oA = fmin(oA, auxv.x); oB = fmin(oB, auxv.y); break;
-        case HJ_COMP_MAX_WITH_AUX: oA = fmax(oA, auxv.x); oB = fmax(oB, auxv.y); break;
-        default: break;
-      }
-      if (st.use_obs) { oA = fmax(oA, -obsv.x); oB = fmax(oB, -obsv.y); }
+      oA = comp_epilogue(oA, st.comp, y0v.x, auxv.x);
+      oB = comp_epilogue(oB, st.comp, y0v.y, auxv.y);
+      if (st.use_obs) { oA = nan_max(oA, -obsv.x); oB = nan_max(oB, -obsv.y); }
     }
     if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
     else if (ok0) st.out[off] = oA;

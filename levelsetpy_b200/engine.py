@@ -384,7 +384,10 @@ class Engine:
         return a.value, b.value
 
     def close(self):
+        """Destroy the context now.  The handle is dropped, so a later call fails in ctypes (NULL ctx ->
+        HJ_ERR_INVALID) instead of touching freed memory."""
         self._fin()
+        self.h = None
 
 
 # ---------------------------------------------------------------------- engine cache
@@ -393,8 +396,8 @@ _CACHE_MAX = 4
 
 
 def clear_engine_cache():
-    for e in list(_CACHE.values()):
-        e.close()
+    """Drop the cache's references.  Contexts are destroyed when their last holder lets go (weakref.finalize on the
+    Engine), never under a caller that still holds one."""
     _CACHE.clear()
 
 
@@ -409,7 +412,7 @@ def engine_for_grid(grid, weno="as_shipped", device=None):
     eng = _CACHE.get(key)
     if eng is None:
         while len(_CACHE) >= _CACHE_MAX:
-            _CACHE.pop(next(iter(_CACHE))).close()
+            _CACHE.pop(next(iter(_CACHE)))          # not closed: other holders may still use it (see clear_engine_cache)
         eng = Engine(grid, weno, device)
         _CACHE[key] = eng
     return eng

@@ -28,7 +28,9 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
 
     compMethod: None/'set'/'none', 'minVOverTime', 'maxVOverTime', 'minVWithV0', 'maxVWithV0',
                 'minVWithTarget'/'minVWithL', 'maxVWithTarget'/'maxVWithL'  (:566-599), fused into RK stage 3;
-                'zero'/'minWithZero': termRestrictUpdate with positive = 0 (:438-442), fused into every stage.
+                'zero': as shipped, identical to 'set' (the driver's termRestrictUpdate swap at :438-442 is never used
+                by its time loop, :542); 'minWithZero': as shipped, error (:599).  With extraArgs.restrictUpdate=True
+                both run the intended termRestrictUpdate(positive=0), ydot = min(ydot, 0), fused into every stage.
     extraArgs : Bundle with optional ``quiet``, ``keepLast``, ``obstacleFunction`` (pointwise max(V, -obstacle),
                 the intended semantics of :641-644), ``targetFunction``, ``stopConverge`` + ``convergeThreshold``.
                 Time-varying obstacles/targets, discounting, SDModFunc, visualisation: NotImplementedError.
@@ -42,12 +44,18 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
                 "ignoreBoundary", "stopInit", "stopSetInclude", "stopSetIntersect", "saveFilename"):
         if isfield(extraArgs, bad) and getattr(extraArgs, bad):
             raise NotImplementedError("extraArgs.%s is outside the accelerated hot path" % bad)
-    # 'zero' / 'minWithZero': the driver swaps the term for termRestrictUpdate with positive = 0, i.e. ydot = min(ydot, 0)
-    # (hji_solver.py:438-442), and applies no epilogue (:566-570).  Intended semantics: as shipped, the restricted
-    # term returns ydot squeezed to (n,) while the driver's y is (n,1), so y + dt*ydot broadcasts to (n,n).
-    restrict_sign = -1 if compMethod in ("zero", "minWithZero") else 0
-    if restrict_sign:
-        compMethod = "set"
+    # 'zero' / 'minWithZero' AS SHIPPED: the driver builds a termRestrictUpdate scheme (hji_solver.py:438-442) but its
+    # time loop hard-codes odeCFL3(termLaxFriedrichs, ...) (:542) and never uses it, so 'zero' integrates exactly like
+    # 'set' (the epilogue is a `pass`, :566-570) and 'minWithZero' reaches error('Check which compMethod you are
+    # using') (:599).  That is the default here.  extraArgs.restrictUpdate = True opts into what the comment at
+    # :436-437 says was meant: ydot = min(ydot, 0) (termRestrictUpdate, positive = 0) fused into every stage kernel.
+    restrict_sign = 0
+    if compMethod in ("zero", "minWithZero"):
+        if bool(getattr(extraArgs, "restrictUpdate", False)):
+            restrict_sign = -1
+            compMethod = "set"
+        elif compMethod == "zero":
+            compMethod = "set"
     if compMethod not in _COMP:
         error("Check which compMethod you are using")                   # hji_solver.py:599
     comp = _COMP[compMethod]
@@ -74,6 +82,7 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
             raise NotImplementedError("time-varying obstacleFunction is outside the accelerated hot path")
         eng.upload(obs, L.FIELD_OBSTACLE)
         use_obs = True
+        data0 = np.maximum(data0, -obs)                                 # hji_solver.py:222 (before the first frame is stored)
     if comp in (L.COMP_MIN_WITH_AUX, L.COMP_MAX_WITH_AUX):
         if compMethod in ("minVWithV0", "maxVWithV0"):
             aux = data0

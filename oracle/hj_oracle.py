@@ -419,8 +419,10 @@ def hji_solve(data0, tau, sd, comp_method="minVOverTime", obstacle=None, target=
     small = 1e-4
     grid = sd.grid
     data = np.asarray(data0, dtype=np.float64)
-    d0 = np.expand_dims(data.flatten(), 1)
     obs = None if obstacle is None else np.expand_dims(np.asarray(obstacle, dtype=np.float64).flatten(), 1)
+    if obstacle is not None:
+        data = np.maximum(data, -np.asarray(obstacle, dtype=np.float64))   # :222: data0 is masked before the march
+    d0 = np.expand_dims(data.flatten(), 1)                                  # 'minVWithV0' sees the masked data0
     tgt = None if target is None else np.expand_dims(np.asarray(target, dtype=np.float64).flatten(), 1)
     dts, ts = [], []
     for i in range(1, len(tau)):
@@ -444,9 +446,9 @@ def hji_solve(data0, tau, sd, comp_method="minVOverTime", obstacle=None, target=
                 y = np.minimum(y, d0)
             elif comp_method == "maxVWithV0":
                 y = np.maximum(y, d0)
-            elif comp_method in ("minVWithL", "minVWithTarget"):
+            elif comp_method in ("minVWithL", "minVwithL", "minVWithTarget"):                # :592
                 y = np.minimum(y, tgt)
-            elif comp_method in ("maxVWithL", "maxVWithTarget"):
+            elif comp_method in ("maxVWithL", "maxVwithL", "maxVWithTarget"):                # :583
                 y = np.maximum(y, tgt)
             else:
                 raise ValueError("Check which compMethod you are using")

@@ -3,7 +3,11 @@
 usage: python profiles/ncu_source_hot.py rep.ncu-rep <kernel index> [min_exec]"""
 import csv, subprocess, sys
 rep, kidx = sys.argv[1], int(sys.argv[2])
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+if rep.endswith('.gz'):       # a source page exported on the GPU box: ncu -i rep --page source --csv | gzip
+    import gzip
+    out = gzip.open(rep, 'rt').read()
+else:
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 blocks, cur = [], None
 for row in csv.reader(out.splitlines()):
     if row and row[0] == 'Kernel Name':

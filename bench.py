@@ -8,6 +8,13 @@ One "step" = one full TVD-RK3 step (3 fused RHS+stage kernels) of the hot path o
 1 point-step = one grid node advanced by one RK3 step.  N=1 workload: air3D 512^3 (configs[1]).
 N>1: the same 512^2 cross-section with 512 planes per GPU, slab-decomposed along dim 0 with a 3-plane halo
 exchange per RK stage (weak scaling).  Prints ONE JSON line (rank 0).
+
+The same run also measures BASELINE.json's other configs and reports them under "workloads" in that line:
+configs[2] (4-D double-integrator pair 161^4) and configs[3] (6-D relative-Dubins pair 41^6) STRONG-scaled over the
+N ranks -- ms per step, point-steps/s, fraction of the aggregate 64-B HBM roofline, halo bytes per step, compute-only
+and exchange-only times -- each with a "verify" record (the slabs after a few steps against a single-domain answer:
+max_rel_err, dt_identical; 41^6 also against per-plane checksums committed from the N=1 run), and at N=1 configs[4]
+(the 256 x 101^3 Flock batch).  ``--blocks none`` skips them.
 """
 import argparse
 import json
@@ -113,6 +120,230 @@ def fill_resident(eng, g, fill, planes_per_chunk=None, slab=None):
     for lo in range(0, n0, step):
         hi = min(n0, lo + step)
         fill(body[lo:hi], lo0 + lo, lo0 + hi)
+
+
+# ----------------------------------------------------------------------------- configs[2..4] in the same run
+GOLDEN_6D = os.path.join(ROOT, "tests", "golden", "bench_dubins6d_41_checksums.json")
+VERIFY_STEPS = 2
+
+
+def _interior(eng, g, n0):
+    """Torch view [n0, N1, ..., N_{D-2}, pitch] of the interior planes of RK buffer 0."""
+    N = [int(x) for x in np.asarray(g.N).reshape(-1)]
+    pitch = (N[-1] + 1) // 2 * 2
+    buf = eng.buffer_tensor(0)
+    halo = (buf.numel() - n0 * int(np.prod(N[1:-1])) * pitch) // 2
+    return buf[halo:buf.numel() - halo].view(n0, *N[1:-1], pitch)
+
+
+def _plane_checksums(view, nx):
+    """Per dim-0 plane (sum, min, max) of the nodes (pad columns excluded)."""
+    out = []
+    for p in range(view.shape[0]):
+        v = view[p][..., :nx]
+        out.append([float(v.sum(dtype=v.dtype).item()), float(v.min().item()), float(v.max().item())])
+    return out
+
+
+def _timed(step, steps, barrier, world, torch):
+    """K steps between barriers, device-timed, max over ranks (ms per step)."""
+    t = 0.0
+    torch.cuda.synchronize()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        t = step(t)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        import torch.distributed as dist
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    return ms / steps
+
+
+def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backend):
+    """configs[2] / [3]: the fixed product grid, one context (N=1) or slab-decomposed along dim 0 over the ranks
+    (strong scaling), state made on the device; timing, attribution and verification.  Returns a dict (rank 0)."""
+    import torch
+    from levelsetpy_b200.engine import Engine, clear_engine_cache
+    from levelsetpy_b200.integration import rk3_step_resident
+    from levelsetpy_b200.term import prepare_scheme
+    n = {"dint4d": 161, "dubins6d": 41}[kind] if args.block_n is None else args.block_n
+    steps = max(1, min(args.steps, args.block_steps))
+    gg, system, fill = product_setup(lsp, kind, n)
+    sd = scheme_for(lsp, gg, args.weno, system)
+    N = [int(x) for x in np.asarray(gg.N).reshape(-1)]
+    points = float(np.prod(np.asarray(N, dtype=np.float64)))
+    fmax = np.finfo(np.float64).max
+    out = {"config": ("configs[2]: 4-D double-integrator pair %d^4" if kind == "dint4d" else
+                      "configs[3]: 6-D relative-Dubins pair %d^6") % n, "scaling": "strong", "n_gpus": world,
+           "steps": steps, "warmup": 3}
+    solver = None
+    if world > 1:
+        import torch.distributed as dist
+        from levelsetpy_b200.slab import SlabSolver
+        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport)
+        eng, lo, hi = solver.eng, solver.lo, solver.hi
+        step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
+        barrier = dist.barrier
+        refill = lambda: fill_resident(eng, gg, fill, slab=(lo, hi))
+    else:
+        eng, ad = prepare_scheme(sd)
+        eng.set_backend(backend)
+        lo, hi = 0, N[0]
+        step = lambda t: rk3_step_resident(eng, ad, gg, t, 1e9, 0.8, fmax, comp)[0]
+        barrier = lambda: None
+        refill = lambda: fill_resident(eng, gg, fill)
+    refill()
+    t = 0.0
+    for _ in range(3):
+        t = step(t)
+    ms = _timed(step, steps, barrier, world, torch)
+    out.update({"ms_per_step": ms, "value": points / (ms * 1e-3), "unit": UNIT,
+                "frac_of_aggregate_64B_roofline": points * ALG_BYTES_PER_POINT_STEP / (ms * 1e-3) / (world * hbm_peak * 1e9)})
+    if solver is not None:
+        plane_bytes = eng.plane_elems * 8
+        faces = (1 if solver.lo_peer is not None else 0) + (1 if solver.hi_peer is not None else 0)
+        out.update({"planes_per_rank": [hi - lo], "transport": "peer memory (copy engines)" if solver.peer else "NCCL send/recv",
+                    "protocol": "two_pass" if solver.two_pass() else ("ranged" if solver.ranged() else "exchange_first"),
+                    "halo_bytes_in_per_step_per_rank": 3 * faces * L.HJ_GHOST * plane_bytes})
+        # attribution: the same step with the exchange switched off, and the exchange alone (results are discarded:
+        # the state is re-made before verification)
+        solver.mode = "compute"
+        out["compute_only_ms"] = _timed(step, steps, barrier, world, torch)
+        solver.mode = "comm"
+        out["exchange_only_ms"] = _timed(step, steps, barrier, world, torch)
+        solver.mode = "full"
+
+    # ---- verify: VERIFY_STEPS steps from the initial data against a single-domain answer
+    refill()
+    t, dts = 0.0, []
+    for _ in range(VERIFY_STEPS):
+        t_new = step(t)
+        dts.append(t_new - t)
+        t = t_new
+    torch.cuda.synchronize()
+    mine = _interior(eng, gg, hi - lo)
+    sums = _plane_checksums(mine, N[-1])
+    ver = {"steps": VERIFY_STEPS}
+    if world > 1:
+        import torch.distributed as dist
+        allsums = [None] * world
+        dist.all_gather_object(allsums, (lo, sums, dts))
+        allsums.sort(key=lambda x: x[0])
+        sums = [p for _, part, _ in allsums for p in part]
+        ver["dt_identical_across_ranks"] = all(d == allsums[0][2] for _, _, d in allsums)
+    if kind == "dubins6d" and n == 41:
+        if args.write_golden and world == 1 and rank == 0:
+            with open(args.write_golden, "w") as fh:
+                json.dump({"what": "per dim-0 plane (sum, min, max) of the 41^6 field after %d steps (bench.py N=1)" % VERIFY_STEPS,
+                           "dts": dts, "planes": sums}, fh)
+        if os.path.exists(GOLDEN_6D):
+            with open(GOLDEN_6D) as fh:
+                gold = json.load(fh)
+            gp = np.asarray(gold["planes"])
+            sp = np.asarray(sums)
+            scale = np.maximum(np.abs(gp[:, 0]), 1.0)
+            ver["checksum_max_rel_diff_vs_n1_golden"] = float(np.max(np.abs(sp[:, 0] - gp[:, 0]) / scale))
+            ver["plane_minmax_identical_to_n1_golden"] = bool(np.array_equal(sp[:, 1:], gp[:, 1:]))
+            ver["dt_identical"] = list(dts) == list(gold["dts"])
+        else:
+            ver["checksums"] = "no committed N=1 checksums (bench.py --write-golden at N=1)"
+    # element-wise against a single-domain run on rank 0: 161^4 on the gather backend (an independent kernel),
+    # 41^6 (N > 1 only: two 114 GB contexts do not fit one GPU) on the dimension-split path of one context
+    do_elem = kind == "dint4d" or world > 1
+    if do_elem:                                         # ... if rank 0 has room for the single-domain context
+        need = 3.0 * points * 8 * ((N[-1] + 1) // 2 * 2) / N[-1] + 4e9
+        room = torch.tensor([1 if torch.cuda.mem_get_info()[0] > need else 0], device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(room, 0)
+        do_elem = bool(room.item())
+        if not do_elem:
+            ver["elementwise"] = "skipped: no room on rank 0 for a %.0f GB single-domain context next to its slab" % (need * 1e-9)
+    if do_elem:
+        ref = None
+        if rank == 0:
+            ref_backend = L.BACKEND_GATHER if kind == "dint4d" else backend
+            ref = Engine(gg, args.weno, local, backend=ref_backend)
+            ad0 = solver.adapter if solver is not None else ad
+            fill_resident(ref, gg, fill)
+            tr, rdts = 0.0, []
+            for _ in range(VERIFY_STEPS):
+                tn = rk3_step_resident(ref, ad0, gg, tr, 1e9, 0.8, fmax, comp)[0]
+                rdts.append(tn - tr)
+                tr = tn
+            torch.cuda.synchronize()
+            refv = _interior(ref, gg, N[0])
+            ver["reference"] = "single-domain, %s backend, rank 0" % ("gather" if ref_backend == L.BACKEND_GATHER else "plane-ring")
+            ver["dt_identical"] = ver.get("dt_identical", True) and list(rdts) == list(dts)
+        err = torch.zeros(1, dtype=torch.float64, device="cuda")
+        rng_ = 1.0
+        if world == 1:
+            err = (mine[..., :N[-1]] - refv[..., :N[-1]]).abs().max().reshape(1)
+            rng_ = float((refv[..., :N[-1]].max() - refv[..., :N[-1]].min()).item())
+        else:
+            import torch.distributed as dist
+            parts = partition_of(N[0], world)
+            for r in range(world):                      # one slab at a time through a plane-sized staging tensor
+                rlo, rhi = parts[r]
+                for p in range(rlo, rhi):
+                    if rank == 0:
+                        if r == 0:
+                            got = mine[p - rlo]
+                        else:
+                            got = torch.empty_like(refv[p])
+                            dist.recv(got, src=r)
+                        err = torch.maximum(err, (got[..., :N[-1]] - refv[p][..., :N[-1]]).abs().max().reshape(1))
+                    elif rank == r:
+                        dist.send(mine[p - rlo].contiguous(), dst=0)
+            if rank == 0:
+                rng_ = float((refv[..., :N[-1]].max() - refv[..., :N[-1]].min()).item())
+        if rank == 0:
+            ver["max_abs_err"] = float(err.item())
+            ver["max_rel_err"] = float(err.item()) / rng_
+            ver["bit_identical"] = float(err.item()) == 0.0
+            ref.close()
+    out["verify"] = ver
+    if solver is not None:
+        torch.cuda.synchronize()
+        solver.close()
+    else:
+        clear_engine_cache()
+        eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def partition_of(n0, world):
+    from levelsetpy_b200.slab import partition
+    return partition(n0, world)
+
+
+def flock_block(args, lsp, L, local, hbm_peak, comp):
+    """configs[4] at N=1: 256 independent 101^3 Flock grids as one batch context."""
+    import torch
+    steps = max(1, min(args.steps, args.block_steps))
+    sds, data = flock_batch_setup(lsp, args.batch, 101)
+    bsolver = lsp.BatchSolver(sds, device=local)
+    bsolver.upload(np.stack(data))
+    step = lambda t: float(bsolver.step(1e9, 0.8, comp)[0][0])
+    t = 0.0
+    for _ in range(3):
+        t = step(t)
+    ms = _timed(step, steps, lambda: None, 1, torch)
+    points = float(args.batch) * 101.0 ** 3
+    del bsolver
+    torch.cuda.empty_cache()
+    return {"config": "configs[4]: batch of %d independent 101^3 Flock grids (4 birds each, per-grid dt)" % args.batch,
+            "n_gpus": 1, "steps": steps, "warmup": 3, "ms_per_step": ms, "value": points / (ms * 1e-3), "unit": UNIT,
+            "frac_of_aggregate_64B_roofline": points * ALG_BYTES_PER_POINT_STEP / (ms * 1e-3) / (hbm_peak * 1e9),
+            "scaling": "replicas only (independent grids, no exchange)"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -255,7 +486,7 @@ def run_ours(args):
         from levelsetpy_b200.slab import SlabSolver
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         gg, system, fill = product_setup(lsp, args.workload, n, args.planes0)
-        solver = SlabSolver(scheme_for(lsp, gg, args.weno, system), device=local, backend=backend)
+        solver = SlabSolver(scheme_for(lsp, gg, args.weno, system), device=local, backend=backend, transport=args.transport)
         fill_resident(solver.eng, gg, fill, slab=(solver.lo, solver.hi))
         data0 = None
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
@@ -269,7 +500,7 @@ def run_ours(args):
         # global grid: world*n planes along dim 0; each rank builds only its slab of the initial data
         gg = lsp.createGrid(np.array([-6.0, -10.0, 0.0]), np.array([20.0, 10.0, 2 * np.pi * (1 - 1 / n)]),
                             np.array([n * world, n, n]), pdDims=2, low_mem=True)
-        solver = SlabSolver(scheme_for(lsp, gg, args.weno), device=local, backend=backend)
+        solver = SlabSolver(scheme_for(lsp, gg, args.weno), device=local, backend=backend, transport=args.transport)
         lo, hi = solver.lo, solver.hi
         x0 = gg.vs[0].reshape(-1)[lo:hi].reshape(-1, 1, 1)
         slab0 = np.ascontiguousarray(np.broadcast_to(np.sqrt(x0 ** 2 + gg.xs[1] ** 2) - 5.0, (hi - lo, n, n)))
@@ -342,20 +573,23 @@ def run_ours(args):
     elif data0 is None and slab0 is None:
         pass                                   # product workloads: resident-state numbers only (no host copy of a 38 GB field)
     elif world == 1:
-        y_host = torch.from_numpy(data0.reshape(-1)).pin_memory()
-        y_np = y_host.numpy()
+        # the call a user of the reference makes (hji_solver.py:542): odeCFL3(termLaxFriedrichs, [t, tau], y, options, sd)
+        # with a HOST numpy y and singleStep='on'; y comes back as a host array.  H2D + 3 stage kernels + D2H per call.
+        opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
+        y_np = np.ascontiguousarray(data0.reshape(-1, 1))
         te = 0.0
-        for _ in range(1):
-            te, _, _ = eng.ode_cfl3_single(te, 1e9, 0.8, np.finfo(np.float64).max, y_np, comp)
+        for _ in range(3):                              # also brings up the engine's three pinned output arrays
+            te, y_np, _ = lsp.odeCFL3(lsp.termLaxFriedrichs, [te, 1e9], y_np, opts, sd)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            te, _, _ = eng.ode_cfl3_single(te, 1e9, 0.8, np.finfo(np.float64).max, y_np, comp)
+            te, y_np, _ = lsp.odeCFL3(lsp.termLaxFriedrichs, [te, 1e9], y_np, opts, sd)
         torch.cuda.synchronize()
         es = time.perf_counter() - t0
         e2e = {"value": points * args.e2e_steps / es, "unit": UNIT, "h2d_bytes_per_step": int(points * 8),
                "d2h_bytes_per_step": int(points * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * es / args.e2e_steps,
-               "api": "hj_ode_cfl3_single (odeCFL3 drop-in, pinned host y in/out)"}
+               "api": "levelsetpy_b200.odeCFL3(termLaxFriedrichs, [t, tau], y_host, odeCFLset(singleStep='on'), schemeData) "
+                      "-> hj_ode_cfl3_step (host y in, host y out; no min-over-time epilogue: that is the driver's line)"}
     else:
         import torch.distributed as dist
         # slab job: every rank uploads its slab from pinned host memory, steps once, downloads it
@@ -376,6 +610,53 @@ def run_ours(args):
         e2e = {"value": points * args.e2e_steps / es, "unit": UNIT, "h2d_bytes_per_step": int(points * 8),
                "d2h_bytes_per_step": int(points * 8), "steps": args.e2e_steps, "ms_per_step": 1e3 * es / args.e2e_steps,
                "api": "SlabSolver.upload/step/download (pinned host slabs)"}
+        # the host-link ceiling of that pattern: every rank moves its slab up and down at once, nothing else running
+        dev = torch.empty_like(y_host, device="cuda")
+        back = torch.empty_like(y_host).pin_memory()
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(up):
+                dev.copy_(y_host, non_blocking=True)
+            with torch.cuda.stream(down):
+                back.copy_(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        cs = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cs, op=dist.ReduceOp.MAX)
+        e2e["host_link_floor_ms_per_step"] = 1e3 * float(cs.item()) / 2
+        e2e["host_link_note"] = ("H2D + D2H of one slab per rank, all ranks at once, both directions overlapped "
+                                 "(cudaMemcpyAsync on two streams, pinned): the floor of any per-step host round trip")
+        del dev, back
+
+    # ---- BASELINE.json configs[2..4] in the same run (strong-scaled over the same ranks), each with a verify record
+    workloads = None
+    if args.blocks != "none" and args.workload == "air3d" and args.weno == "as_shipped":
+        from levelsetpy_b200.engine import clear_engine_cache
+        if world > 1:
+            solver.close()
+            del solver
+        else:
+            clear_engine_cache()
+            eng.close()
+        torch.cuda.empty_cache()
+        workloads = {}
+        for kind, key in (("dubins6d", "dubins6d_41^6"), ("dint4d", "dint4d_161^4")):
+            if args.blocks not in ("all", kind):
+                continue
+            try:
+                workloads[key] = product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backend)
+            except Exception as e:                        # the headline line must survive a failing block
+                workloads[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+                if world > 1:
+                    raise
+        if world == 1 and args.blocks in ("all", "flockbatch"):
+            try:
+                workloads["flockbatch_256x101^3"] = flock_block(args, lsp, L, local, hbm_peak, comp)
+            except Exception as e:
+                workloads["flockbatch_256x101^3"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if world > 1:
         import torch.distributed as dist
@@ -396,6 +677,7 @@ def run_ours(args):
                    "point_stage_updates_per_s": 3 * value},
         "clocks": clocks,
         "e2e": e2e,
+        "workloads": workloads,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": args.traffic if args.traffic is not None else (
@@ -426,6 +708,15 @@ def main():
     ap.add_argument("--weno", default="as_shipped", choices=["as_shipped", "intended"])
     ap.add_argument("--backend", default="auto", choices=["auto", "gather", "tma"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "p2p"],
+                    help="slab halos: peer-memory pushes on the copy engines (default) or NCCL send/recv")
+    ap.add_argument("--blocks", default="all", choices=["all", "none", "dubins6d", "dint4d", "flockbatch"],
+                    help="also measure + verify configs[2..4] in the default run ('workloads' in the JSON line)")
+    ap.add_argument("--block-steps", type=int, default=5, help="timed steps of each workloads block (<= --steps)")
+    ap.add_argument("--block-n", type=int, default=None, help="developer: nodes per dim of the product blocks")
+    ap.add_argument("--write-golden", default=None, metavar="PATH",
+                    help="N=1: write the per-plane checksums of the 41^6 verify run to PATH (committed as "
+                         "tests/golden/bench_dubins6d_41_checksums.json)")
     ap.add_argument("--cpu-sample", type=int, default=101, help="CPU arm: air3D n^3 sample (101 = configs[0])")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")

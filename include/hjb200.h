@@ -196,6 +196,29 @@ int hj_eps_prepass(hj_ctx* ctx, void* stream, int buf, uint64_t** eps_dev);
  * global dim-0 boundary that is not periodic.  Interior slab faces get their halos from the neighbour instead. */
 int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
 
+/* Slab halos over NVLink peer memory.  The reference has no multi-GPU path: the planes a
+ * rank receives are the ghost planes addGhostPeriodic / the interior of a larger array would have supplied
+ * (BoundaryCondition/add_ghost_periodic.py:78-87, SpatialDerivative/ENO3aHelper.py:64).  A slab context (dim 0 =
+ * HJ_BC_HALO) PUSHES its 3 edge planes into its neighbours' stored halo planes with the copy engines -- no NCCL, no
+ * SM copy kernel -- so any host that can move HJ_HALO_DESC_BYTES bytes between ranks can run slabs:
+ *   hj_halo_export   fills `desc` (CUDA IPC handles of the three RK buffers and of the arrival counters; POD bytes).
+ *   hj_halo_attach   maps the lower / upper neighbour's descriptor (NULL = no neighbour on that side; contexts of one
+ *                    process are attached by pointer).  For a two-rank periodic ring pass the same descriptor twice.
+ *   hj_halo_push     ordered behind `stream`: copy my edge planes of RK buffer `buf` into both neighbours' halos on
+ *                    dedicated copy streams, then bump their arrival counters.  col_begin/col_end/row_len select
+ *                    columns of every row_len-element row of the planes (pushing a buffer in pieces while later
+ *                    pieces are still being computed); 0, 0, 0 = whole planes.
+ *   hj_halo_wait     makes `stream` wait until `npush` further pushes of `buf` from each neighbour have landed and
+ *                    my own outbound copies have left.  Every rank must push and await each buffer equally often.
+ *   hj_halo_attached bit 0 / bit 1: a lower / upper neighbour is attached.                                        */
+#define HJ_HALO_DESC_BYTES 512
+int hj_halo_export(hj_ctx* ctx, void* desc);
+int hj_halo_attach(hj_ctx* ctx, const void* lower_desc, const void* upper_desc);
+int hj_halo_detach(hj_ctx* ctx);
+int hj_halo_attached(const hj_ctx* ctx);
+int hj_halo_push(hj_ctx* ctx, void* stream, int buf, int64_t col_begin, int64_t col_end, int64_t row_len);
+int hj_halo_wait(hj_ctx* ctx, void* stream, int buf, int npush);
+
 /* odeCFL3(schemeFunc, [t, t_end], y, options{factorCFL,maxStep,singleStep='on'}, schemeData)
  * ExplicitIntegration/Integration/ode_cfl_3.py:11 for one CFL-limited step on a dense array that may live
  * on the host (is_host) -- upload, dt = min(factorCFL*stepBound, t_end-t, maxStep) (:142-143), step,
@@ -204,6 +227,16 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
  * (HJ_ERR_UNSUPPORTED): step them with hj_upload + hj_step(stage_params) + hj_download.                    */
 int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
                        double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out);
+/* The same call out of place, as odeCFL3 returns a fresh y (ode_cfl_3.py:11: `t, y, schemeData = odeCFL3(...)`):
+ * reads y_in, writes y_out (may alias).  With pinned host buffers (hj_host_alloc) on a 3-D grid the step is a software
+ * pipeline -- chunked H2D, a wavefront of stage launches on plane ranges, chunked D2H -- bit-identical to the
+ * resident step.  This is what levelsetpy_b200.odeCFL3(..., singleStep='on') calls for a host array.               */
+int hj_ode_cfl3_step(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
+                     const double* y_in, double* y_out, int is_host, int comp, int use_obstacle, double* t_new,
+                     double* dt_out);
+/* Pinned (page-locked) host memory for those buffers. */
+int hj_host_alloc(int64_t bytes, void** out);
+int hj_host_free(void* p);
 
 /* termRestrictUpdate (ExplicitIntegration/Term/term_restrict_update.py:56-96): restrict the sign of the update,
  * ydot = max(ydot, 0) (sign > 0, schemeData.positive true) or min(ydot, 0) (sign < 0), fused into every stage kernel

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "_hjb200.so")
 
 HJ_MAX_DIM, HJ_MAX_PARAMS, HJ_MAX_TABLES, HJ_GHOST = 6, 96, 8, 3
+HJ_HALO_DESC_BYTES = 512
 HJ_OK, HJ_ERR_INVALID, HJ_ERR_CUDA, HJ_ERR_UNSUPPORTED, HJ_ERR_STATE, HJ_ERR_NAN = 0, -1, -2, -3, -4, -5
 BC_EXTRAPOLATE, BC_PERIODIC, BC_HALO = 0, 1, 2
 WENO_AS_SHIPPED, WENO_INTENDED, SCHEME_ENO3A, SCHEME_ENO2 = 0, 1, 2, 3
@@ -57,11 +58,20 @@ SIGNATURES = {
     "hj_memcpy": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
     "hj_stream_sync": (_i, [_vp]),
     "hj_ode_cfl3_single": (_i, [_vp, _vp, _d, _d, _d, _d, _vp, _i, _i, _i, _pd, _pd]),
+    "hj_ode_cfl3_step": (_i, [_vp, _vp, _d, _d, _d, _d, _vp, _vp, _i, _i, _i, _pd, _pd]),
+    "hj_host_alloc": (_i, [_i64, C.POINTER(_vp)]),
+    "hj_host_free": (_i, [_vp]),
     "hj_set_restrict": (_i, [_vp, _i]),
     "hj_step_rk2": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_create_batch": (_i, [C.POINTER(_vp), _i, _i, _i, _pi64, _pd, _pi, _pi, _i]),
     "hj_step_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "hj_batch_size": (_i, [_vp]),
+    "hj_halo_export": (_i, [_vp, _vp]),
+    "hj_halo_attach": (_i, [_vp, _vp, _vp]),
+    "hj_halo_detach": (_i, [_vp]),
+    "hj_halo_attached": (_i, [_vp]),
+    "hj_halo_push": (_i, [_vp, _vp, _i, _i64, _i64, _i64]),
+    "hj_halo_wait": (_i, [_vp, _vp, _i, _i]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "_hjb200.so")
-SOURCES = ["hj_api.cu", "hj_gather.cu", "hj_tma.cu"]
+SOURCES = ["hj_api.cu", "hj_gather.cu", "hj_tma.cu", "hj_halo.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++20", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "hj_ctx.h"
 #include "hj_internal.h"
 #include "hj_systems.cuh"
 
@@ -14,7 +15,7 @@ static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void hj_count_launch(int n) { g_launches += n; }
 
-static int fail(int code, const char* fmt, ...) {
+int hj_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -23,47 +24,8 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-#define CK(call)                                                                                       \
-  do {                                                                                                 \
-    cudaError_t e_ = (call);                                                                           \
-    if (e_ != cudaSuccess) return fail(HJ_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
-  } while (0)
-
-struct hj_ctx {
-  int device = 0, D = 0, weno = 0, backend = HJ_BACKEND_AUTO, system_id = HJ_SYS_NONE, nparams = 0;
-  int halo0 = 0;                 // dim 0 carries stored halo planes (slab decomposition)
-  long long pitch = 0;           // padded innermost extent
-  long long plane = 0;           // pitched elements of one dim-0 plane
-  long long elems = 0;           // pitched elements of a whole field incl. halo planes
-  long long origin = 0;          // element offset of the first interior node
-  long long nodes = 0;           // prod N
-  KGrid gp{}, gd{};              // pitched (resident fields) and dense (user arrays) views
-  KSys ks{};
-  double* vs_dev[HJ_MAX_DIM] = {};
-  double* tab_dev[HJ_MAX_TABLES] = {};
-  unsigned axes_set = 0;
-  double* buf[3] = {};           // y, y1, yHalf (base pointers incl. halo planes)
-  double* aux = nullptr;
-  double* obs = nullptr;
-  double* staging = nullptr;     // dense staging for host <-> pitched conversion
-  unsigned long long* red = nullptr;  // 4 reduction records (3 stages + scratch) + eps record
-  unsigned long long* eps = nullptr;
-  double* pinned = nullptr;      // host scratch
-  bool have_state = false, alpha_valid = false;
-  double alpha_cache[HJ_MAX_DIM] = {};
-  double step_bound_cache = 0.0;
-  int restrict_sign = 0;         // termRestrictUpdate: 0 off, +1 / -1
-  int nbatch = 0;                // > 0: batch context (dim 0 of the internal grid is the batch index)
-  double* batch_dt = nullptr;    // [nbatch] per-element dt of the current step
-  double* batch_params = nullptr;// [3][nbatch][nparams] per-stage parameter blocks
-  // pipelined host <-> device stepping (hj_ode_cfl3_single with host buffers)
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  std::vector<cudaEvent_t> ev_up, ev_done;
-  cudaEvent_t ev_start = nullptr;
-  HjTmaPlan* plan = nullptr;
-  bool plan_tried = false;
-  std::string plan_err;
-};
+#define fail hj_fail
+#define CK HJ_CK
 
 static const int RED_STRIDE = 32;  // slots per reduction record (>= HJ_REDUCE_LEN(6) = 19)
 
@@ -142,6 +104,7 @@ int hj_create(hj_ctx** out, int device, int ndim, const int64_t* N, const double
 int hj_destroy(hj_ctx* c) {
   if (!c) return HJ_OK;
   cudaSetDevice(c->device);
+  hj_halo_destroy(c);
   if (c->plan) hj_tma_plan_destroy(c->plan);
   for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
@@ -672,7 +635,7 @@ static bool can_pipeline(hj_ctx* c, int is_host) {
   return use_tma(c) && !hj_tma_plan_is_split(c->plan);
 }
 
-static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, double* y_host, int comp, int use_obs) {
+static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, const double* y_host, double* y_out, int comp, int use_obs) {
   const int N0 = c->gp.N[0];
   int P = (N0 + 15) / 16;
   if (P < 32) P = 32;
@@ -715,7 +678,7 @@ static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, double* y_host, 
       if ((r = stage_impl(c, s, 3, dt, nullptr, comp, use_obs, 0, false, false, lo(k), hi(k)))) return r;
       CK(cudaEventRecord(c->ev_done[k], s));
       CK(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
-      CK(cudaMemcpyAsync(y_host + lo(k) * plane, c->buf[0] + lo(k) * plane, (hi(k) - lo(k)) * plane * sizeof(double),
+      CK(cudaMemcpyAsync(y_out + lo(k) * plane, c->buf[0] + lo(k) * plane, (hi(k) - lo(k)) * plane * sizeof(double),
                          cudaMemcpyDeviceToHost, c->s_d2h));
     }
   }
@@ -724,16 +687,17 @@ static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, double* y_host, 
   return HJ_OK;
 }
 
-int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double factor_cfl, double max_step,
-                       double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out) {
+int hj_ode_cfl3_step(hj_ctx* c, void* stream, double t, double t_end, double factor_cfl, double max_step,
+                     const double* y_in, double* y_out, int is_host, int comp, int use_obstacle, double* t_new,
+                     double* dt_out) {
   int r = check_ready(c, true);
   if (r) return r;
-  if (!y_inout) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_single: null y");
-  if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: not available on a slab / batch context");
+  if (!y_in || !y_out) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_step: null y");
+  if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_step: not available on a slab / batch context");
   // a Flock re-derives its parameter block on each of the three RHS evaluations (flock.py:213) and its alphas are host
   // scalars of those blocks: this entry point takes neither, so it must not step one with a frozen block
   if (c->system_id == HJ_SYS_FLOCK)
-    return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_single: HJ_SYS_FLOCK needs per-stage parameter blocks; use hj_upload + hj_step(stage_params) + hj_download");
+    return fail(HJ_ERR_UNSUPPORTED, "hj_ode_cfl3_step: HJ_SYS_FLOCK needs per-stage parameter blocks; use hj_upload + hj_step(stage_params) + hj_download");
   if (factor_cfl < 0.0) return fail(HJ_ERR_INVALID, "FactorCFL must be a positive scalar double value");   // ode_cfl_set.py:104
   if (max_step < 0.0) return fail(HJ_ERR_INVALID, "MaxStep must be a positive scalar double value");       // ode_cfl_set.py:106
   double sb = 0;
@@ -744,14 +708,14 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   if (t_end - t < dt) dt = t_end - t;
   if (max_step < dt) dt = max_step;
   if (can_pipeline(c, is_host)) {
-    r = pipelined_step(c, (cudaStream_t)stream, dt, y_inout, comp, use_obstacle);
+    r = pipelined_step(c, (cudaStream_t)stream, dt, y_in, y_out, comp, use_obstacle);
     if (r) return r;
   } else {
-    r = hj_upload(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+    r = hj_upload(c, stream, HJ_FIELD_STATE, y_in, is_host);
     if (r) return r;
     r = hj_step(c, stream, t, dt, nullptr, comp, use_obstacle, 0);
     if (r) return r;
-    r = hj_download(c, stream, HJ_FIELD_STATE, y_inout, is_host);
+    r = hj_download(c, stream, HJ_FIELD_STATE, y_out, is_host);
     if (r) return r;
     if (!is_host) CK(cudaStreamSynchronize((cudaStream_t)stream));
   }
@@ -762,6 +726,25 @@ int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double f
   const double t_three_half = t_half + dt;
   if (t_new) *t_new = (1.0 / 3.0) * (t + 2 * t_three_half);
   if (dt_out) *dt_out = dt;
+  return HJ_OK;
+}
+
+int hj_ode_cfl3_single(hj_ctx* c, void* stream, double t, double t_end, double factor_cfl, double max_step,
+                       double* y_inout, int is_host, int comp, int use_obstacle, double* t_new, double* dt_out) {
+  if (!y_inout) return fail(HJ_ERR_INVALID, "hj_ode_cfl3_single: null y");
+  return hj_ode_cfl3_step(c, stream, t, t_end, factor_cfl, max_step, y_inout, y_inout, is_host, comp, use_obstacle, t_new,
+                          dt_out);
+}
+
+/* pinned host memory for the host-buffer entry points (cudaHostAlloc: both PCIe directions run at full rate and the
+ * chunked copies of the pipelined step overlap its kernels) */
+int hj_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(HJ_ERR_INVALID, "hj_host_alloc: bad argument");
+  CK(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 8), cudaHostAllocDefault));
+  return HJ_OK;
+}
+int hj_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
   return HJ_OK;
 }
 

@@ -337,6 +337,33 @@ class Engine:
                                             C.byref(tn), C.byref(dt)))
         return tn.value, flat, dt.value
 
+    def pinned_out(self):
+        """Next of this engine's three pinned host arrays (``nodes`` doubles each), handed out round-robin: what the
+        host-buffer odeCFL3 path returns its ``y`` in.  An array stays untouched until three further calls -- long
+        enough for the driver's ``yLast`` / ``y`` pattern (hji_solver.py:538-599) -- copy it to keep it longer."""
+        ring = self.__dict__.setdefault("_pin_ring", [])
+        if len(ring) < 3:
+            p = C.c_void_p()
+            L.check(self.lib.hj_host_alloc(self.nodes * 8, C.byref(p)))
+            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.nodes,))
+            weakref.finalize(self, self.lib.hj_host_free, p)
+            ring.append(arr)
+            self._pin_next = 0
+            return arr
+        self._pin_next = (self._pin_next + 1) % 3
+        return ring[self._pin_next]
+
+    def ode_cfl3_step(self, t, t_end, factor_cfl, max_step, y_in, y_out, comp=L.COMP_NONE, use_obstacle=False):
+        """hj_ode_cfl3_step on host numpy arrays (or torch CUDA tensors): reads y_in, writes y_out.  (t_new, dt)."""
+        fin, pin, host_in = self._flat(y_in)
+        fout, pout, host_out = self._flat(y_out)
+        assert host_in == host_out, "y_in and y_out must both be host arrays or both be CUDA tensors"
+        tn, dt = C.c_double(), C.c_double()
+        L.check(self.lib.hj_ode_cfl3_step(self.h, self.stream(), float(t), float(t_end), float(factor_cfl),
+                                          float(max_step), pin, pout, host_in, int(comp), int(bool(use_obstacle)),
+                                          C.byref(tn), C.byref(dt)))
+        return tn.value, dt.value
+
     def sync(self):
         L.check(self.lib.hj_stream_sync(self.stream()))
 
@@ -367,6 +394,29 @@ class Engine:
 
     def fill_edge_halo(self, which, side):
         L.check(self.lib.hj_fill_edge_halo(self.h, self.stream(), int(which), int(side)))
+
+    # peer-memory halos (hj_halo_*): descriptors are plain bytes the caller moves between ranks
+    def halo_export(self):
+        buf = C.create_string_buffer(L.HJ_HALO_DESC_BYTES)
+        L.check(self.lib.hj_halo_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def halo_attach(self, lower, upper):
+        """``lower`` / ``upper``: the neighbours' ``halo_export()`` bytes, or None where the slab has no neighbour."""
+        keep = [C.create_string_buffer(d, L.HJ_HALO_DESC_BYTES) if d is not None else None for d in (lower, upper)]
+        L.check(self.lib.hj_halo_attach(self.h, *[C.cast(k, C.c_void_p) if k is not None else None for k in keep]))
+
+    def halo_push(self, which, cols=None):
+        """Push my edge planes of RK buffer ``which`` into the neighbours' halos, ordered behind the current stream.
+        ``cols`` = (begin, end, row_len): only those columns of every row (see hj_halo_push)."""
+        b, e, n = cols if cols is not None else (0, 0, 0)
+        L.check(self.lib.hj_halo_push(self.h, self.stream(), int(which), int(b), int(e), int(n)))
+
+    def halo_wait(self, which, npush=1):
+        L.check(self.lib.hj_halo_wait(self.h, self.stream(), int(which), int(npush)))
+
+    def halo_detach(self):
+        L.check(self.lib.hj_halo_detach(self.h))
 
     def eps_prepass(self, which):
         """intended WENO: per-dim raw max(D1^2) of buffer ``which`` -> torch int64 view (D entries, ordered

@@ -112,6 +112,23 @@ def _ode_cfl(order, schemeFunc, tspan, y0, options, schemeData):
     t = tspan[0]
     steps = 0
     startTime = cputime()
+    single = isfield(options, "singleStep") and strcmp(options.singleStep, "on")
+    if (single and order == 3 and isinstance(y0, np.ndarray) and not ad.time_varying
+            and tspan[1] - t >= small * np.abs(tspan[1])):
+        # the driver's call (hji_solver.py:542: one CFL step per odeCFL3 call on a host array): one C-ABI call that
+        # pipelines upload, the three stage kernels and download (hj_ode_cfl3_step); y comes back in one of the
+        # engine's pinned arrays (Engine.pinned_out: valid until three further calls)
+        eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(grid))))
+        y = eng.pinned_out()
+        eng.set_restrict(sign)
+        try:
+            t, _ = eng.ode_cfl3_step(t, tspan[1], options.factorCFL, options.maxStep,
+                                     np.ascontiguousarray(y0, dtype=np.float64).reshape(-1), y)
+        finally:
+            eng.set_restrict(0)
+        if isfield(options, "stats") and strcmp(options.stats, "on"):
+            info("1 steps in %.2g seconds from  %.2f to %.2f." % (cputime() - startTime, tspan[0], t))
+        return t, y.reshape(tuple(y0.shape)), schemeData
     eng.upload(y0)
     eng.set_restrict(sign)
     try:

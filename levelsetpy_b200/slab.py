@@ -13,8 +13,12 @@ max_x alpha_d -- hence dt -- is state-only for every registered system: it is ma
 computed identically on every rank with the reference's own host arithmetic (artificial_diss_glf.py:104-109,
 ode_cfl_3.py:142-143).  No other data-path collective exists.
 
-The transport is a small strategy object so the same solver runs under ``torch.distributed`` (NCCL on GPUs, gloo
-in the CPU tests) and as several slabs inside one process (``LocalWorld``: the single-GPU test of the halo path).
+Transport of the halo planes: on CUDA contexts the rank PUSHES its edge planes into the neighbours' stored halos
+through peer memory (C-ABI hj_halo_*: CUDA IPC handles exchanged once, then one copy-engine transfer per neighbour and
+stage, signalled by a counter -- no SM copy kernel contends with the stage kernel that runs under the transfer);
+``transport="p2p"`` keeps the ``torch.distributed`` send/recv path (NCCL on GPUs, gloo in the CPU tests).  The host-side
+group is only used to move the descriptors and for the one-off max-allreduce.  ``LocalWorld`` runs several slabs inside
+one process (the single-GPU test of the halo path) over the same two transports.
 """
 import numpy as np
 
@@ -27,8 +31,6 @@ from .utilities import isfield, warn
 __all__ = ["partition", "SlabSolver", "DistComm", "LocalWorld"]
 
 GHOST = L.HJ_GHOST
-# developer switch for attribution runs: exchange first, then compute (the protocol of the gather / intended paths)
-_NO_OVERLAP = bool(int(__import__("os").environ.get("HJ_SLAB_NO_OVERLAP", "0")))
 
 
 def partition(n0, world):
@@ -95,6 +97,15 @@ class DistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def allgather_bytes(self, b):
+        """Every rank's ``bytes`` object, in rank order."""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, b, group=self.group)
+        return out
+
 
 class _LocalComm:
     """One member of a LocalWorld: exchanges are deferred to the world, which copies between its slabs."""
@@ -109,7 +120,10 @@ class SlabSolver:
     schemeData: the reference's bundle (grid = the GLOBAL grid).  ``comm``: DistComm() by default.
     ``engine_factory(grid, weno, device, slab, backend)`` builds the per-slab context (default: the CUDA Engine)."""
 
-    def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None):
+    def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None, transport="auto", overlap=True):
+        """``transport``: "peer" (copy-engine pushes into peer memory, hj_halo_*), "p2p" (send/recv of the group) or
+        "auto" (peer wherever the per-slab engine offers it).  ``overlap=False``: exchange first, then compute (the
+        protocol of the gather / intended paths; attribution runs)."""
         sd = schemeData
         for f in ("grid", "hamFunc", "partialFunc"):
             assert isfield(sd, f), "%s not in bundle thisschemeData" % f
@@ -134,6 +148,31 @@ class SlabSolver:
         self._ranged = None
         self._tables = list(enumerate(self.adapter.tables(g)))
         self.shape = (self.n0,) + tuple(int(x) for x in np.asarray(g.N).reshape(-1)[1:])
+        self._no_overlap = not overlap
+        self.mode = "full"        # attribution runs (bench.py): "compute" = no exchange, "comm" = no stage kernels
+        if transport not in ("auto", "peer", "p2p"):
+            raise ValueError("transport must be 'auto', 'peer' or 'p2p', got %r" % (transport,))
+        can_peer = hasattr(self.eng, "halo_export")
+        if transport == "peer" and not can_peer:
+            raise NotImplementedError("the per-slab engine has no peer-memory halo transport")
+        self.peer = can_peer and transport != "p2p"
+        if self.peer and hasattr(self.comm, "allgather_bytes"):
+            self.attach_peers(self.comm.allgather_bytes(self.eng.halo_export()))
+
+    def attach_peers(self, descs):
+        """``descs``: every rank's ``Engine.halo_export()`` bytes in rank order (moved by the host-side group)."""
+        pick = lambda r: descs[r] if (r is not None and r != self.rank) else None
+        self.eng.halo_attach(pick(self.lo_peer), pick(self.hi_peer))
+
+    def close(self):
+        """Collective: unmap the neighbours' buffers on every rank BEFORE any rank frees its own (memory exported through
+        CUDA IPC must outlive its importers), then destroy the context."""
+        if self.peer and hasattr(self.eng, "halo_detach"):
+            self.eng.halo_detach()
+            if hasattr(self.comm, "barrier"):
+                self.comm.barrier()
+        if hasattr(self.eng, "close"):
+            self.eng.close()
 
     # ------------------------------------------------------------------ fields
     def upload(self, slab, field=L.FIELD_STATE):
@@ -184,11 +223,31 @@ class SlabSolver:
         if self.hi_peer is None:
             self.eng.fill_edge_halo(b, 1)
 
+    def post(self, b):
+        """Start refreshing the neighbours' (peer transport) / my (p2p) halos of buffer b; work queued on the current
+        stream afterwards runs under the transfer until ``wait``."""
+        if self.mode == "compute":
+            return ("none", b)
+        if self.peer:
+            self.eng.halo_push(b)
+            return ("peer", b)
+        return self.comm.post(*self.halo_ops(b))
+
+    def wait(self, handle):
+        if handle is not None and handle[0] == "none":
+            return
+        if handle is not None and handle[0] == "peer":
+            self.eng.halo_wait(handle[1])
+        else:
+            self.comm.wait(handle)
+
     def exchange(self, b):
         if isinstance(self.comm, _LocalComm):
             raise RuntimeError("slabs of a LocalWorld are stepped through LocalWorld.step")
-        sends, recvs = self.halo_ops(b)
-        self.comm.exchange(sends, recvs)
+        if self.peer:
+            self.wait(self.post(b))
+        else:
+            self.comm.exchange(*self.halo_ops(b))
         self.finish_halos(b)
 
     # ------------------------------------------------------------------ dt
@@ -239,6 +298,8 @@ class SlabSolver:
         """Stage kernel(s) on this slab; the halos of the buffer it reads must already be current (pass 1 of a
         product system's stage reads none)."""
         t, dt, blocks = self._step
+        if self.mode == "comm":
+            return
         if self.weno == "intended" and which_pass != 2:
             eps = self.eng.eps_prepass(self.eng.stage_io(stage)[0])
             if self.world > 1:
@@ -249,19 +310,19 @@ class SlabSolver:
     def overlapped(self):
         """Product systems on the dimension-split path under as_shipped WENO: the halo exchange of a stage runs
         under its first kernel.  ('intended' needs the halos for the WENO eps pre-pass, so it exchanges first.)"""
-        return self.two_pass() and hasattr(self.comm, "post")
+        return self.two_pass() and (self.peer or hasattr(self.comm, "post"))
 
     def ranged(self):
         """Whole 3-D systems on the plane-ring backend under as_shipped WENO: the planes whose dim-0 stencil stays
         inside the slab are advanced under the halo exchange, the two 3-plane edge ranges after it (hj_stage_range)."""
         if self._ranged is None:
-            self._ranged = bool(self.weno != "intended" and not _NO_OVERLAP and self.eng.D == 3 and self.n0 > 2 * GHOST
+            self._ranged = bool(self.weno != "intended" and not self._no_overlap and self.eng.D == 3 and self.n0 > 2 * GHOST
                                 and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
         return self._ranged
 
     def two_pass(self):
         if self._overlap is None:
-            self._overlap = bool(self.weno != "intended" and not _NO_OVERLAP
+            self._overlap = bool(self.weno != "intended" and not self._no_overlap
                                  and getattr(self.eng, "is_split", lambda: False)())
         return self._overlap
 
@@ -271,21 +332,26 @@ class SlabSolver:
         for stage in (1, 2, 3):
             b = self.eng.stage_io(stage)[0]
             if self.overlapped():
-                reqs = self.comm.post(*self.halo_ops(b))
+                reqs = self.post(b)
                 self.run_stage(stage, comp, use_obstacle, which_pass=1)
-                self.comm.wait(reqs)
+                self.wait(reqs)
                 self.finish_halos(b)
                 self.run_stage(stage, comp, use_obstacle, which_pass=2)
-            elif self.ranged() and hasattr(self.comm, "post"):
+            elif self.ranged() and (self.peer or hasattr(self.comm, "post")):
                 t_, dt_, blocks = self._step
-                reqs = self.comm.post(*self.halo_ops(b))
-                self.eng.stage_range(stage, GHOST, self.n0 - GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
-                self.comm.wait(reqs)
+                reqs = self.post(b)
+                if self.mode != "comm":
+                    self.eng.stage_range(stage, GHOST, self.n0 - GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                self.wait(reqs)
                 self.finish_halos(b)
-                self.eng.stage_range(stage, 0, GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
-                self.eng.stage_range(stage, self.n0 - GHOST, self.n0, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                if self.mode != "comm":
+                    self.eng.stage_range(stage, 0, GHOST, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                    self.eng.stage_range(stage, self.n0 - GHOST, self.n0, t_, dt_, blocks[stage - 1], comp, use_obstacle)
             else:
-                self.exchange(b)
+                if self.mode != "compute":
+                    self.exchange(b)
+                else:
+                    self.finish_halos(b)
                 self.run_stage(stage, comp, use_obstacle)
         return rk3_times(t, dt)[2], dt
 
@@ -297,9 +363,15 @@ class LocalWorld:
 
     poison_halos = False     # tests: NaN the halo planes a stage will receive before its pass 1 runs
 
-    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None):
+    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None, transport="auto"):
         self.world = int(world)
-        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory) for r in range(self.world)]
+        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory, transport)
+                      for r in range(self.world)]
+        self.peer = all(s.peer for s in self.slabs) and self.world > 1
+        if self.peer:                       # contexts of one process attach by pointer (hj_halo_attach)
+            descs = [s.eng.halo_export() for s in self.slabs]
+            for s in self.slabs:
+                s.attach_peers(descs)
 
     def upload(self, data, field=L.FIELD_STATE):
         for s in self.slabs:
@@ -309,6 +381,14 @@ class LocalWorld:
         return np.concatenate([s.download() for s in self.slabs], axis=0)
 
     def _exchange(self, b):
+        if self.peer:                       # every push is queued before the first wait: one stream serves all slabs
+            for s in self.slabs:
+                s.eng.halo_push(b)
+            for s in self.slabs:
+                s.eng.halo_wait(b)
+            for s in self.slabs:
+                s.finish_halos(b)
+            return
         for s in self.slabs:
             sends, _ = s.halo_ops(b)
             for t, peer, tag in sends:

@@ -26,7 +26,8 @@ def _grid3(lsp, N, pd):
 @pytest.mark.parametrize("pd", [[2], [0, 2]])
 @pytest.mark.parametrize("weno", ["as_shipped", "intended"])
 @pytest.mark.parametrize("backend", ["gather", "tma"])
-def test_slabs_match_single_domain(lsp, world, pd, weno, backend):
+@pytest.mark.parametrize("transport", ["peer", "p2p"])
+def test_slabs_match_single_domain(lsp, world, pd, weno, backend, transport):
     from levelsetpy_b200 import _lib as L
     from levelsetpy_b200.slab import LocalWorld
     g, d0 = _grid3(lsp, [26, 37, 34], pd)
@@ -35,7 +36,8 @@ def test_slabs_match_single_domain(lsp, world, pd, weno, backend):
     o = osys.DubinsVehicleRel(g, 5, 1)
     osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
     be = L.BACKEND_GATHER if backend == "gather" else L.BACKEND_TMA
-    w = LocalWorld(sd, world, backend=be)
+    w = LocalWorld(sd, world, backend=be, transport=transport)   # peer: hj_halo_push / hj_halo_wait between contexts
+    assert w.peer == (transport == "peer" and world > 1)
     w.poison_halos = True     # ranged mode (TMA, as_shipped): the interior range runs on NaN halos and must not read them
     w.upload(d0)
     t, to, yo = 0.0, 0.0, d0.reshape(-1, 1)

@@ -149,14 +149,16 @@ def test_device_restrict_on_split_path(lsp):
 
 @pytest.mark.gpu
 def test_device_hjipde_solve_comp_zero(lsp):
-    """HJIPDE_solve(compMethod='zero'): the driver's termRestrictUpdate(positive=0) swap (hji_solver.py:438-442) on the
-    resident state, against the oracle's restricted odeCFL3 driven by the same time loop."""
+    """HJIPDE_solve(compMethod='zero', extraArgs.restrictUpdate=True): the termRestrictUpdate(positive=0) swap the
+    driver sets up at hji_solver.py:438-442 (and, as shipped, never uses: the default 'zero' equals 'set', see
+    tests/test_gpu_driver.py) on the resident state, against the oracle's restricted odeCFL3 in the same time loop."""
     gold = load_golden("restrict_rk2")
     g, mk, d0 = _case(lsp, gold, "air3d")
     s = mk(lsp)
     sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation))
     tau = np.array([0.0, 0.05, 0.1])
-    data, tau_out, extra = lsp.HJIPDE_solve(d0, tau, sd, "zero", lsp.Bundle(dict(quiet=True, keepLast=True)))
+    data, tau_out, extra = lsp.HJIPDE_solve(d0, tau, sd, "zero", lsp.Bundle(dict(quiet=True, keepLast=True,
+                                                                                 restrictUpdate=True)))
     o = mk(osys)
     osd = orc.OracleSchemeData(grid=g, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
     y, dts = d0.flatten(), []

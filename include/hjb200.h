@@ -177,6 +177,14 @@ int hj_stage(hj_ctx* ctx, void* stream, int stage, double t, double dt, const do
 int hj_stage_pass(hj_ctx* ctx, void* stream, int stage, int which_pass, double t, double dt, const double* params,
                   int comp, int use_obstacle, int want_reduce);
 int hj_is_split(const hj_ctx* ctx);
+/* Pass 2 in pieces: the trailing dims of a product system are one flattened "vector" axis without stencil (length
+ * *vlen doubles, the pitched stride of the last leading dim); hj_stage_pass_cols runs pass 2 of `stage` on columns
+ * [col_begin, col_end) of it only (multiples of *quantum; col_end may be *vlen).  Disjoint pieces covering the axis
+ * equal hj_stage_pass(2) bit for bit.  A slab job pushes each finished piece of its edge planes to the neighbours
+ * (hj_halo_push with the same columns) while the next piece is computed.  want_reduce as for hj_stage_range.      */
+int hj_split_cols(hj_ctx* ctx, int64_t* vlen, int* quantum);
+int hj_stage_pass_cols(hj_ctx* ctx, void* stream, int stage, int64_t col_begin, int64_t col_end, double t, double dt,
+                       const double* params, int comp, int use_obstacle, int want_reduce);
 /* Whole (non-product) systems on the plane-ring backend: run stage `stage` on planes [z_begin, z_end) of the marched
  * dim D-3 only (dim 0 of a 3-D grid, i.e. the slab dim).  A slab job posts its halo exchange, advances the planes
  * whose stencil stays inside the slab ([3, N0-3)) under it, and advances the two 3-plane edge ranges once the halos

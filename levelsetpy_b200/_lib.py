@@ -48,6 +48,8 @@ SIGNATURES = {
     "hj_stage": (_i, [_vp, _vp, _i, _d, _d, _vp, _i, _i, _i]),
     "hj_stage_pass": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _i, _i, _i]),
     "hj_is_split": (_i, [_vp]),
+    "hj_split_cols": (_i, [_vp, _pi64, _pi]),
+    "hj_stage_pass_cols": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _i, _i, _i]),
     "hj_stage_range": (_i, [_vp, _vp, _i, _i64, _i64, _d, _d, _vp, _i, _i, _i]),
     "hj_stage_io": (_i, [_vp, _i, _pi, _pi]),
     "hj_eps_prepass": (_i, [_vp, _vp, _i, C.POINTER(_vp)]),

@@ -34,12 +34,11 @@ def _deps_mtime():
     return m
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    extra = os.environ.get("HJ_EXTRA_NVCC_FLAGS", "").split()      # developer hook (tile-shape experiments)
-    cmd = [nvcc()] + ARCH + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src, verbose, extra=(), objdir=OBJ):
+    obj = os.path.join(objdir, src.replace(".cu", ".o"))
+    cmd = [nvcc()] + ARCH + FLAGS + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(OBJ, src + ".log")
+    log = os.path.join(objdir, src + ".log")
     with open(log, "w") as fh:
         fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
@@ -55,11 +54,26 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [nvcc()] + ARCH + ["-shared", "-o", SO] + objs + ["-cudart", "static"]
+    return _link(objs, SO)
+
+
+def _link(objs, so):
+    cmd = [nvcc()] + ARCH + ["-shared", "-o", so] + objs + ["-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])
-    return SO
+    return so
+
+
+def build_variant(tag, defines):
+    """Developer tooling (tools/build_variants.py): the library with other tile shapes, as _hjb200_<tag>.so.  Only
+    hj_tma.cu depends on the tile-shape macros; the other objects are the production ones."""
+    build()
+    vdir = os.path.join(OBJ, "variant_" + tag)
+    os.makedirs(vdir, exist_ok=True)
+    obj = _compile("hj_tma.cu", False, ["-D%s" % d for d in defines], vdir)
+    objs = [obj if s == "hj_tma.cu" else os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    return _link(objs, os.path.join(HERE, "_hjb200_%s.so" % tag))
 
 
 if __name__ == "__main__":

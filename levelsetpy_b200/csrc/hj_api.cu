@@ -466,7 +466,7 @@ static bool use_tma(hj_ctx* c) {
 // (ode_cfl_2.py: y = 0.5 (y + (y1 + dt f(y1)))), which is the stage-3 kernel reading buffer 1
 static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const double* params, int comp, int use_obs,
                       int want_reduce, bool run_prepass, bool batch = false, int zbeg = 0, int zend = 0,
-                      int which_pass = 0) {
+                      int which_pass = 0, long long col_begin = 0, long long col_end = 0) {
   static const int in_[5] = {0, 0, 1, 2, 1}, out_[5] = {0, 1, 2, 0, 0};
   const bool final_stage = stage >= 3;
   const int slot = stage == 4 ? 1 : stage - 1;   // reduction record / batch parameter set of this stage
@@ -508,7 +508,8 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
     CK(hj_launch_maxd1sq(c->gp, st.in, c->eps, -1, s));
   }
   if (use_tma(c)) {
-    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s, zbeg, zend, which_pass));
+    CK(hj_launch_stage_tma(c->plan, c->system_id, c->weno, c->gp, ks, st, in_[stage], s, zbeg, zend, which_pass, col_begin,
+                           col_end));
   } else if (c->nbatch) {
     return fail(HJ_ERR_UNSUPPORTED, "batch contexts run on the TMA backend only: %s", c->plan_err.c_str());
   } else {
@@ -570,6 +571,35 @@ int hj_stage_pass(hj_ctx* c, void* stream, int stage, int which_pass, double t, 
   CK(cudaSetDevice(c->device));
   return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0, false, 0, 0,
                     which_pass);
+}
+
+int hj_split_cols(hj_ctx* c, int64_t* vlen, int* quantum) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  long long v = 0;
+  int q = 0;
+  if (c->system_id == HJ_SYS_NONE || !c->buf[0] || !use_tma(c) || !hj_tma_plan_cols(c->plan, &v, &q))
+    return fail(HJ_ERR_UNSUPPORTED, "hj_split_cols: this context does not advance a product system on the dimension-split path");
+  if (vlen) *vlen = v;
+  if (quantum) *quantum = q;
+  return HJ_OK;
+}
+
+int hj_stage_pass_cols(hj_ctx* c, void* stream, int stage, int64_t col_begin, int64_t col_end, double t, double dt,
+                       const double* params, int comp, int use_obstacle, int want_reduce) {
+  (void)t;
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_stage_pass_cols: not available on a batch context");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage_pass_cols: no resident state (hj_upload first)");
+  if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage_pass_cols: stage must be 1..3");
+  CK(cudaSetDevice(c->device));
+  int64_t v = 0;
+  int q = 0;
+  if ((r = hj_split_cols(c, &v, &q))) return r;
+  if (col_begin < 0 || col_begin >= col_end || col_end > v || col_begin % q || (col_end % q && col_end != v))
+    return fail(HJ_ERR_INVALID, "hj_stage_pass_cols: need 0 <= col_begin < col_end <= %lld, both multiples of %d (col_end may be the axis length)", (long long)v, q);
+  return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, false, false, 0, 0, 2,
+                    col_begin, col_end);
 }
 
 int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_params, int comp, int use_obstacle,

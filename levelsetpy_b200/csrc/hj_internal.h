@@ -33,7 +33,8 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g_pitched, int system_id, int weno, d
 void hj_tma_plan_destroy(HjTmaPlan* p);
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
                                 const KStage& st, int in_buf, cudaStream_t s, int zbeg = 0, int zend = 0,
-                                int which_pass = 0);
+                                int which_pass = 0, long long col_begin = 0, long long col_end = 0);
+bool hj_tma_plan_cols(const HjTmaPlan* p, long long* vlen, int* quantum);
 bool hj_tma_plan_is_split(const HjTmaPlan* p);
 
 void hj_count_launch(int n);

@@ -24,29 +24,56 @@ using namespace hjtma;
 //   4 x 7 tile and a 6-slot ring (2 CTAs/SM) measured best: 53.6 / 65.5 / 65.3 ms per launch at 41^6 against
 //   73.7 / 90.5 / 90.0 ms for 64-byte rows with a 7 x 7 tile.
 using ProdCfg = TmaCfg<8, 2, 1>;
+// whole systems whose planes are a few tiles wide run a ghost-warp configuration (hj_tma_kernel.cuh): the Flock batch
+// (101 x 101 planes, rows of 101 = one 102-wide tile, 13 tiles of 8 rows; 13 consumer warps + the ghost warp, 1 CTA/SM)
+template <class Sys> struct WholeCfg { using type = ProdCfg; };
+#ifndef HJ_FB_TY
+#define HJ_FB_TY 8
+#define HJ_FB_TXP 51
+#define HJ_FB_MINB 1
+#define HJ_FB_GW 1
+#define HJ_FB_XPAD 0
+#define HJ_FB_R 8
+#endif
+template <> struct WholeCfg<SysFlockBatch> { using type = TmaCfg<HJ_FB_R, HJ_FB_MINB, 1, HJ_FB_TY, HJ_FB_TXP, false, 143, HJ_FB_GW, HJ_FB_XPAD>; };
 template <class Sys> struct SplitCfg;
-// tile shapes of the 6-D pair; the -D overrides are a developer hook (HJ_EXTRA_NVCC_FLAGS in build.py)
+// tile shapes of the 6-D pair; the -D overrides are a developer hook (HJ_EXTRA_NVCC_FLAGS in build.py).
+//   pass 1: 41 x 41 planes as two 42 x 21 tiles (14 consumer warps + two ghost warps on alternate planes, 1 CTA/SM,
+//           94 % of the lanes on nodes, slot rows padded to a conflict-free 58 doubles; measured on 8 x 41^5: 5.8 ms
+//           against 9.9 ms for the 42 x 12 tile without ghost warps, which ran every plane in the general body, 7.9 ms
+//           with one ghost warp -- the fill of one plane is a latency chain of about a plane time);
+//   pass 2: 8 vector pairs x (4 x 7) tile, 7 consumer warps + the ghost warp, 2 CTAs/SM.
 #ifndef HJ_P2_R
 #define HJ_P2_R 6
 #define HJ_P2_MINB 2
 #define HJ_P2_VP 8
 #define HJ_P2_TA 4
 #define HJ_P2_TB 7
+#define HJ_P2_GW 1
+#define HJ_P2_OPT 0
 #endif
 #ifndef HJ_P1_TY
-#define HJ_P1_MINB 2
-#define HJ_P1_TY 12
+#define HJ_P1_MINB 1
+#define HJ_P1_TY 21
 #define HJ_P1_TXP 21
+#define HJ_P1_GW 2
+#define HJ_P1_XPAD 8
+#define HJ_P1_R 8
+#define HJ_P1_OPT 143
 #endif
-#define HJ_P2_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, HJ_P2_TA, HJ_P2_TB>
-#define HJ_P1_6D TmaCfg<8, HJ_P1_MINB, 1, HJ_P1_TY, HJ_P1_TXP>
+#define HJ_P2_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, HJ_P2_TA, HJ_P2_TB, HJ_P2_GW, HJ_P2_OPT>
+#define HJ_P1_6D TmaCfg<HJ_P1_R, HJ_P1_MINB, 1, HJ_P1_TY, HJ_P1_TXP, false, HJ_P1_OPT, HJ_P1_GW, HJ_P1_XPAD>
 // P2T: pass-2 tile for THIN dim-0 extents (slabs of a multi-GPU job: 41 planes over 8 ranks are 5..6 planes each, of
 // which a 4-row tile wastes a third); chosen per context by pick_thin() below
 #define HJ_P2T_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, 6, 5>
 template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; using P2T = HJ_P2T_6D; };
+#ifndef HJ_P1_4D_GW
+#define HJ_P1_4D_GW 0
+#define HJ_P2_4D_GW 0
+#endif
 template <> struct SplitCfg<SysDoubleIntPair> {
-  using P1 = TmaCfg<8, 2, 1, 9, 27>;
-  using P2 = VecCfg<2, 8, 2, 16, 16, 1>;
+  using P1 = TmaCfg<8, 2, 1, 9, 27, false, 143, HJ_P1_4D_GW>;
+  using P2 = VecCfg<2, 8, 2, 16, 16, 1, HJ_P2_4D_GW>;
   using P2T = P2;
 };
 // rows of dim 0 a tiling of height `ta` processes per useful row
@@ -127,9 +154,9 @@ struct TmaLauncher {
     const CUtensorMap& tm = p->tmap[in_buf];
     launches = 1;
     switch (st.stage) {
-      case 1: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 1, ProdCfg>(p, tm, g, ks, st, s);
-      case 2: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 2, ProdCfg>(p, tm, g, ks, st, s);
-      case 3: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 3, ProdCfg>(p, tm, g, ks, st, s);
+      case 1: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 1, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
+      case 2: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 2, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
+      case 3: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 3, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
       default: return cudaErrorNotSupported;
     }
   }
@@ -185,7 +212,7 @@ struct TmaLauncher {
 
 // tile shapes of a system's kernels, for the plan
 struct PlanShape {
-  int txp = ProdCfg::TXP, ty = ProdCfg::TY;
+  int txp = ProdCfg::TXP, ty = ProdCfg::TY, bw = ProdCfg::BW;
   bool split = false, thin = false;
   int n0 = 0;
   int ns = 0, vb = 0, ta = 0, tb = 0;
@@ -195,10 +222,13 @@ struct PlanShape {
       using P1 = typename SplitCfg<Sys>::P1;
       using P2 = typename SplitCfg<Sys>::P2;
       using P2T = typename SplitCfg<Sys>::P2T;
-      txp = P1::TXP; ty = P1::TY;
+      txp = P1::TXP; ty = P1::TY; bw = P1::BW;
       split = true;
       thin = pick_thin<P2, P2T>(n0);
       ns = P2::NS; vb = P2::VB; ta = thin ? P2T::TA : P2::TA; tb = thin ? P2T::TB : P2::TB;
+    } else {
+      using W = typename WholeCfg<Sys>::type;
+      txp = W::TXP; ty = W::TY; bw = W::BW;
     }
   }
 };
@@ -212,6 +242,7 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   if (!hj_dispatch_system(system_id, shape)) { snprintf(err, errlen, "unknown system"); return nullptr; }
   const int TY = tile_y > 0 ? tile_y : shape.ty;
   const int TX = 2 * shape.txp;
+  const int BWD = shape.bw;                            // slot row = TX + 8 (+ XPAD) doubles
   if (D < 3) { snprintf(err, errlen, "2-D grids use the gather backend"); return nullptr; }
   if (hj_system_ndim(system_id) != D) { snprintf(err, errlen, "system/grid dim mismatch"); return nullptr; }
   PFN_encodeTiled enc = get_encode();
@@ -255,7 +286,7 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
   for (int bidx = 0; bidx < 4; ++bidx) {                    // 0..2: haloed boxes on the RK buffers; 3: y0 tile on buffer 0
     cuuint64_t dims[3] = {(cuuint64_t)NX, (cuuint64_t)NY, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 8, (cuuint64_t)pitch * NY * 8};
-    cuuint32_t box[3] = {(cuuint32_t)(bidx < 3 ? TX + 8 : TX), (cuuint32_t)(bidx < 3 ? TY + 6 : TY), 1};
+    cuuint32_t box[3] = {(cuuint32_t)(bidx < 3 ? BWD : TX), (cuuint32_t)(bidx < 3 ? TY + 6 : TY), 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(bidx < 3 ? &p->tmap[bidx] : &p->tmap_y0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                      (void*)bufs[bidx < 3 ? bidx : 0], dims, strides, box, es,
@@ -277,6 +308,9 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
     const long long planes0 = g.N[0] + (halo0 ? 2 * HJ_GHOST : 0);
     VecGeom& vg = p->vgeo;
     vg.nvc = (int)((V + shape.vb - 1) / shape.vb);
+    vg.vc0 = 0;
+    p->vb = shape.vb;
+    p->vlen = V;
     vg.nta = (g.N[0] + shape.ta - 1) / shape.ta;
     vg.ntb = NS == 3 ? (g.N[1] + shape.tb - 1) / shape.tb : 1;
     vg.cz = g.N[MD];
@@ -323,9 +357,25 @@ HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* c
 void hj_tma_plan_destroy(HjTmaPlan* p) { delete p; }
 bool hj_tma_plan_is_split(const HjTmaPlan* p) { return p && p->split; }
 
+bool hj_tma_plan_cols(const HjTmaPlan* p, long long* vlen, int* quantum) {
+  if (!p || !p->split) return false;
+  if (vlen) *vlen = p->vlen;
+  if (quantum) *quantum = p->vb;
+  return true;
+}
+
 cudaError_t hj_launch_stage_tma(HjTmaPlan* plan, int system_id, int weno, const KGrid& g, const KSys& ks,
-                                const KStage& st, int in_buf, cudaStream_t s, int zbeg, int zend, int which_pass) {
+                                const KStage& st, int in_buf, cudaStream_t s, int zbeg, int zend, int which_pass,
+                                long long col_begin, long long col_end) {
   HjTmaPlan sub;
+  if (col_end > col_begin) {       // pass 2 on columns [col_begin, col_end) of the vector axis only
+    if (!plan->split || which_pass != 2 || col_begin % plan->vb) return cudaErrorInvalidValue;
+    sub = *plan;
+    sub.vgeo.vc0 = (int)(col_begin / plan->vb);
+    const long long c1 = (col_end + plan->vb - 1) / plan->vb;
+    sub.vblocks = plan->vblocks / plan->vgeo.nvc * (c1 - sub.vgeo.vc0);
+    plan = &sub;
+  }
   if (zend > zbeg) {               // advance only planes [zbeg, zend) of Z (pipelined host <-> device stepping)
     if (plan->split) return cudaErrorNotSupported;
     sub = *plan;

@@ -42,9 +42,23 @@ struct TmaGeom {
 //   8  fast march software-pipelined across dims (see PIPE in the plane body; +2 % on stage 3)
 // 128  fast march specialised for the common epilogue (SIMPLE)
 //  16/32/64  tuning harness only: no arithmetic / every load hits L2 / no store (bound-finding experiments)
-template <int R_, int MINB_, int UNROLL_, int TY_ = 16, int TXP_ = 16, bool SEQ_ = false, int OPT_ = 143>
+//
+// GW_ (ghost warp): one extra warp per CTA writes the extrapolated / periodic ghost cells of every landed plane INTO its
+// ring slot (the columns / rows the TMA unit zero-filled), so that tiles touching the domain boundary march through the
+// same ghost-free FAST body as interior tiles.  Made for planes that are one or two tiles wide (41 x 41, 101 x 101: the
+// trailing block of the 6-D pair, the Flock batch), where EVERY tile touches the boundary.  Consumers then wait on a
+// second barrier per slot (ready[s], armed by the ghost warp) instead of the TMA barrier.
+//
+// XPAD_: extra columns loaded at the right end of every slot row.  A row of the slot is TX + 8 + XPAD doubles; thread
+// pair t of tile row r reads the 16-byte bank group (t + r (4 + XPAD / 2) + 2) mod 8, so a quarter-warp that straddles
+// two tile rows (TXP not a multiple of 8: the 21-pair rows of 41-wide planes) hits 2-way bank conflicts unless
+// XPAD = 8 makes the row-to-row shift a whole 128 bytes.
+template <int R_, int MINB_, int UNROLL_, int TY_ = 16, int TXP_ = 16, bool SEQ_ = false, int OPT_ = 143, int GW_ = 0,
+          int XPAD_ = 0>
 struct TmaCfg {
   static constexpr int OPT = OPT_;
+  static constexpr int NGW = GW_;          // ghost warps (0 = none; 2: they take alternate planes)
+  static constexpr bool GW = GW_ > 0;
   static constexpr bool SEQ = SEQ_;       // evaluate the stencil one dim at a time (smaller live set)
   static constexpr int R = R_;            // ring slots (planes z+1..z+3 are needed, the rest is prefetch distance)
   static constexpr int MINB = MINB_;      // resident CTAs per SM the register allocation is sized for
@@ -52,14 +66,15 @@ struct TmaCfg {
   static constexpr int TXP = TXP_;        // node pairs per tile row: one node pair per thread
   static constexpr int TX = 2 * TXP_, TY = TY_;   // tile (X, Y)
   static constexpr int NACTIVE = TXP * TY;
-  static constexpr int NTHREADS = (NACTIVE + 31) / 32 * 32;        // whole warps; the surplus threads idle
-  static constexpr int BW = TX + 8, BH = TY + 6;                   // haloed plane box (doubles)
+  static constexpr int NCONS = (NACTIVE + 31) / 32 * 32;           // consumer threads: whole warps; the surplus idles
+  static constexpr int NTHREADS = NCONS + 32 * GW_;                // + the ghost warp(s)
+  static constexpr int BW = TX + 8 + XPAD_, BH = TY + 6;           // haloed plane box (doubles)
   static constexpr int BOX = BW * BH, YBOX = TX * TY;              // doubles the TMA unit writes per plane
   static constexpr int SLOT = (BOX + 15) / 16 * 16;                // slot strides keep 128-byte alignment
   static constexpr int YSLOT_FULL = (YBOX + 15) / 16 * 16;
   template <int STAGE>
   static constexpr size_t smem_bytes() {
-    return (size_t)R * (SLOT + (STAGE >= 2 ? YSLOT_FULL : 0)) * 8 + 2 * R * 8;
+    return (size_t)R * (SLOT + (STAGE >= 2 ? YSLOT_FULL : 0)) * 8 + 3 * R * 8;
   }
 };
 
@@ -233,7 +248,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   constexpr bool ZIN = DZ >= B0;                             // is the marching dim differentiated?
   constexpr int TX = Cfg::TX, BW = Cfg::BW, PAIRS = Cfg::TXP;
   constexpr int R = Cfg::R;
-  constexpr int TY = Cfg::TY, NTHREADS = Cfg::NTHREADS, NCONS_WARPS = NTHREADS / 32;
+  constexpr int TY = Cfg::TY, NTHREADS = Cfg::NTHREADS, NCONS_WARPS = Cfg::NCONS / 32;
   constexpr int SLOT = Cfg::SLOT, YSLOT_FULL = Cfg::YSLOT_FULL;
   static_assert((SLOT * 8) % 128 == 0 && (YSLOT_FULL * 8) % 128 == 0, "slots must keep 128-byte alignment");
   static_assert(R >= 6 && R <= 16, "ring depth");
@@ -248,6 +263,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   const uint32_t yring_s = ring_s + R * SLOT * 8;
   const uint32_t full_s = ring_s + R * (SLOT + YSLOT) * 8;
   const uint32_t empty_s = full_s + R * 8;
+  const uint32_t ready_s = empty_s + R * 8;                      // ghost-warp configurations only
 
   const int tid = threadIdx.x;
   long long b = blockIdx.x;
@@ -264,7 +280,11 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < R; ++s) { mbar_init(full_s + 8 * s, 1); mbar_init(empty_s + 8 * s, NCONS_WARPS); }
+    for (int s = 0; s < R; ++s) {
+      mbar_init(full_s + 8 * s, 1);
+      mbar_init(empty_s + 8 * s, NCONS_WARPS);
+      mbar_init(ready_s + 8 * s, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // batch functors keep the parameter block of this CTA's batch element (= the slow index) in shared memory
@@ -303,9 +323,114 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   if (tid == 0) {
     for (unsigned k = 0; k < (unsigned)R && k <= klast; ++k) issue(k, k);
   }
+  // does any node of this tile have an X / Y stencil that leaves the grid?  (CTA-uniform)
+  const bool need_patch_x = x0 - 3 < 0 || x0 + TX + 2 >= NX;
+  const bool need_patch_y = y0 - 3 < 0 || y0 + TY + 2 >= NY;
+  const int lane = tid & 31;
+
+  // ================================================================== ghost warp
+  // Plane by plane, behind the TMA unit: write the ghost cells of the landed plane into its slot, then release it to the
+  // consumers (ready[s]).  Only planes that will be "current" need them (the Z stencil reads interior nodes only).
+  // The slot was written through the async proxy and will be again: fence.proxy.async orders this warp's generic-proxy
+  // stores before the consumers' release of the slot lets the producer re-arm it.
+  const bool gw_on = Cfg::GW && (need_patch_x || need_patch_y);
+  if constexpr (Cfg::GW) {
+    if (tid >= Cfg::NCONS) {
+      if (!gw_on) return;
+      long long base = 0;
+      {
+        long long r = slow_flat;
+#pragma unroll
+        for (int d = NSLOW - 1; d >= 0; --d) { base += (long long)(r % g.N[d]) * g.stride[d]; r /= g.N[d]; }
+      }
+      const long long ystride = g.stride[DY];
+      const double mx = g.slope_mult[DX], my = g.slope_mult[DY];
+      const bool whole_x = NX <= TX, whole_y = NY <= TY;
+      const int nrow = min(TY, NY - y0);                       // tile rows inside the grid
+      for (unsigned k = (unsigned)(tid - Cfg::NCONS) / 32; k <= klast; k += Cfg::NGW) {
+        const unsigned s = k % R;
+        mbar_wait(full_s + 8 * s, (k / R) & 1);
+        const int zp = z0 - 3 + (int)k;
+        int zsrc = zp;
+        bool loaded = true;
+        if (zp < 0 || zp >= NZ) {
+          if (bcz == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NZ : zp - NZ;
+          else if (bcz == HJ_BC_EXTRAPOLATE) loaded = false;
+        }
+        if ((Cfg::OPT & 256) == 0 && loaded && k >= 3 && k + 3 <= klast) {     // 256: tuning harness only, no fill
+          double* sl = ring + (size_t)s * SLOT;
+          const double* gplane = st.in + base + (long long)zsrc * g.stride[DZ];
+          // One lane per row (X sides) / per column pair (Y sides): the two edge values are read once and give all the
+          // ghost cells of that side (the slope of add_ghost_extrapolate.py:88-100 is common to them).
+          if (need_patch_x) {
+            for (int row = lane; row < nrow; row += 32) {
+              double* rowp = sl + (row + 3) * BW + 4 - x0;          // rowp[c] = column c of the grid
+              const double* grow = gplane + (long long)(y0 + row) * ystride;
+              if (x0 == 0) {                                        // columns -3..-1
+                if (bcx == HJ_BC_PERIODIC) {
+#pragma unroll
+                  for (int c = -3; c < 0; ++c) rowp[c] = whole_x ? rowp[c + NX] : __ldg(grow + c + NX);
+                } else {
+                  const double e0 = rowp[0], e1 = rowp[1];
+#pragma unroll
+                  for (int c = -3; c < 0; ++c) rowp[c] = ghost_extrapolate(e0, e1, -c, mx);
+                }
+              }
+              if (x0 + TX + 2 >= NX) {                              // columns NX..NX+3 (as far as the box reaches)
+                const int cmax = min(NX + 3, x0 + TX + 3);
+                if (bcx == HJ_BC_PERIODIC) {
+                  for (int c = NX; c <= cmax; ++c) rowp[c] = whole_x ? rowp[c - NX] : __ldg(grow + c - NX);
+                } else {
+                  const double f0 = rowp[NX - 1], f1 = rowp[NX - 2];
+                  for (int c = NX; c <= cmax; ++c) rowp[c] = ghost_extrapolate(f0, f1, c - (NX - 1), mx);
+                }
+              }
+            }
+          }
+          if (need_patch_y) {
+            for (int cp = lane; cp < TX / 2; cp += 32) {
+              if (x0 + 2 * cp >= NX) continue;
+              double* colp = sl + 4 + 2 * cp + (3 - y0) * BW;       // colp[r * BW] = row r of the grid, my column pair
+              const double* gcol = gplane + x0 + 2 * cp;
+              if (y0 == 0) {                                        // rows -3..-1
+                if (bcy == HJ_BC_PERIODIC) {
+#pragma unroll
+                  for (int r = -3; r < 0; ++r)
+                    *reinterpret_cast<double2*>(colp + r * BW) = whole_y ? lds2(colp + (r + NY) * BW) : ldg2(gcol + (long long)(r + NY) * ystride);
+                } else {
+                  const double2 e0 = lds2(colp), e1 = lds2(colp + BW);
+#pragma unroll
+                  for (int r = -3; r < 0; ++r)
+                    *reinterpret_cast<double2*>(colp + r * BW) =
+                        make_double2(ghost_extrapolate(e0.x, e1.x, -r, my), ghost_extrapolate(e0.y, e1.y, -r, my));
+                }
+              }
+              if (y0 + TY + 2 >= NY) {                              // rows NY..NY+2 (as far as the box reaches)
+                const int rmax = min(NY + 2, y0 + TY + 2);
+                if (bcy == HJ_BC_PERIODIC) {
+                  for (int r = NY; r <= rmax; ++r)
+                    *reinterpret_cast<double2*>(colp + r * BW) = whole_y ? lds2(colp + (r - NY) * BW) : ldg2(gcol + (long long)(r - NY) * ystride);
+                } else {
+                  const double2 f0 = lds2(colp + (NY - 1) * BW), f1 = lds2(colp + (NY - 2) * BW);
+                  for (int r = NY; r <= rmax; ++r)
+                    *reinterpret_cast<double2*>(colp + r * BW) =
+                        make_double2(ghost_extrapolate(f0.x, f1.x, r - (NY - 1), my), ghost_extrapolate(f0.y, f1.y, r - (NY - 1), my));
+                }
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_s + 8 * s);
+      }
+      return;
+    }
+  }
+  // consumers see a plane when it has landed (and, with a working ghost warp, when its ghost cells are in place)
+  const uint32_t land_s = gw_on ? ready_s : full_s;
 
   // ================================================================== consumers
-  const int lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp index, known warp-uniform to the compiler
   const bool live = tid < Cfg::NACTIVE;                     // surplus threads of the last warp only keep the barriers
   const int tp = tid % PAIRS, ty = live ? tid / PAIRS : TY - 1;
@@ -334,9 +459,8 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   typename Sys::Pt ptB = Sys::load(idx, g, ks, scratch);
 
   const int myoff = (ty + 3) * BW + 4 + 2 * tp;              // my pair inside a slot (doubles); 16-byte aligned
-  // does any node of this tile have an X / Y stencil that leaves the grid?  (CTA-uniform)
-  const bool need_patch_x = x0 - 3 < 0 || x0 + TX + 2 >= NX;
-  const bool need_patch_y = y0 - 3 < 0 || y0 + TY + 2 >= NY;
+  // a tile with nodes outside the grid keeps its stores masked in the fast march too
+  const bool full_tile = x0 + TX <= NX && y0 + TY <= NY;
 
   RedAcc<D> acc;
   acc.init();
@@ -346,7 +470,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   double2 q[3];                                              // planes z-3, z-2, z-1 of my pair
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    mbar_wait(full_s + 8 * k, 0);
+    mbar_wait(land_s + 8 * k, 0);
     if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
   }
   if (bcz == HJ_BC_EXTRAPOLATE && z0 == 0) {
@@ -406,7 +530,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     }
     // plane z+3 (the newest the stencil needs) has normally landed long ago: probe now, consume the answer later
     uint32_t landed = 0;
-    if constexpr ((Cfg::OPT & 1) != 0) landed = mbar_test(full_s + 8 * s_new, p_new);
+    if constexpr ((Cfg::OPT & 1) != 0) landed = mbar_test(land_s + 8 * s_new, p_new);
     Sys::template apply<DZ>(ptA, raw_next, ks);              // the marching dim is shared by my two nodes
     Sys::template apply<DZ>(ptB, raw_next, ks);
     raw_next = Sys::template fetch<DZ>(min(z + 1, NZ - 1), g, ks);
@@ -455,7 +579,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     }
     if constexpr (!FAST) {
       // ghost cells of the current plane in X (tiles touching the domain boundary only), in registers
-      if (need_patch_x && ok0)
+      if (!gw_on && need_patch_x && ok0)
         patch_x(w0, w1, w2, w3, w4, ix, x0, NX, bcx, g.slope_mult[DX], cur + (ty + 3) * BW, st.in + off - ix, NX <= TX);
     }
     const double2 ctr = w2;
@@ -476,14 +600,14 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     auto load_z = [&]() {
       if (STAGE >= 2) y0v = lds2(yring + (size_t)s_cur * YSLOT + ty * TX + 2 * tp);
       if (ZIN) { zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff); zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff); }
-      if (!landed) mbar_wait(full_s + 8 * s_new, p_new);
+      if (!landed) mbar_wait(land_s + 8 * s_new, p_new);
       if (ZIN) zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
     };
     if constexpr (PIPE) { load_z(); HJ_PIPE_BARRIER }
     {  // Y neighbours of the pair
       if constexpr (!PIPE) load_y();
       if constexpr (!FAST) {
-        if (need_patch_y && ok0)
+        if (!gw_on && need_patch_y && ok0)
           patch_y<BW>(ym3, ym2, ym1, yp1, yp2, yp3, iy, y0, NY, bcy, g.slope_mult[DY], cur + 4 + 2 * tp,
                       st.in + off - (long long)iy * g.stride[DY], g.stride[DY], NY <= TY);
       }
@@ -583,7 +707,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       if (!SIMPLE && st.use_obs) { oA = nan_max(oA, -obsv.x); oB = nan_max(oB, -obsv.y); }
     }
     if (FAST && (Cfg::OPT & 64)) { if (oA == 1.2345e300) st.out[off] = oB; }      // tuning harness only: no store
-    else if (FAST && (Cfg::OPT & 4) && Cfg::NACTIVE == Cfg::NTHREADS) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
+    else if (FAST && (Cfg::OPT & 4) && Cfg::NACTIVE == Cfg::NCONS && (!Cfg::GW || full_tile)) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
     else if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
     else if (ok0) st.out[off] = oA;
     if (red && ((ok0 && oA != oA) || (ok1 && oB != oB))) acc.nan = 1;
@@ -597,7 +721,7 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   };
 
   // head (general body) -> fast segment z in [z0+1, z1-R] (the prefetched plane z+R-1 <= z1-1 <= NZ-1) -> tail
-  const int zf_end = (need_patch_x || need_patch_y) ? z0 : z1 - R + 1;
+  const int zf_end = ((need_patch_x || need_patch_y) && !gw_on) ? z0 : z1 - R + 1;
   plane.template operator()<false>();
   if ((Cfg::OPT & 8) != 0 && z < zf_end) {                   // pipeline prologue: X window of the first fast plane
     const double2* rowp = reinterpret_cast<const double2*>(ring + (size_t)s_cur * SLOT + myoff);

@@ -18,4 +18,6 @@ struct HjTmaPlan {
   CUtensorMap vmap[3];
   VecGeom vgeo;
   long long vblocks = 0;
+  int vb = 0;              // doubles per vector chunk of pass 2 (the column quantum of hj_stage_pass_cols)
+  long long vlen = 0;      // length of the vector axis (flattened trailing dims, pitched)
 };

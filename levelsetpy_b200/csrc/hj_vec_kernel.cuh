@@ -22,6 +22,7 @@
 
 struct VecGeom {
   int nvc;          // chunks along the vector axis
+  int vc0;          // first chunk this launch advances (pass 2 in column pieces: hj_stage_pass_cols)
   int nta, ntb;     // tiles along the two tiled block dims (ntb = 1 for a 2-dim block)
   int nzc, cz;      // chunks / planes per chunk along the marching block dim
   int zcoord0;      // TMA coordinate shift of dim 0 (stored halo planes of a slab context)
@@ -31,8 +32,12 @@ struct VecGeom {
 // The marching dim MD is the LAST dim of the block: for the relative-Dubins block that is the periodic heading, whose
 // wrap-around costs nothing when it is the marched dim (the ring simply loads plane z +- N), and on a slab context
 // dim 0 (thin, with stored halo planes) is then a tiled dim that one tile covers.
-template <int NS_, int R_, int MINB_, int VP_, int TA_, int TB_>
+// GW_: ghost warp, as in TmaCfg -- one extra warp writes the ghost rows of the tiled dims into the landed slot.
+template <int NS_, int R_, int MINB_, int VP_, int TA_, int TB_, int GW_ = 0, int OPT_ = 0>
 struct VecCfg {
+  static constexpr int OPT = OPT_;        // 256: tuning harness only -- the ghost warp forwards the barrier, no fill
+  static constexpr int NGW = GW_;
+  static constexpr bool GW = GW_ > 0;
   static constexpr int NS = NS_;          // dims of the leading block (2 or 3)
   static constexpr int MD = NS_ - 1;      // marching block dim
   static constexpr int DA = 0, DB = NS_ == 3 ? 1 : -1;             // tiled block dims (DA slower in memory)
@@ -42,10 +47,11 @@ struct VecCfg {
   static constexpr int HA = TA + 6, HB = NS_ == 3 ? TB + 6 : 1;    // haloed tile
   static constexpr int SB = VB, SA = HB * VB;                      // slot strides (doubles) of dims DB, DA
   static constexpr int NACTIVE = VP * TA * TB;
-  static constexpr int NTHREADS = (NACTIVE + 31) / 32 * 32;
+  static constexpr int NCONS = (NACTIVE + 31) / 32 * 32;
+  static constexpr int NTHREADS = NCONS + 32 * GW_;
   static constexpr int BOX = HA * HB * VB;
   static constexpr int SLOT = (BOX + 15) / 16 * 16;
-  static constexpr size_t smem_bytes() { return (size_t)R * SLOT * 8 + 2 * R * 8; }
+  static constexpr size_t smem_bytes() { return (size_t)R * SLOT * 8 + 3 * R * 8; }
 };
 
 namespace hjtma {
@@ -65,7 +71,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   static_assert(STAGE >= 1 && STAGE <= 3, "RK stages only");
   constexpr int R = Cfg::R, SLOT = Cfg::SLOT, VB = Cfg::VB, VP = Cfg::VP, TA = Cfg::TA, TB = Cfg::TB;
   constexpr int SA = Cfg::SA, SB = Cfg::SB;
-  constexpr int NTHREADS = Cfg::NTHREADS, NWARPS = NTHREADS / 32;
+  constexpr int NWARPS = Cfg::NCONS / 32;
   static_assert((SLOT * 8) % 128 == 0, "slot must keep 128-byte alignment");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -73,13 +79,14 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   const uint32_t ring_s = smem_u32(smem_raw);
   const uint32_t full_s = ring_s + R * SLOT * 8;
   const uint32_t empty_s = full_s + R * 8;
+  const uint32_t ready_s = empty_s + R * 8;
 
   const int tid = threadIdx.x;
   long long b = blockIdx.x;
   const int tb = (int)(b % geo.ntb); b /= geo.ntb;
   const int ta = (int)(b % geo.nta); b /= geo.nta;
   const int zc = (int)(b % geo.nzc); b /= geo.nzc;
-  const int v0 = (int)b * VB;
+  const int v0 = ((int)b + geo.vc0) * VB;
   const int NM = g.N[MD], NA = g.N[DA], NB = NS == 3 ? g.N[DB] : 1;
   const long long V = g.stride[NS - 1];
   const int ia0 = ta * TA, ib0 = tb * TB, z0 = zc * geo.cz;
@@ -91,7 +98,11 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < R; ++s) { mbar_init(full_s + 8 * s, 1); mbar_init(empty_s + 8 * s, NWARPS); }
+    for (int s = 0; s < R; ++s) {
+      mbar_init(full_s + 8 * s, 1);
+      mbar_init(empty_s + 8 * s, NWARPS);
+      mbar_init(ready_s + 8 * s, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -119,8 +130,104 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     for (unsigned k = 0; k < (unsigned)R && k <= klast; ++k) issue(k, k);
   }
 
-  // ================================================================== consumers
   const int lane = tid & 31;
+  const bool need_patch_a = bca != HJ_BC_HALO && (ia0 - 3 < 0 || ia0 + TA + 2 >= NA);
+  const bool need_patch_b = NS == 3 && (ib0 - 3 < 0 || ib0 + TB + 2 >= NB);
+
+  // ================================================================== ghost warp (see k_stage_tma)
+  // Ghost rows of the tiled dims: for dim A rows a = -3..-1 / NA..NA+2 over the tile's B rows, for dim B likewise over
+  // the tile's A rows; every row is VB doubles, moved as double2.
+  const bool gw_on = Cfg::GW && (need_patch_a || need_patch_b);
+  if constexpr (Cfg::GW) {
+    if (tid >= Cfg::NCONS) {
+      if (!gw_on) return;
+      const double ma = g.slope_mult[DA], mb = g.slope_mult[DB];
+      const bool whole_a = NA <= TA, whole_b = NB <= TB;
+      const int na = min(TA, NA - ia0), nb = NS == 3 ? min(TB, NB - ib0) : 1;      // tile rows inside the grid
+      for (unsigned k = (unsigned)(tid - Cfg::NCONS) / 32; k <= klast; k += Cfg::NGW) {
+        const unsigned s = k % R;
+        mbar_wait(full_s + 8 * s, (k / R) & 1);
+        const int zp = z0 - 3 + (int)k;
+        int zsrc = zp;
+        bool loaded = true;
+        if (zp < 0 || zp >= NM) {
+          if (bcm == HJ_BC_PERIODIC) zsrc = zp < 0 ? zp + NM : zp - NM;
+          else loaded = false;
+        }
+        if ((Cfg::OPT & 256) == 0 && loaded && k >= 3 && k + 3 <= klast) {
+          double* sl = ring + (size_t)s * SLOT;
+          const double* gplane = st.in + (long long)zsrc * g.stride[MD] + v0;
+          auto ghost2 = [](double2 e, double2 n, int dist, double m) {
+            return make_double2(ghost_extrapolate(e.x, n.x, dist, m), ghost_extrapolate(e.y, n.y, dist, m));
+          };
+          // one lane per (row of the other tiled dim, vector pair): the two edge values give the three ghost rows
+          if (need_patch_a) {
+            for (int it = lane; it < nb * VP; it += 32) {
+              const int bb = it / VP, vp2 = it % VP;
+              double* colp = sl + (NS == 3 ? bb + 3 : 0) * SB + 2 * vp2 + (3 - ia0) * SA;   // colp[a * SA] = row a of dim A
+              const double* gcol = gplane + (NS == 3 ? (long long)(ib0 + bb) * g.stride[DB] : 0) + 2 * vp2;
+              if (ia0 == 0) {
+                if (bca == HJ_BC_PERIODIC) {
+#pragma unroll
+                  for (int a = -3; a < 0; ++a)
+                    *reinterpret_cast<double2*>(colp + a * SA) = whole_a ? lds2(colp + (a + NA) * SA) : ldg2(gcol + (long long)(a + NA) * g.stride[DA]);
+                } else {
+                  const double2 e0 = lds2(colp), e1 = lds2(colp + SA);
+#pragma unroll
+                  for (int a = -3; a < 0; ++a) *reinterpret_cast<double2*>(colp + a * SA) = ghost2(e0, e1, -a, ma);
+                }
+              }
+              if (ia0 + TA + 2 >= NA) {
+                const int amax = min(NA + 2, ia0 + TA + 2);
+                if (bca == HJ_BC_PERIODIC) {
+                  for (int a = NA; a <= amax; ++a)
+                    *reinterpret_cast<double2*>(colp + a * SA) = whole_a ? lds2(colp + (a - NA) * SA) : ldg2(gcol + (long long)(a - NA) * g.stride[DA]);
+                } else {
+                  const double2 f0 = lds2(colp + (NA - 1) * SA), f1 = lds2(colp + (NA - 2) * SA);
+                  for (int a = NA; a <= amax; ++a) *reinterpret_cast<double2*>(colp + a * SA) = ghost2(f0, f1, a - (NA - 1), ma);
+                }
+              }
+            }
+          }
+          if (NS == 3 && need_patch_b) {
+            for (int it = lane; it < na * VP; it += 32) {
+              const int aa2 = it / VP, vp2 = it % VP;
+              double* colp = sl + (aa2 + 3) * SA + 2 * vp2 + (3 - ib0) * SB;                 // colp[b * SB] = row b of dim B
+              const double* gcol = gplane + (long long)(ia0 + aa2) * g.stride[DA] + 2 * vp2;
+              if (ib0 == 0) {
+                if (bcb == HJ_BC_PERIODIC) {
+#pragma unroll
+                  for (int q2 = -3; q2 < 0; ++q2)
+                    *reinterpret_cast<double2*>(colp + q2 * SB) = whole_b ? lds2(colp + (q2 + NB) * SB) : ldg2(gcol + (long long)(q2 + NB) * g.stride[DB]);
+                } else {
+                  const double2 e0 = lds2(colp), e1 = lds2(colp + SB);
+#pragma unroll
+                  for (int q2 = -3; q2 < 0; ++q2) *reinterpret_cast<double2*>(colp + q2 * SB) = ghost2(e0, e1, -q2, mb);
+                }
+              }
+              if (ib0 + TB + 2 >= NB) {
+                const int bmax = min(NB + 2, ib0 + TB + 2);
+                if (bcb == HJ_BC_PERIODIC) {
+                  for (int q2 = NB; q2 <= bmax; ++q2)
+                    *reinterpret_cast<double2*>(colp + q2 * SB) = whole_b ? lds2(colp + (q2 - NB) * SB) : ldg2(gcol + (long long)(q2 - NB) * g.stride[DB]);
+                } else {
+                  const double2 f0 = lds2(colp + (NB - 1) * SB), f1 = lds2(colp + (NB - 2) * SB);
+                  for (int q2 = NB; q2 <= bmax; ++q2) *reinterpret_cast<double2*>(colp + q2 * SB) = ghost2(f0, f1, q2 - (NB - 1), mb);
+                }
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_s + 8 * s);
+      }
+      return;
+    }
+  }
+  const uint32_t land_s = gw_on ? ready_s : full_s;
+
+  // ================================================================== consumers
   const bool live = tid < Cfg::NACTIVE;
   const int vp = tid % VP;
   const int pos = live ? tid / VP : 0;
@@ -146,9 +253,6 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   typename Blk::Pt pt = Blk::load(idx, g, ks);               // x_A is shared by the two nodes of my pair
 
   const int myoff = ((aa + 3) * Cfg::HB + (NS == 3 ? ab + 3 : 0)) * VB + 2 * vp;
-  const bool need_patch_a = bca != HJ_BC_HALO && (ia0 - 3 < 0 || ia0 + TA + 2 >= NA);
-  const bool need_patch_b = NS == 3 && (ib0 - 3 < 0 || ib0 + TB + 2 >= NB);
-
   RedAcc<GD> acc;
   acc.init();
 
@@ -156,7 +260,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   double2 q[3];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    mbar_wait(full_s + 8 * k, 0);
+    mbar_wait(land_s + 8 * k, 0);
     if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
   }
   if (bcm == HJ_BC_EXTRAPOLATE && z0 == 0) {
@@ -184,8 +288,12 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   double2 raw_next = Blk::template fetch<MD>(z0, g, ks);
   const double2 zero2 = make_double2(0.0, 0.0);
   double2 tmp_next = inb ? ldg2(st.tmp + off) : zero2;       // pass-1 result F_B(in): fetched one plane ahead
+  double2 y0_next = (STAGE >= 2 && inb) ? ldg2(st.y0 + off) : zero2;   // so is y0 (stage 3 overwrites it in place, but
+                                                             // only at this thread's own node of the CURRENT plane)
 
-  auto plane = [&]<bool FAST>() {
+  // SIMPLE (fast march only): the common epilogue -- no termRestrictUpdate; stage 3 = minVOverTime without obstacle --
+  // compiled in, so that the steady-state loop carries no epilogue dispatch (as in k_stage_tma)
+  auto plane = [&]<bool FAST, bool SIMPLE = false>() {
     if constexpr (FAST) {
       if (tid == 0) {
         mbar_wait(empty_s + 8 * s_prev, p_prev);
@@ -201,13 +309,13 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     raw_next = Blk::template fetch<MD>(min(z + 1, NM - 1), g, ks);
     // pointwise streams: issued first, consumed last
     const double2 tmpv = tmp_next;
-    double2 y0v = zero2;
-    if (inb) {
-      if (z + 1 < z1) tmp_next = ldg2(st.tmp + off + zstride);
-      if (STAGE >= 2) y0v = ldg2(st.y0 + off);
+    const double2 y0v = y0_next;
+    if (inb && z + 1 < z1) {
+      tmp_next = ldg2(st.tmp + off + zstride);
+      if (STAGE >= 2) y0_next = ldg2(st.y0 + off + zstride);
     }
     double2 auxv = zero2, obsv = zero2;
-    if (STAGE == 3 && inb) {
+    if (STAGE == 3 && !SIMPLE && inb) {
       if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX) auxv = ldg2(st.aux + off);
       if (st.use_obs) obsv = ldg2(st.obs + off);
     }
@@ -228,7 +336,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
       double2 am3 = lds2(cur - 3 * SA), am2 = lds2(cur - 2 * SA), am1 = lds2(cur - 1 * SA);
       double2 ap1 = lds2(cur + 1 * SA), ap2 = lds2(cur + 2 * SA), ap3 = lds2(cur + 3 * SA);
       if constexpr (!FAST) {
-        if (need_patch_a && inb)
+        if (!gw_on && need_patch_a && inb)
           patch_y<SA>(am3, am2, am1, ap1, ap2, ap3, ia, ia0, NA, bca, g.slope_mult[DA], cur - (aa + 3) * SA,
                       st.in + off - (long long)ia * g.stride[DA], g.stride[DA], NA <= TA);
       }
@@ -242,7 +350,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
       double2 bm3 = lds2(cur - 3 * SB), bm2 = lds2(cur - 2 * SB), bm1 = lds2(cur - 1 * SB);
       double2 bp1 = lds2(cur + 1 * SB), bp2 = lds2(cur + 2 * SB), bp3 = lds2(cur + 3 * SB);
       if constexpr (!FAST) {
-        if (need_patch_b && inb)
+        if (!gw_on && need_patch_b && inb)
           patch_y<SB>(bm3, bm2, bm1, bp1, bp2, bp3, ib, ib0, NB, bcb, g.slope_mult[DB], cur - (ab + 3) * SB,
                       st.in + off - (long long)ib * g.stride[DB], g.stride[DB], NB <= TB);
       }
@@ -254,7 +362,7 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     }
     {  // marching dim: planes z+1, z+2 landed earlier; plane z+3 is the newest one of the ring
       double2 zp1 = lds2(ring + (size_t)s_p1 * SLOT + myoff), zp2 = lds2(ring + (size_t)s_p2 * SLOT + myoff), zp3;
-      mbar_wait(full_s + 8 * s_new, p_new);
+      mbar_wait(land_s + 8 * s_new, p_new);
       zp3 = lds2(ring + (size_t)s_new * SLOT + myoff);
       if constexpr (!FAST) {
         if (bcm == HJ_BC_EXTRAPOLATE && z + 3 >= NM) {
@@ -287,8 +395,12 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     }
 
     // tmp holds F_B(in) from pass 1: total ydot, termRestrictUpdate, then the RK algebra + driver epilogue
-    ydA = restrict_update(tmpv.x + ydA, st.restrict_sign);
-    ydB = restrict_update(tmpv.y + ydB, st.restrict_sign);
+    ydA = tmpv.x + ydA;
+    ydB = tmpv.y + ydB;
+    if constexpr (!SIMPLE) {
+      ydA = restrict_update(ydA, st.restrict_sign);
+      ydB = restrict_update(ydB, st.restrict_sign);
+    }
     const double vA = ctr.x + st.dt * ydA, vB = ctr.y + st.dt * ydB;
     double oA, oB;
     if (STAGE == 1) { oA = vA; oB = vB; }
@@ -296,9 +408,13 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     else {
       oA = st.fin_a * (y0v.x + st.fin_b * vA);
       oB = st.fin_a * (y0v.y + st.fin_b * vB);
-      oA = comp_epilogue(oA, st.comp, y0v.x, auxv.x);
-      oB = comp_epilogue(oB, st.comp, y0v.y, auxv.y);
-      if (st.use_obs) { oA = nan_max(oA, -obsv.x); oB = nan_max(oB, -obsv.y); }
+      if constexpr (SIMPLE) {
+        oA = nan_min(oA, y0v.x); oB = nan_min(oB, y0v.y);
+      } else {
+        oA = comp_epilogue(oA, st.comp, y0v.x, auxv.x);
+        oB = comp_epilogue(oB, st.comp, y0v.y, auxv.y);
+        if (st.use_obs) { oA = nan_max(oA, -obsv.x); oB = nan_max(oB, -obsv.y); }
+      }
     }
     if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
     else if (ok0) st.out[off] = oA;
@@ -312,9 +428,14 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     if (++s_new == (unsigned)R) { s_new = 0; p_new ^= 1; }
   };
 
-  const int zf_end = (need_patch_a || need_patch_b) ? z0 : z1 - R + 1;
+  const int zf_end = ((need_patch_a || need_patch_b) && !gw_on) ? z0 : z1 - R + 1;
   plane.template operator()<false>();
-  while (z < zf_end) plane.template operator()<true>();
+  const bool simple = st.restrict_sign == 0 && (STAGE != 3 || (st.comp == HJ_COMP_MIN_OVER_TIME && !st.use_obs));
+  if (simple) {
+    while (z < zf_end) plane.template operator()<true, true>();
+  } else {
+    while (z < zf_end) plane.template operator()<true>();
+  }
   while (z < z1) plane.template operator()<false>();
   if (RED) acc.flush(st.red);
 }

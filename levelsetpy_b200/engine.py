@@ -296,6 +296,22 @@ class Engine:
         L.check(self.lib.hj_stage_range(self.h, self.stream(), int(stage), int(z_begin), int(z_end), float(t), float(dt),
                                         p, int(comp), int(bool(use_obstacle)), int(want_reduce)))
 
+    def split_cols(self):
+        """(length of the flattened trailing-dims axis, column quantum) of a product system on the split path."""
+        v, q = C.c_int64(), C.c_int()
+        L.check(self.lib.hj_split_cols(self.h, C.byref(v), C.byref(q)))
+        return v.value, q.value
+
+    def stage_cols(self, stage, col_begin, col_end, t, dt, params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=0):
+        """Pass 2 of ``stage`` on columns [col_begin, col_end) of the trailing-dims axis only (hj_stage_pass_cols)."""
+        p = None
+        if params is not None:
+            sp = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+            p = sp.ctypes.data
+            self._sp_keep = sp
+        L.check(self.lib.hj_stage_pass_cols(self.h, self.stream(), int(stage), int(col_begin), int(col_end), float(t),
+                                            float(dt), p, int(comp), int(bool(use_obstacle)), int(want_reduce)))
+
     def supports_range(self):
         """True if hj_stage_range can advance this context (probed with an empty-range call that must fail as INVALID,
         not as UNSUPPORTED)."""

@@ -120,10 +120,13 @@ class SlabSolver:
     schemeData: the reference's bundle (grid = the GLOBAL grid).  ``comm``: DistComm() by default.
     ``engine_factory(grid, weno, device, slab, backend)`` builds the per-slab context (default: the CUDA Engine)."""
 
-    def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None, transport="auto", overlap=True):
+    def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None, transport="auto", overlap=True,
+                 pieces="auto"):
         """``transport``: "peer" (copy-engine pushes into peer memory, hj_halo_*), "p2p" (send/recv of the group) or
         "auto" (peer wherever the per-slab engine offers it).  ``overlap=False``: exchange first, then compute (the
-        protocol of the gather / intended paths; attribution runs)."""
+        protocol of the gather / intended paths; attribution runs).  ``pieces``: product systems over the peer
+        transport advance pass 2 in that many column pieces and push each finished piece of the edge planes while the
+        next is computed ("auto": 4 when the halo is a large fraction of the slab, else 1 = whole-plane pushes)."""
         sd = schemeData
         for f in ("grid", "hamFunc", "partialFunc"):
             assert isfield(sd, f), "%s not in bundle thisschemeData" % f
@@ -150,6 +153,9 @@ class SlabSolver:
         self.shape = (self.n0,) + tuple(int(x) for x in np.asarray(g.N).reshape(-1)[1:])
         self._no_overlap = not overlap
         self.mode = "full"        # attribution runs (bench.py): "compute" = no exchange, "comm" = no stage kernels
+        self._pieces_arg = pieces
+        self._cols = None
+        self._primed = False      # pieces protocol: the halos of the state the next step reads are on their way
         if transport not in ("auto", "peer", "p2p"):
             raise ValueError("transport must be 'auto', 'peer' or 'p2p', got %r" % (transport,))
         can_peer = hasattr(self.eng, "halo_export")
@@ -178,6 +184,20 @@ class SlabSolver:
     def upload(self, slab, field=L.FIELD_STATE):
         """``slab``: this rank's planes [lo, hi) of the field, shape (hi-lo, N1, ...), numpy or torch CUDA."""
         self.eng.upload(slab, field)
+        if field == L.FIELD_STATE:
+            self.state_changed()
+
+    def state_changed(self):
+        """Collective.  The resident state was replaced (upload, or written through ``eng.buffer_tensor``): halo pieces
+        pushed ahead for the old state are consumed and dropped."""
+        if self._primed and self.mode != "compute":
+            self.eng.halo_wait(0, len(self._cols[1]))
+        self._primed = False
+
+    def set_mode(self, mode):
+        """Collective: "full", "compute" (no exchange) or "comm" (no stage kernels) -- attribution runs."""
+        self.state_changed()
+        self.mode = mode
 
     def download(self, out=None):
         if out is not None:
@@ -320,6 +340,47 @@ class SlabSolver:
                                 and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
         return self._ranged
 
+    def pieces(self):
+        """Column pieces [(begin, end), ...] of pass 2 and the axis length, or None for whole-plane pushes."""
+        if self._cols is None:
+            k = self._pieces_arg
+            if not (self.peer and self.two_pass() and hasattr(self.eng, "split_cols")):
+                k = 1
+            elif k == "auto":
+                k = 4 if 2 * GHOST * 4 > self.n0 else 1           # the halo is more than a quarter of the slab
+            if int(k) <= 1:
+                self._cols = (0, None)
+            else:
+                V, q = self.eng.split_cols()
+                per = -(-V // (int(k) * q)) * q
+                self._cols = (V, [(a, min(V, a + per)) for a in range(0, V, per)])
+        return self._cols[1]
+
+    def _step_pieces(self, comp, use_obstacle):
+        """Product system, peer transport: every stage = pass 1, then pass 2 piece by piece; a piece waits for the same
+        piece of the neighbours' edge planes of the buffer it reads and, once computed, is pushed into the neighbours'
+        halos of the buffer it wrote -- the transfer for the NEXT stage runs under the rest of this one."""
+        V, cols = self._cols
+        t, dt, blocks = self._step
+        talk, work = self.mode != "compute", self.mode != "comm"
+        if not self._primed:
+            if talk:
+                for a, e in cols:
+                    self.eng.halo_push(0, (a, e, V))
+            self._primed = True
+        for stage in (1, 2, 3):
+            b_in, b_out = self.eng.stage_io(stage)
+            self.run_stage(stage, comp, use_obstacle, which_pass=1)
+            self.finish_halos(b_in)
+            for a, e in cols:
+                if talk:
+                    self.eng.halo_wait(b_in, 1)
+                if work:
+                    self.eng.stage_cols(stage, a, e, t, dt, blocks[stage - 1], comp if stage == 3 else L.COMP_NONE,
+                                        use_obstacle and stage == 3)
+                if talk:
+                    self.eng.halo_push(b_out, (a, e, V))
+
     def two_pass(self):
         if self._overlap is None:
             self._overlap = bool(self.weno != "intended" and not self._no_overlap
@@ -329,6 +390,9 @@ class SlabSolver:
     def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
         """One CFL-limited TVD-RK3 step of the distributed field.  Returns (t_new, dt)."""
         dt = self.begin_step(t, t_end, factorCFL, maxStep)
+        if self.overlapped() and self.pieces() is not None:
+            self._step_pieces(comp, use_obstacle)
+            return rk3_times(t, dt)[2], dt
         for stage in (1, 2, 3):
             b = self.eng.stage_io(stage)[0]
             if self.overlapped():
@@ -363,9 +427,9 @@ class LocalWorld:
 
     poison_halos = False     # tests: NaN the halo planes a stage will receive before its pass 1 runs
 
-    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None, transport="auto"):
+    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None, transport="auto", pieces="auto"):
         self.world = int(world)
-        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory, transport)
+        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory, transport, True, pieces)
                       for r in range(self.world)]
         self.peer = all(s.peer for s in self.slabs) and self.world > 1
         if self.peer:                       # contexts of one process attach by pointer (hj_halo_attach)
@@ -375,7 +439,7 @@ class LocalWorld:
 
     def upload(self, data, field=L.FIELD_STATE):
         for s in self.slabs:
-            s.upload(np.ascontiguousarray(data[s.lo:s.hi]), field)
+            s.upload(np.ascontiguousarray(data[s.lo:s.hi]), field)       # (state_changed: pieces pushed ahead are dropped)
 
     def download(self):
         return np.concatenate([s.download() for s in self.slabs], axis=0)
@@ -397,6 +461,28 @@ class LocalWorld:
         for s in self.slabs:
             s.finish_halos(b)
 
+    def _step_pieces(self, comp, use_obstacle):
+        """SlabSolver._step_pieces for every slab in lock-step on one stream: all pushes a wait depends on were queued in
+        the previous stage (or when the state was primed), so no wait can block the stream forever."""
+        V, cols = self.slabs[0]._cols
+        for s in self.slabs:
+            if not s._primed:
+                for a, e in cols:
+                    s.eng.halo_push(0, (a, e, V))
+                s._primed = True
+        for stage in (1, 2, 3):
+            b_in, b_out = self.slabs[0].eng.stage_io(stage)
+            for s in self.slabs:
+                t_, dt_, blocks = s._step
+                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, which_pass=1)
+                s.finish_halos(b_in)
+            for a, e in cols:
+                for s in self.slabs:
+                    t_, dt_, blocks = s._step
+                    s.eng.halo_wait(b_in, 1)
+                    s.eng.stage_cols(stage, a, e, t_, dt_, blocks[stage - 1], comp, use_obstacle)
+                    s.eng.halo_push(b_out, (a, e, V))
+
     @staticmethod
     def _max_over(tensors):
         import torch
@@ -411,6 +497,9 @@ class LocalWorld:
                 s._alpha = [float(x) for x in amax]
         dts = [s.begin_step(t, t_end, factorCFL, maxStep) for s in self.slabs]
         assert all(d == dts[0] for d in dts), "dt must be identical on every rank"
+        if self.peer and self.slabs[0].overlapped() and self.slabs[0].pieces() is not None:
+            self._step_pieces(comp, use_obstacle)
+            return rk3_times(t, dts[0])[2], dts[0]
         two = self.slabs[0].two_pass()        # product systems: pass 1 runs before the halos arrive (as under NCCL)
         ranged = all(s.ranged() for s in self.slabs)   # whole 3-D systems: interior planes before, edge planes after
         for stage in (1, 2, 3):

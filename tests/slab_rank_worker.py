@@ -92,7 +92,8 @@ def main():
                     ok = bool(err == 0.0 and same_dt)
                     failures += 0 if ok else 1
                     print(json.dumps({"case": name, "weno": weno, "world": world, "transport": transport,
-                                      "overlap": overlap, "protocol": "two_pass" if solver.two_pass() else (
+                                      "overlap": overlap, "pieces": len(solver.pieces() or [None]) if solver.overlapped() else 1,
+                                      "protocol": "two_pass" if solver.two_pass() else (
                                           "ranged" if solver.ranged() else "exchange_first"),
                                       "max_abs_err": err, "max_rel_err": err / rng_, "bit_identical": err == 0.0,
                                       "dt_identical": same_dt, "steps": nsteps, "ok": ok}), flush=True)

@@ -191,3 +191,33 @@ def test_smallest_and_ragged_grids(lsp, N, pd):
     to, yo, _ = orc.ode_cfl3([0.0, 1.0], y0, osd, factor_cfl=0.8, single_step=True)
     assert t == to
     assert np.max(np.abs(y - yo)) <= 1e-9 * float(yo.max() - yo.min())
+
+
+def test_config1_air3d_512_subslab_vs_oracle(lsp):
+    """configs[1] at its configured size against the ORACLE (not against another kernel of this repo): one TVD-RK3 step
+    of the 512^3 field on the device; the oracle advances planes [a-9, a+41) of dim 0 (a step's domain of dependence is
+    3 planes per stage) with the device's dt, and its middle 32 planes -- untouched by the artificial edges of the
+    sub-domain -- must match planes [a, a+32) of the device field to 1e-9 of the value range, same sign mask.  Two
+    windows: one in the interior, one against the global edge of dim 0 (extrapolated ghosts) ."""
+    from levelsetpy_b200 import _lib as L
+    n = 512
+    g, d0, sd = _air3d(lsp, n)
+    d0 = d0 + 0.25 * np.sin(np.asarray(g.vs[2]).reshape(1, 1, -1) + 0.3 * np.asarray(g.vs[0]).reshape(-1, 1, 1))
+    ts, got = _steps(lsp, sd, g, d0, 1, L.BACKEND_AUTO, L.COMP_MIN_OVER_TIME)
+    dt = ts[0]                                       # t after one step from 0 (ode_cfl_3.py:236 returns exactly t + dt)
+    for a, lo, hi in ((203, 194, 244), (0, 0, 41)):  # (first compared plane, oracle window)
+        sub = lsp.createGrid(np.array([float(np.asarray(g.vs[0]).reshape(-1)[lo]), -10.0, 0.0]),
+                             np.array([float(np.asarray(g.vs[0]).reshape(-1)[hi - 1]), 10.0, 2 * np.pi * (1 - 1 / n)]),
+                             np.array([hi - lo, n, n]), pdDims=2, low_mem=True)
+        sub.vs[0] = np.asarray(g.vs[0]).reshape(-1)[lo:hi].reshape(-1, 1).copy()     # the global axis values, bit for bit
+        sub.dx = np.asarray(g.dx, dtype=np.float64).reshape(np.asarray(sub.dx).shape).copy()
+        o = osys.DubinsVehicleRel(sub, 5, 1)
+        osd = orc.OracleSchemeData(grid=sub, hamFunc=o.hamiltonian, partialFunc=o.dissipation)
+        y0 = np.ascontiguousarray(d0[lo:hi]).reshape(-1, 1)
+        to, yo, _ = orc.ode_cfl3([0.0, dt], y0, osd, factor_cfl=0.8, single_step=True)
+        assert abs(to - dt) <= 1e-15, "the sub-domain's own CFL bound must not be the binding one"
+        yo = np.minimum(yo, y0).reshape(hi - lo, n, n)
+        want, have = yo[a - lo:a - lo + 32], got[a:a + 32]
+        err = float(np.max(np.abs(have - want)))
+        assert err <= 1e-9 * float(want.max() - want.min()), (a, err)
+        assert np.mean(np.sign(have) == np.sign(want)) >= 0.9999

@@ -137,16 +137,23 @@ def test_slabs_6d_pair_split_path(lsp):
         to, yo, _ = orc.ode_cfl3([to, 1.0], yo, osd, factor_cfl=0.8, single_step=True)
         yo = np.minimum(yo, y_last)
     want = yo.reshape(g.shape)
-    for be in (L.BACKEND_GATHER, L.BACKEND_TMA):
-        w = LocalWorld(sd, 2, backend=be)
+    got = {}
+    for be, pieces in ((L.BACKEND_GATHER, 1), (L.BACKEND_TMA, 1), (L.BACKEND_TMA, 3), (L.BACKEND_TMA, "auto")):
+        # pieces > 1: pass 2 in column pieces (hj_stage_pass_cols), each piece of the edge planes pushed to the neighbour
+        # as soon as it is computed (hj_halo_push with columns) and awaited piece by piece in the next stage
+        w = LocalWorld(sd, 2, backend=be, pieces=pieces)
         w.poison_halos = True        # pass 1 (hj_stage_pass) runs on NaN halos: it must not read them
         w.upload(d0)
         t = 0.0
         for _ in range(2):
             t, dt = w.step(t, 1.0, 0.8, comp=L.COMP_MIN_OVER_TIME)
         assert w.slabs[0].two_pass() == (be == L.BACKEND_TMA)   # the two-kernel protocol is what ran on the TMA backend
+        assert (w.slabs[0].pieces() is not None) == (be == L.BACKEND_TMA and pieces != 1)
         assert t == to
-        assert np.max(np.abs(w.download() - want)) <= 1e-9 * (want.max() - want.min())
+        got[(be, pieces)] = w.download()
+        assert np.max(np.abs(got[(be, pieces)] - want)) <= 1e-9 * (want.max() - want.min())
+    assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, 3)])      # the pieces change nothing, bit for bit
+    assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, "auto")])
 
 
 def test_stage_pass_equals_stage(lsp):
@@ -160,20 +167,29 @@ def test_stage_pass_equals_stage(lsp):
     sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
                          dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstWENO5a))
     outs = []
-    for two in (False, True):
+    for two in (0, 1, 2):
         eng, ad = prepare_scheme(sd)
         eng.set_backend(L.BACKEND_TMA)
         eng.upload(d0)
         eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(g))))
         assert eng.is_split()
+        V, q = eng.split_cols()
+        assert V == 18 * 34 and q > 0 and q % 2 == 0
         for stage in (1, 2, 3):
-            if two:
+            if two == 1:
                 eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, which_pass=1)
                 eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, which_pass=2)
+            elif two == 2:          # pass 2 in three uneven column pieces, last piece first (hj_stage_pass_cols)
+                eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME, which_pass=1)
+                for a, e in ((5 * q, V), (0, 2 * q), (2 * q, 5 * q)):
+                    eng.stage_cols(stage, a, e, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME)
             else:
                 eng.stage(stage, 0.0, 1e-3, None, L.COMP_MIN_OVER_TIME)
         outs.append(eng.download(shape=g.shape))
+        with pytest.raises(Exception):
+            eng.stage_cols(1, 1, V, 0.0, 1e-3)              # not a multiple of the quantum
     assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
     g3, d3 = _grid3(lsp, [26, 37, 34], [2])
     s3 = lsp.DubinsVehicleRel(g3, 5, 1)
     eng, ad = prepare_scheme(lsp.Bundle(dict(grid=g3, hamFunc=s3.hamiltonian, partialFunc=s3.dissipation,

@@ -149,6 +149,20 @@ int hj_add_ghost(hj_ctx* ctx, void* stream, const double* data_dev, int dim, int
 int hj_rhs(hj_ctx* ctx, void* stream, double t, const double* y_dev, double* ydot_dev, double* step_bound,
            double* reduce_host);
 
+/* The single hooks of the reference's operator API on dense device arrays, for a host that keeps the
+ * reference's termLaxFriedrichs and swaps one callable at a time; the fused stage kernels do not use them.
+ *   hj_ham       ham = hamFunc(t, data, derivC, schemeData): deriv_c_dev[d] = derivC of dim d (n doubles each)
+ *                (DynamicalSystems/dubins_relative.py:63-88, double_integrator.py:49-74, bird.py:266-316, flock.py:190-233)
+ *   hj_alpha     alpha = partialFunc(t, data, derivMin, derivMax, schemeData, dim) as a dense array of n doubles (every
+ *                registered system's alpha is state-only; dubins_relative.py:90-111, double_integrator.py:76-89)
+ *   hj_diss_glf  diss, stepBound = artificialDissipationGLF(t, data, derivL, derivR, schemeData)
+ *                (ExplicitIntegration/Dissipation/artificial_diss_glf.py:7-111): diss = sum_d 0.5 (R_d - L_d) alpha_d in the
+ *                reference's order; reduce_host (optional) receives HJ_REDUCE_LEN(D) doubles like hj_rhs; synchronises. */
+int hj_ham(hj_ctx* ctx, void* stream, double t, const double* const* deriv_c_dev, double* ham_dev);
+int hj_alpha(hj_ctx* ctx, void* stream, double t, int dim, double* alpha_dev);
+int hj_diss_glf(hj_ctx* ctx, void* stream, double t, const double* const* deriv_l_dev, const double* const* deriv_r_dev,
+                double* diss_dev, double* step_bound, double* reduce_host);
+
 /* max_x alpha_d for d = 0..D-1 without touching a field (state-only partialFunc); synchronises.
  * stepBound = 1 / sum_d alpha_max[d] / dx[d]  (artificial_diss_glf.py:104-109).                       */
 int hj_alpha_max(hj_ctx* ctx, void* stream, double t, double* alpha_max_host, double* step_bound);
@@ -245,6 +259,18 @@ int hj_ode_cfl3_step(hj_ctx* ctx, void* stream, double t, double t_end, double f
 /* Pinned (page-locked) host memory for those buffers. */
 int hj_host_alloc(int64_t bytes, void** out);
 int hj_host_free(void* p);
+
+/* Driver epilogues of HJIPDE_solve beyond the fused min / max (ValueFuncs/hji_solver.py), on the resident state:
+ *   hj_snapshot   keeps a device copy of the state (the frame at tau[i-1]; :509-533).
+ *   hj_change     max |state - snapshot| (stopConverge's "change", :661-672) and a NaN flag of the state (the check of
+ *                 :544) from one device reduction; synchronises; no field leaves the device.
+ *   hj_discount   discounting after a step: mode 0 (:603-611) y = gamma y + (1 - gamma) l with l = the HJ_FIELD_AUX field
+ *                 (target, or data0); mode 1 ("Kene", :615-637) y = gamma (y - m) min|max (l - m) + m with m = max_val =
+ *                 max |l| (take_max selects max: maxVWithL); mode 2: the obstacle mask on its own, y = max(y, -obstacle)
+ *                 (:641-644), for when discounting sits between the compMethod epilogue and the mask.                */
+int hj_snapshot(hj_ctx* ctx, void* stream);
+int hj_change(hj_ctx* ctx, void* stream, double* max_abs_change, int* has_nan);
+int hj_discount(hj_ctx* ctx, void* stream, double gamma, int mode, int take_max, double max_val);
 
 /* termRestrictUpdate (ExplicitIntegration/Term/term_restrict_update.py:56-96): restrict the sign of the update,
  * ydot = max(ydot, 0) (sign > 0, schemeData.positive true) or min(ydot, 0) (sign < 0), fused into every stage kernel

@@ -9,7 +9,7 @@ from .boundary import addGhostExtrapolate, addGhostPeriodic  # noqa: F401
 from .grids import createGrid, processGrid, flockGrid  # noqa: F401
 from .initial_conditions import *  # noqa: F401,F403
 from .spatial import upwindFirstWENO5, upwindFirstWENO5a, upwindFirstENO3a, upwindFirstENO3, upwindFirstENO2  # noqa: F401
-from .dissipation import artificialDissipationGLF  # noqa: F401
+from .dissipation import artificialDissipationGLF, artificialDissipationLLF  # noqa: F401
 from .term import termLaxFriedrichs, termRestrictUpdate  # noqa: F401
 from .integration import odeCFL3, odeCFL2, odeCFLset  # noqa: F401
 from .systems import DubinsVehicleRel, DoubleIntegrator, Bird, Flock, ProductSystem  # noqa: F401

@@ -42,6 +42,9 @@ SIGNATURES = {
     "hj_deriv": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "hj_add_ghost": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "hj_rhs": (_i, [_vp, _vp, _d, _vp, _vp, _pd, _pd]),
+    "hj_ham": (_i, [_vp, _vp, _d, C.POINTER(_vp), _vp]),
+    "hj_alpha": (_i, [_vp, _vp, _d, _i, _vp]),
+    "hj_diss_glf": (_i, [_vp, _vp, _d, C.POINTER(_vp), C.POINTER(_vp), _vp, _pd, _pd]),
     "hj_alpha_max": (_i, [_vp, _vp, _d, _pd, _pd]),
     "hj_step": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_step_reductions": (_i, [_vp, _vp, _pd]),
@@ -63,6 +66,9 @@ SIGNATURES = {
     "hj_ode_cfl3_step": (_i, [_vp, _vp, _d, _d, _d, _d, _vp, _vp, _i, _i, _i, _pd, _pd]),
     "hj_host_alloc": (_i, [_i64, C.POINTER(_vp)]),
     "hj_host_free": (_i, [_vp]),
+    "hj_snapshot": (_i, [_vp, _vp]),
+    "hj_change": (_i, [_vp, _vp, _pd, _pi]),
+    "hj_discount": (_i, [_vp, _vp, _d, _i, _i, _d]),
     "hj_set_restrict": (_i, [_vp, _i]),
     "hj_step_rk2": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_create_batch": (_i, [C.POINTER(_vp), _i, _i, _i, _pi64, _pd, _pi, _pi, _i]),

@@ -118,6 +118,7 @@ int hj_destroy(hj_ctx* c) {
   cudaFree(c->batch_params);
   cudaFree(c->aux);
   cudaFree(c->obs);
+  cudaFree(c->snap);
   cudaFree(c->staging);
   cudaFree(c->red);
   cudaFreeHost(c->pinned);
@@ -359,6 +360,58 @@ int hj_rhs(hj_ctx* c, void* stream, double t, const double* y_dev, double* ydot_
   st.red = red;
   st.epsmax = c->eps;
   CK(hj_launch_stage_gather(c->system_id, c->weno, c->gd, c->ks, st, s));
+  CK(cudaMemcpyAsync(c->pinned, red, RED_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double rec[RED_STRIDE];
+  decode_record((const unsigned long long*)c->pinned, c->D, rec);
+  if (reduce_host) std::memcpy(reduce_host, rec, HJ_REDUCE_LEN(c->D) * sizeof(double));
+  if (step_bound) *step_bound = step_bound_from_alpha(c, rec);
+  return HJ_OK;
+}
+
+static int sys_op_ready(hj_ctx* c, const char* who) {
+  int r = check_ready(c, true);
+  if (r) return r;
+  if (c->halo0 || c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "%s: dense-array entry point is not available on a slab / batch context", who);
+  return HJ_OK;
+}
+
+int hj_ham(hj_ctx* c, void* stream, double t, const double* const* deriv_c_dev, double* ham_dev) {
+  (void)t;
+  int r = sys_op_ready(c, "hj_ham");
+  if (r) return r;
+  if (!deriv_c_dev || !ham_dev) return fail(HJ_ERR_INVALID, "hj_ham: null argument");
+  for (int d = 0; d < c->D; ++d)
+    if (!deriv_c_dev[d]) return fail(HJ_ERR_INVALID, "hj_ham: deriv[%d] is null", d);
+  CK(cudaSetDevice(c->device));
+  CK(hj_launch_sys_op(c->system_id, 0, c->gd, c->ks, deriv_c_dev, nullptr, ham_dev, 0, nullptr, (cudaStream_t)stream));
+  return HJ_OK;
+}
+
+int hj_alpha(hj_ctx* c, void* stream, double t, int dim, double* alpha_dev) {
+  (void)t;
+  int r = sys_op_ready(c, "hj_alpha");
+  if (r) return r;
+  if (!alpha_dev) return fail(HJ_ERR_INVALID, "hj_alpha: null argument");
+  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "Illegal dim parameter");
+  CK(cudaSetDevice(c->device));
+  CK(hj_launch_sys_op(c->system_id, 1, c->gd, c->ks, nullptr, nullptr, alpha_dev, dim, nullptr, (cudaStream_t)stream));
+  return HJ_OK;
+}
+
+int hj_diss_glf(hj_ctx* c, void* stream, double t, const double* const* deriv_l_dev, const double* const* deriv_r_dev,
+                double* diss_dev, double* step_bound, double* reduce_host) {
+  (void)t;
+  int r = sys_op_ready(c, "hj_diss_glf");
+  if (r) return r;
+  if (!deriv_l_dev || !deriv_r_dev || !diss_dev) return fail(HJ_ERR_INVALID, "hj_diss_glf: null argument");
+  for (int d = 0; d < c->D; ++d)
+    if (!deriv_l_dev[d] || !deriv_r_dev[d]) return fail(HJ_ERR_INVALID, "hj_diss_glf: derivL/derivR[%d] is null", d);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* red = c->red + 3 * RED_STRIDE;
+  CK(hj_launch_init_reduce(red, c->D, s));
+  CK(hj_launch_sys_op(c->system_id, 2, c->gd, c->ks, deriv_l_dev, deriv_r_dev, diss_dev, 0, red, s));
   CK(cudaMemcpyAsync(c->pinned, red, RED_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   double rec[RED_STRIDE];
@@ -616,6 +669,51 @@ int hj_step(hj_ctx* c, void* stream, double t, double dt, const double* stage_pa
     r = stage_impl(c, (cudaStream_t)stream, stage, dt, p, comp, use_obstacle, want_reduce, true);
     if (r) return r;
   }
+  return HJ_OK;
+}
+
+int hj_snapshot(hj_ctx* c, void* stream) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_snapshot: no resident state (hj_upload first)");
+  CK(cudaSetDevice(c->device));
+  if (!c->snap) CK(cudaMalloc(&c->snap, c->elems * sizeof(double)));
+  CK(cudaMemcpyAsync(c->snap, c->buf[0], c->elems * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HJ_OK;
+}
+
+int hj_change(hj_ctx* c, void* stream, double* max_abs_change, int* has_nan) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_change: no resident state (hj_upload first)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* red = c->red + 3 * RED_STRIDE;
+  CK(cudaMemsetAsync(red, 0, 2 * sizeof(unsigned long long), s));      // enc_ordered(x) > 0 for every x >= 0
+  const double* cur = c->buf[0] + c->origin;
+  // without a snapshot the field is compared with itself: change 0, NaN flag only
+  const double* ref = c->snap ? c->snap + c->origin : cur;
+  CK(hj_launch_change(cur, ref, c->plane * c->gp.N[0], red, s));
+  CK(cudaMemcpyAsync(c->pinned, red, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const unsigned long long* h = (const unsigned long long*)c->pinned;
+  double m = 0.0;
+  if (h[0]) {
+    unsigned long long b = (h[0] >> 63) ? (h[0] & 0x7fffffffffffffffull) : ~h[0];
+    std::memcpy(&m, &b, 8);
+  }
+  if (max_abs_change) *max_abs_change = m;
+  if (has_nan) *has_nan = h[1] ? 1 : 0;
+  return HJ_OK;
+}
+
+int hj_discount(hj_ctx* c, void* stream, double gamma, int mode, int take_max, double max_val) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (!c->have_state) return fail(HJ_ERR_STATE, "hj_discount: no resident state (hj_upload first)");
+  if (mode < 0 || mode > 2) return fail(HJ_ERR_INVALID, "check your discountFactor and discountMode");     // :638
+  const double* ref = mode == 2 ? c->obs : c->aux;
+  if (!ref) return fail(HJ_ERR_STATE, mode == 2 ? "obstacle field not uploaded" : "Need to define target function l(x)!");   // :617
+  CK(cudaSetDevice(c->device));
+  CK(hj_launch_discount(c->buf[0] + c->origin, ref + c->origin, c->plane * c->gp.N[0], gamma, mode, take_max, max_val,
+                        (cudaStream_t)stream));
   return HJ_OK;
 }
 

@@ -26,6 +26,7 @@ struct hj_ctx {
   double* buf[3] = {};           // y, y1, yHalf (base pointers incl. halo planes)
   double* aux = nullptr;
   double* obs = nullptr;
+  double* snap = nullptr;        // the state at the last hj_snapshot (driver: the frame at tau[i-1])
   double* staging = nullptr;     // dense staging for host <-> pitched conversion
   unsigned long long* red = nullptr;  // 4 reduction records (3 stages + scratch) + eps record
   unsigned long long* eps = nullptr;

@@ -253,6 +253,78 @@ inline int flat_blocks(long long n) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// The reference's per-callable operators on dense arrays, for hosts that keep termLaxFriedrichs and swap single hooks
+// (hamFunc, partialFunc, dissFunc):
+//   OP 0  ham   = hamFunc(t, data, derivC, schemeData)                     (dubins_relative.py:63-88 etc.)
+//   OP 1  alpha = partialFunc(t, data, derivMin, derivMax, schemeData, dl) as a dense array (state-only alphas)
+//   OP 2  diss  = sum_d 0.5 (R_d - L_d) alpha_d, summed d = 0..D-1 from 0 like artificial_diss_glf.py:100, plus the
+//         derivative min / max and max alpha reductions that give stepBound (:82-88, :104-109)
+struct KPtrs {
+  const double* a[HJ_MAX_DIM];
+  const double* b[HJ_MAX_DIM];
+};
+template <class Sys, int OP>
+__global__ void __launch_bounds__(256) k_sys_op(const KGrid g, const KSys ks, const KPtrs in, double* __restrict__ out,
+                                                const int dl, unsigned long long* red, const long long n) {
+  constexpr int D = Sys::ND;
+  RedAcc<D> acc;
+  acc.init();
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int idx[D];
+    long long r = e;
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) { idx[d] = (int)(r % g.N[d]); r /= g.N[d]; }
+    const typename Sys::Pt pt = Sys::load(idx, g, ks);
+    if (OP == 0) {
+      double pc[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) pc[d] = __ldg(in.a[d] + e);
+      out[e] = Sys::ham(pt, pc, ks);
+    } else if (OP == 1) {
+      out[e] = Sys::alpha(dl, pt, ks);
+    } else {
+      double diss = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double L = __ldg(in.a[d] + e), Rr = __ldg(in.b[d] + e), al = Sys::alpha(d, pt, ks);
+        diss = __dadd_rn(diss, __dmul_rn(__dmul_rn(0.5, __dsub_rn(Rr, L)), al));
+        acc.dmin[d] = fmin(acc.dmin[d], fmin(L, Rr));
+        acc.dmax[d] = fmax(acc.dmax[d], fmax(L, Rr));
+        acc.amax[d] = fmax(acc.amax[d], al);
+      }
+      out[e] = diss;
+    }
+  }
+  if (OP == 2) acc.flush(red);
+}
+
+struct SysOpLauncher {
+  int op;
+  const KGrid& g;
+  const KSys& ks;
+  const KPtrs& in;
+  double* out;
+  int dl;
+  unsigned long long* red;
+  cudaStream_t s;
+  bool ok = true;
+  template <class Sys>
+  void operator()() {
+    if constexpr (Sys::BASE_DIM == 0 && Sys::NSCRATCH == 0) {
+      long long n = 1;
+      for (int d = 0; d < Sys::ND; ++d) n *= g.N[d];
+      switch (op) {
+        case 0: k_sys_op<Sys, 0><<<flat_blocks(n), 256, 0, s>>>(g, ks, in, out, dl, red, n); break;
+        case 1: k_sys_op<Sys, 1><<<flat_blocks(n), 256, 0, s>>>(g, ks, in, out, dl, red, n); break;
+        case 2: k_sys_op<Sys, 2><<<flat_blocks(n), 256, 0, s>>>(g, ks, in, out, dl, red, n); break;
+        default: ok = false;
+      }
+    } else {
+      ok = false;
+    }
+  }
+};
+
 struct StageLauncher {
   int weno;
   const KGrid& g;
@@ -308,6 +380,20 @@ struct AlphaLauncher {
 cudaError_t hj_launch_stage_gather(int system_id, int weno, const KGrid& g, const KSys& ks, const KStage& st,
                                    cudaStream_t s) {
   StageLauncher l{weno, g, ks, st, s};
+  if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
+  if (!l.ok) return cudaErrorNotSupported;
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_sys_op(int system_id, int op, const KGrid& g, const KSys& ks, const double* const* a,
+                             const double* const* b, double* out, int dl, unsigned long long* red, cudaStream_t s) {
+  KPtrs in{};
+  for (int d = 0; d < g.D; ++d) {
+    in.a[d] = a ? a[d] : nullptr;
+    in.b[d] = b ? b[d] : nullptr;
+  }
+  SysOpLauncher l{op, g, ks, in, out, dl, red, s};
   if (!hj_dispatch_system(system_id, l)) return cudaErrorInvalidValue;
   if (!l.ok) return cudaErrorNotSupported;
   hj_count_launch(1);
@@ -374,6 +460,57 @@ cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s) {
 
 cudaError_t hj_launch_edge_halo(double* buf, long long plane, int n0, int side, double m, cudaStream_t s) {
   k_edge_halo<<<flat_blocks(plane), 256, 0, s>>>(buf, plane, n0, side, m);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+// driver epilogue helpers (hji_solver.py:603-672), pointwise over the pitched interior of a field
+// max |a - b| and a NaN flag of a (the change since the last frame: stopConverge, :661-672; the NaN check of :544)
+__global__ void __launch_bounds__(256) k_change(const double* __restrict__ a, const double* __restrict__ b, long long n,
+                                                unsigned long long* red) {
+  double m = 0.0;
+  int nan = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = a[i];
+    if (x != x) nan = 1;
+    else m = fmax(m, fabs(x - b[i]));
+  }
+  m = warp_max(m);
+  nan = __any_sync(0xffffffffu, nan);
+  if (threadIdx.x % 32 == 0) {
+    atomicMax(red, enc_ordered(m));
+    if (nan) atomicOr(red + 1, 1ull);
+  }
+}
+// discounting: mode 0 (:603-611) y = gamma y + (1 - gamma) ref;  mode 1 ("Kene", :615-637) shift below zero by
+// max |l|, discount, min / max with the shifted target, shift back
+__global__ void __launch_bounds__(256) k_discount(double* __restrict__ y, const double* __restrict__ ref, long long n,
+                                                  double gamma, int mode, int take_max, double max_val) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = y[i];
+    if (mode == 2) {                 // the obstacle mask on its own (:641-644): y = max(y, -obstacle)
+      v = nan_max(v, -ref[i]);
+    } else if (mode == 0) {
+      v = __dmul_rn(v, gamma);
+      v = __dadd_rn(v, __dmul_rn(1.0 - gamma, ref[i]));
+    } else {
+      double yt = __dmul_rn(__dsub_rn(v, max_val), gamma);
+      const double tt = __dsub_rn(ref[i], max_val);
+      yt = take_max ? nan_max(yt, tt) : nan_min(yt, tt);
+      v = __dadd_rn(yt, max_val);
+    }
+    y[i] = v;
+  }
+}
+
+cudaError_t hj_launch_change(const double* a, const double* b, long long n, unsigned long long* red, cudaStream_t s) {
+  k_change<<<flat_blocks(n), 256, 0, s>>>(a, b, n, red);
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t hj_launch_discount(double* y, const double* ref, long long n, double gamma, int mode, int take_max,
+                               double max_val, cudaStream_t s) {
+  k_discount<<<flat_blocks(n), 256, 0, s>>>(y, ref, n, gamma, mode, take_max, max_val);
   hj_count_launch(1);
   return cudaGetLastError();
 }

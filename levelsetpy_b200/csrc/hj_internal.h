@@ -13,6 +13,8 @@ cudaError_t hj_launch_stage_gather(int system_id, int weno, const KGrid& g, cons
                                    cudaStream_t s);
 cudaError_t hj_launch_deriv(int weno, const KGrid& g, const double* in, int dim, double* dl, double* dr,
                             const unsigned long long* epsmax, cudaStream_t s);
+cudaError_t hj_launch_sys_op(int system_id, int op, const KGrid& g, const KSys& ks, const double* const* a,
+                             const double* const* b, double* out, int dl, unsigned long long* red, cudaStream_t s);
 cudaError_t hj_launch_add_ghost(const KGrid& g, const double* in, int dim, int width, double* out, cudaStream_t s);
 cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, unsigned long long* red,
                                 cudaStream_t s);
@@ -21,6 +23,9 @@ cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long lo
 cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s);
 cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s);
 cudaError_t hj_launch_edge_halo(double* buf, long long plane, int n0, int side, double m, cudaStream_t s);
+cudaError_t hj_launch_change(const double* a, const double* b, long long n, unsigned long long* red, cudaStream_t s);
+cudaError_t hj_launch_discount(double* y, const double* ref, long long n, double gamma, int mode, int take_max,
+                               double max_val, cudaStream_t s);
 cudaError_t hj_launch_pack(const double* dense, double* pitched, const KGrid& g_dense, const KGrid& g_pitched,
                            cudaStream_t s);
 cudaError_t hj_launch_unpack(const double* pitched, double* dense, const KGrid& g_dense, const KGrid& g_pitched,

@@ -255,6 +255,42 @@ class Engine:
         D = self.D
         return get(), sb.value, dict(alphaMax=r[:D], derivMin=r[D:2 * D], derivMax=r[2 * D:3 * D], nan=bool(r[3 * D]))
 
+    def _ptr_list(self, arrays):
+        """(keep-alive list, C array of D device pointers) for a list of D dense arrays."""
+        if len(arrays) != self.D:
+            raise ValueError("need one array per grid dimension (%d), got %d" % (self.D, len(arrays)))
+        keep, ptrs = [], (C.c_void_p * self.D)()
+        for d, a in enumerate(arrays):
+            k, p = self._to_device(a)
+            keep.append(k)
+            ptrs[d] = p
+        return keep, ptrs
+
+    def ham(self, t, derivs):
+        """hamFunc(t, data, derivC, schemeData) on dense arrays (hj_ham); same kind / shape as ``derivs[0]``."""
+        keep, ptrs = self._ptr_list(derivs)
+        o, po, _, get = self._like(derivs[0], self.nodes, tuple(derivs[0].shape))
+        L.check(self.lib.hj_ham(self.h, self.stream(), float(t), ptrs, po))
+        return get()
+
+    def alpha(self, t, dim, like):
+        """partialFunc(..., dim) as a dense array shaped like ``like`` (hj_alpha)."""
+        o, po, _, get = self._like(like, self.nodes, tuple(like.shape))
+        L.check(self.lib.hj_alpha(self.h, self.stream(), float(t), int(dim), po))
+        return get()
+
+    def diss_glf(self, t, derivL, derivR):
+        """artificialDissipationGLF on dense arrays (hj_diss_glf): (diss, stepBound, reductions dict)."""
+        kl, pl = self._ptr_list(derivL)
+        kr, pr = self._ptr_list(derivR)
+        o, po, _, get = self._like(derivL[0], self.nodes, tuple(derivL[0].shape))
+        sb = C.c_double()
+        red = (C.c_double * (3 * self.D + 1))()
+        L.check(self.lib.hj_diss_glf(self.h, self.stream(), float(t), pl, pr, po, C.byref(sb), red))
+        r = np.array(red[:])
+        D = self.D
+        return get(), sb.value, dict(alphaMax=r[:D], derivMin=r[D:2 * D], derivMax=r[2 * D:3 * D])
+
     def alpha_max(self, t=0.0):
         a = (C.c_double * self.D)()
         sb = C.c_double()
@@ -321,6 +357,23 @@ class Engine:
     def is_split(self):
         """True if this context advances its (product) system as two kernels per stage (system and state set)."""
         return bool(self.lib.hj_is_split(self.h))
+
+    def snapshot(self):
+        """Device copy of the resident state (the frame the next ``change()`` compares with)."""
+        L.check(self.lib.hj_snapshot(self.h, self.stream()))
+
+    def change(self):
+        """(max |state - snapshot|, has_nan) from one device reduction (hji_solver.py:661-672, :544)."""
+        m, n = C.c_double(), C.c_int()
+        L.check(self.lib.hj_change(self.h, self.stream(), C.byref(m), C.byref(n)))
+        return m.value, bool(n.value)
+
+    def discount(self, gamma, mode=0, take_max=False, max_val=0.0):
+        L.check(self.lib.hj_discount(self.h, self.stream(), float(gamma), int(mode), int(bool(take_max)), float(max_val)))
+
+    def mask_obstacle(self):
+        """y = max(y, -obstacle) as its own pass (normally fused into stage 3)."""
+        self.discount(1.0, 2)
 
     def set_restrict(self, sign):
         """termRestrictUpdate: +1 -> ydot = max(ydot, 0); -1 -> min(ydot, 0); 0 -> off."""

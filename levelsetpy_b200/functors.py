@@ -129,11 +129,14 @@ class _Flock(Adapter):
               float(b.w_p + w_up)]
         return [float(W), float(a1), float(a2), float(cs[0, 0]), float(cs[1, 0])], al
 
-    def block(self):
+    def block(self, mutate=True):
+        """``mutate=False``: the block of the flock as it stands (partialFunc alone does not re-run the bookkeeping,
+        flock.py:236-258)."""
         o = self.o
         if self.mode == "flock":
-            o._housekeeping()                              # flock.py:213 -- mutates headings every RHS
-            o.attacked_idx = 0                             # flock.py:216
+            if mutate:
+                o._housekeeping()                          # flock.py:213 -- mutates headings every RHS
+                o.attacked_idx = 0                         # flock.py:216
             if len(o.vehicles) == 2:
                 raise IndexError("list index out of range")    # shapeUnion 2-shape bug, shape_ops.py:37
             att, others = o.vehicles[0], list(o.vehicles[1:])

@@ -31,17 +31,21 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
                 'zero': as shipped, identical to 'set' (the driver's termRestrictUpdate swap at :438-442 is never used
                 by its time loop, :542); 'minWithZero': as shipped, error (:599).  With extraArgs.restrictUpdate=True
                 both run the intended termRestrictUpdate(positive=0), ydot = min(ydot, 0), fused into every stage.
-    extraArgs : Bundle with optional ``quiet``, ``keepLast``, ``obstacleFunction`` (pointwise max(V, -obstacle),
-                the intended semantics of :641-644), ``targetFunction``, ``stopConverge`` + ``convergeThreshold``.
-                Time-varying obstacles/targets, discounting, SDModFunc, visualisation: NotImplementedError.
+    extraArgs : Bundle with optional ``quiet``, ``keepLast``, ``obstacleFunction`` (pointwise max(V, -obstacle), the
+                intended semantics of :641-644) and ``targetFunction`` -- static (grid.shape) or time-varying ((len(tau),)
+                + grid.shape: slice i serves the interval ending at tau[i], :596, :642-650) --, ``discountFactor`` with
+                ``discountMode`` (default :603-611, 'Kene' :615-637) and ``discountAnneal`` (:703-716), ``stopConverge``
+                + ``convergeThreshold`` (a device-side max-change reduction, no frame leaves the GPU for it),
+                ``stopInit`` (:676-685), ``stopSetInclude`` / ``stopSetIntersect`` + ``stopLevel`` (:688-698).
+                SDModFunc, ignoreBoundary, lowMemory / flipOutput, noise, visualisation: NotImplementedError.
     Returns ``data`` of shape grid.shape (keepLast) or (len(tau),) + grid.shape (time on axis 0, as :483-484
-    indexes it), ``tau`` (truncated if converged) and an ``extraOuts`` Bundle."""
+    indexes it), ``tau`` (truncated if stopped early) and an ``extraOuts`` Bundle (dts, steps, stoptau)."""
     if extraArgs is None:
         extraArgs = Bundle({})
     if not isfield(schemeData, "grid"):
         error("grid not in bundle schemeData")
-    for bad in ("SDModFunc", "discountFactor", "discountMode", "addGaussianNoiseStandardDeviation", "visualize",
-                "ignoreBoundary", "stopInit", "stopSetInclude", "stopSetIntersect", "saveFilename"):
+    for bad in ("SDModFunc", "addGaussianNoiseStandardDeviation", "visualize", "ignoreBoundary", "saveFilename",
+                "lowMemory", "flipOutput"):
         if isfield(extraArgs, bad) and getattr(extraArgs, bad):
             raise NotImplementedError("extraArgs.%s is outside the accelerated hot path" % bad)
     # 'zero' / 'minWithZero' AS SHIPPED: the driver builds a termRestrictUpdate scheme (hji_solver.py:438-442) but its
@@ -75,69 +79,184 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
     eng, ad = prepare_scheme(schemeData)
     grid = eng_grid(schemeData)
 
-    use_obs = False
+    gdim = len(tuple(g.shape))
+    tau = np.asarray(tau, dtype=np.float64)
+
+    def field_of(name, arr):
+        """(static array or None, time-varying stack or None) of an obstacle / target function (:205-238)."""
+        a = np.asarray(arr, dtype=np.float64)
+        if a.ndim == gdim and a.shape == tuple(g.shape):
+            return a, None
+        if a.ndim == gdim + 1 and a.shape[1:] == tuple(g.shape):
+            if a.shape[0] < len(tau):
+                raise ValueError("time-varying %s needs one slice per entry of tau" % name)
+            return None, a
+        raise ValueError("Inconsistent %s dimensions!" % name)              # :217, :236
+
+    use_obs, obs_tv = False, None
     if isfield(extraArgs, "obstacleFunction") and extraArgs.obstacleFunction is not None:
-        obs = np.asarray(extraArgs.obstacleFunction, dtype=np.float64)
-        if obs.shape != tuple(g.shape):
-            raise NotImplementedError("time-varying obstacleFunction is outside the accelerated hot path")
-        eng.upload(obs, L.FIELD_OBSTACLE)
+        obs, obs_tv = field_of("obstacle", extraArgs.obstacleFunction)
+        first = obs if obs is not None else obs_tv[0]
+        eng.upload(first, L.FIELD_OBSTACLE)
         use_obs = True
-        data0 = np.maximum(data0, -obs)                                 # hji_solver.py:222 (before the first frame is stored)
-    if comp in (L.COMP_MIN_WITH_AUX, L.COMP_MAX_WITH_AUX):
-        if compMethod in ("minVWithV0", "maxVWithV0"):
-            aux = data0
+        data0 = np.maximum(data0, -first)                               # hji_solver.py:222 (before the first frame is stored)
+    tgt, tgt_tv = None, None
+    if isfield(extraArgs, "targetFunction") and extraArgs.targetFunction is not None:
+        tgt, tgt_tv = field_of("target", extraArgs.targetFunction)
+
+    # discounting (:603-637): gamma in (0, 1]; 'Kene' replaces the compMethod epilogue, the default mode follows it
+    gamma = float(getattr(extraArgs, "discountFactor", 0) or 0)
+    kene = bool(gamma) and str(getattr(extraArgs, "discountMode", "")) == "Kene"
+    disc = None
+    if gamma:
+        if kene:
+            if tgt is None and tgt_tv is None:
+                error("Need to define target function l(x)!")           # :617
+            if compMethod not in ("minVWithL", "minVwithL", "minVWithTarget", "maxVWithL", "maxVwithL", "maxVWithTarget"):
+                error("check your compMethod!")                         # :634
+            disc = dict(gamma=gamma, mode=1, take_max=comp == L.COMP_MAX_WITH_AUX)
+            comp = L.COMP_NONE                                          # the min / max is part of the discount step
         else:
-            if not isfield(extraArgs, "targetFunction"):
+            disc = dict(gamma=gamma, mode=0, take_max=False)
+    aux_is_target = False
+    if comp in (L.COMP_MIN_WITH_AUX, L.COMP_MAX_WITH_AUX) or disc is not None:
+        if compMethod in ("minVWithV0", "maxVWithV0") or (disc is not None and tgt is None and tgt_tv is None):
+            aux = data0                                                 # V0, resp. (:610) the discount's fallback l = data0
+            if disc is not None and compMethod in ("minVWithV0", "maxVWithV0") and (tgt is not None or tgt_tv is not None):
+                raise NotImplementedError("discounting towards a target while comparing with V0 needs two auxiliary fields")
+        else:
+            if tgt is None and tgt_tv is None:
                 error("Need to define target function l(x)!")           # hji_solver.py:584
-            aux = np.asarray(extraArgs.targetFunction, dtype=np.float64)
-            if aux.shape != tuple(g.shape):
-                raise NotImplementedError("time-varying targetFunction is outside the accelerated hot path")
+            aux = tgt if tgt is not None else tgt_tv[0]
+            aux_is_target = True
         eng.upload(aux, L.FIELD_AUX)
     stopConverge = bool(getattr(extraArgs, "stopConverge", False))
     convergeThreshold = getattr(extraArgs, "convergeThreshold", 1e-5)
+    stops = _stop_conditions(extraArgs, g, gdim)
 
-    tau = np.asarray(tau, dtype=np.float64)
     eng.upload(data0)
     frames = None if keepLast else [data0.copy()]
-    last = data0
     extraOuts = Bundle(dict(dts=[], steps=0))
-    i_end = len(tau) - 1
     eng.set_restrict(restrict_sign)
     try:
         i_end, last = _march(eng, ad, grid, g, tau, comp, use_obs, quiet, keepLast, stopConverge, convergeThreshold,
-                             frames, last, extraOuts, small)
+                             frames, data0, extraOuts, small, obs_tv, tgt_tv if aux_is_target else None, disc, extraArgs,
+                             stops)
     finally:
         eng.set_restrict(0)
     data = last if keepLast else np.stack(frames, axis=0)
     return data, tau[: i_end + 1], extraOuts
 
 
+def _stop_conditions(extraArgs, g, gdim):
+    """stopInit (:240-242) and stopSetInclude / stopSetIntersect + stopLevel (:244-262), validated like the reference."""
+    out = {}
+    if isfield(extraArgs, "stopInit") and extraArgs.stopInit is not None:
+        p = np.asarray(extraArgs.stopInit, dtype=np.float64).reshape(-1)
+        if p.size != gdim:
+            raise ValueError("stopInit must be a vector of length g.dim!")
+        out["init"] = p
+    for name in ("stopSetInclude", "stopSetIntersect"):
+        if isfield(extraArgs, name) and getattr(extraArgs, name) is not None:
+            ss = np.asarray(getattr(extraArgs, name), dtype=np.float64)
+            if ss.shape != tuple(g.shape):
+                raise ValueError("Inconsistent stopSet dimensions!")
+            out["set"] = ss < 0                                            # the nodes of the stop set (:256)
+            out["all"] = name == "stopSetInclude"
+            out["level"] = float(getattr(extraArgs, "stopLevel", 0.0) or 0.0)
+            break
+    return out
+
+
+def _interp_at(g, data, p):
+    """Multilinear interpolation of ``data`` at the state ``p`` (what eval_u does for stopInit, :677); NaN outside."""
+    idx, w = [], []
+    for d in range(len(p)):
+        v = np.asarray(g.vs[d], dtype=np.float64).reshape(-1)
+        if not (v[0] <= p[d] <= v[-1]):
+            return float("nan")
+        k = int(min(max(np.searchsorted(v, p[d]) - 1, 0), v.size - 2))
+        idx.append(k)
+        w.append((p[d] - v[k]) / (v[k + 1] - v[k]))
+    val = 0.0
+    for corner in range(1 << len(p)):
+        c, ii = 1.0, []
+        for d in range(len(p)):
+            hi = (corner >> d) & 1
+            c *= w[d] if hi else 1.0 - w[d]
+            ii.append(idx[d] + hi)
+        val += c * float(data[tuple(ii)])
+    return val
+
+
 def _march(eng, ad, grid, g, tau, comp, use_obs, quiet, keepLast, stopConverge, convergeThreshold, frames, last,
-           extraOuts, small):
-    """The time loop of hji_solver.py:509-672 on the resident state; returns (index of the last tau reached, field)."""
+           extraOuts, small, obs_tv=None, tgt_tv=None, disc=None, extraArgs=None, stops=None):
+    """The time loop of hji_solver.py:509-728 on the resident state; returns (index of the last tau reached, field).
+    The field only leaves the device when a frame is asked for (not keepLast, the last tau, stopInit / stopSet); the NaN
+    check (:544) and stopConverge's max change (:661-672) are one device reduction per tau interval."""
+    stops = stops or {}
     i_end = len(tau) - 1
+    gamma = disc["gamma"] if disc else 0.0
+    max_val = 0.0
     for i in range(1, len(tau)):
         if not quiet:
             info("Computing value function at time tau[%d]: %.4f" % (i, tau[i]))
+        if obs_tv is not None:
+            eng.upload(obs_tv[i], L.FIELD_OBSTACLE)                     # :642-643: slice i masks the steps towards tau[i]
+        if tgt_tv is not None:
+            eng.upload(tgt_tv[i], L.FIELD_AUX)                          # :596, :648-650
+        if disc is not None and disc["mode"] == 1:
+            tg = tgt_tv[i] if tgt_tv is not None else extraArgs.targetFunction
+            max_val = float(np.max(np.abs(np.asarray(tg, dtype=np.float64))))       # :621
+        if stopConverge:
+            eng.snapshot()                                              # the frame at tau[i-1] (y0 of :522-532)
         tNow = float(tau[i - 1])
         while tNow < tau[i] - small:                                    # hji_solver.py:536
             tNow, dt = rk3_step_resident(eng, ad, grid, tNow, float(tau[i]), 0.8, np.finfo(np.float64).max,
-                                         comp, use_obs)
+                                         comp, use_obs and disc is None)
+            if disc is not None:                                        # :603-637, then the obstacle mask of :641-644
+                eng.discount(gamma, disc["mode"], disc["take_max"], max_val)
+                if use_obs:
+                    eng.mask_obstacle()
             extraOuts.dts.append(dt)
             extraOuts.steps += 1
-        if not keepLast or stopConverge or i == len(tau) - 1:
-            cur = eng.download(shape=tuple(g.shape))
-            if np.any(np.isnan(cur)):
-                error("Nans encountered in the integrated result of HJI PDE data")   # hji_solver.py:544
-            if frames is not None:
-                frames.append(cur)
-            if stopConverge:
-                change = float(np.max(np.abs(cur - last)))              # hji_solver.py:661-672
-                if not quiet:
-                    info("Max change since last iteration: %g" % change)
-                if change < convergeThreshold:
-                    last = cur
-                    i_end = i
-                    break
+        change, has_nan = eng.change()
+        if has_nan:
+            error("Nans encountered in the integrated result of HJI PDE data")       # hji_solver.py:544
+        need_frame = frames is not None or i == len(tau) - 1 or bool(stops)
+        cur = eng.download(shape=tuple(g.shape)) if need_frame else None
+        if frames is not None:
+            frames.append(cur)
+        if cur is not None:
             last = cur
+        stop = False
+        if stopConverge and not quiet:
+            info("Max change since last iteration: %g" % change)
+        if "init" in stops:                                             # :676-685
+            v = _interp_at(g, cur, stops["init"])
+            if not np.isnan(v) and v <= 0:
+                stop = True
+        if "set" in stops and not stop:                                 # :688-698
+            inside = cur[stops["set"]] <= stops["level"]
+            if (np.all(inside) if stops["all"] else np.any(inside)):
+                stop = True
+        if stopConverge and change < convergeThreshold and not stop:    # :700-726
+            anneal = getattr(extraArgs, "discountAnneal", None) if extraArgs is not None else None
+            if disc is not None and anneal and gamma != 1:
+                if anneal == "soft":
+                    gamma = 1 - ((1 - gamma) / 2)
+                    if abs(1 - gamma) < .00005:
+                        gamma = 1.0
+                elif anneal == "hard" or anneal == 1:
+                    gamma = 1.0
+                if not quiet:
+                    info("Discount factor: %s" % gamma)
+            else:
+                stop = True
+        if stop:
+            extraOuts.stoptau = float(tau[i])
+            i_end = i
+            if cur is None:
+                last = eng.download(shape=tuple(g.shape))
+            break
     return i_end, last

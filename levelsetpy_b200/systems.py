@@ -10,16 +10,31 @@ import numpy as np
 
 __all__ = ["DubinsVehicleRel", "DoubleIntegrator", "Bird", "Flock", "ProductSystem"]
 
-_MSG = ("%s.%s is a compiled device functor: it is evaluated inside the fused stage kernel "
-        "(termLaxFriedrichs / odeCFL3); there is no standalone CPU evaluation")
+def _device_op(owner, ham_name, part_name, mutate):
+    """(engine with this system's functor + parameter block set, adapter) for a standalone hamFunc / partialFunc call."""
+    from .engine import engine_for_grid
+    from .functors import _adapter_for_owner
+    ad = _adapter_for_owner(owner, ham_name, part_name)
+    eng = engine_for_grid(owner.grid)
+    block = ad.block(mutate) if ad.time_varying else ad.block()
+    eng.set_system(ad.system_id, block, list(enumerate(ad.tables(owner.grid))))
+    return eng, ad, block
 
 
 class _DeviceFunctorSystem:
+    """Inside odeCFL3 / termLaxFriedrichs these methods are only tokens that name the compiled functor.  Called on their
+    own -- by the reference's termLaxFriedrichs / artificialDissipationGLF, or by a user -- they evaluate that functor
+    on dense arrays on the device (C-ABI hj_ham / hj_alpha)."""
+
     def hamiltonian(self, t, data, value_derivs, finite_diff_bundle=None):
-        raise NotImplementedError(_MSG % (type(self).__name__, "hamiltonian"))
+        eng, _, _ = _device_op(self, "hamiltonian", "dissipation", True)
+        return eng.ham(t, list(value_derivs))
 
     def dissipation(self, t, data, derivMin, derivMax, schemeData, dim):
-        raise NotImplementedError(_MSG % (type(self).__name__, "dissipation"))
+        eng, ad, block = _device_op(self, "hamiltonian", "dissipation", False)
+        if ad.host_alpha:
+            return ad.alphas(block)[dim]                   # scalar alphas (bird.py:339-344, flock.py:248-258)
+        return eng.alpha(t, dim, data)
 
 
 class DubinsVehicleRel(_DeviceFunctorSystem):
@@ -99,10 +114,12 @@ class Bird(_DeviceFunctorSystem):
         return len(self.neighbors)
 
     def hamiltonian_abs(self, t, data, value_derivs, finite_diff_bundle=None):
-        raise NotImplementedError(_MSG % ("Bird", "hamiltonian_abs"))
+        eng, _, _ = _device_op(self, "hamiltonian_abs", "dissipation_abs", True)
+        return eng.ham(t, list(value_derivs))
 
     def dissipation_abs(self, t, data, derivMin, derivMax, schemeData, dim):
-        raise NotImplementedError(_MSG % ("Bird", "dissipation_abs"))
+        _, ad, block = _device_op(self, "hamiltonian_abs", "dissipation_abs", False)
+        return ad.alphas(block)[dim]
 
 
 class Flock(_DeviceFunctorSystem):

@@ -19,8 +19,10 @@ def prepare_scheme(schemeData):
     name = getattr(sd.CoStateCalc, "__name__", None)
     if name not in _COSTATE:
         raise NotImplementedError("CoStateCalc=%r: only upwindFirstWENO5(a) / upwindFirstENO3(a) / upwindFirstENO2 run on the device" % (sd.CoStateCalc,))
-    if getattr(sd.dissFunc, "__name__", None) != "artificialDissipationGLF":
-        raise NotImplementedError("dissFunc=%r: only artificialDissipationGLF is fused into the stage kernel" % (sd.dissFunc,))
+    diss_name = getattr(sd.dissFunc, "__name__", None)
+    if diss_name not in ("artificialDissipationGLF", "artificialDissipationLLF"):
+        raise NotImplementedError("dissFunc=%r: only artificialDissipationGLF / artificialDissipationLLF are fused into "
+                                  "the stage kernel" % (sd.dissFunc,))
     adapter = sd.__dict__.get("_hjb200_adapter")
     if adapter is None or adapter[0] is not sd.hamFunc or adapter[1] is not sd.partialFunc:
         ad = resolve(sd.hamFunc, sd.partialFunc, sd.grid)
@@ -30,6 +32,10 @@ def prepare_scheme(schemeData):
             pass
     else:
         ad = adapter[2]
+    if diss_name == "artificialDissipationLLF" and not ad.host_alpha:
+        # as shipped LLF only runs for systems whose alphas are all scalars (Bird, Flock), where it equals GLF; with an
+        # array alpha its `(1 / stepBoundInv).get().item()` raises (diss_local_laxfried.py:126-134)
+        raise ValueError("can only convert an array of size 1 to a Python scalar")
     eng = engine_for_grid(sd.grid, weno_mode_of(sd))
     return eng, ad
 

@@ -409,25 +409,38 @@ def ode_cfl3_restricted(tspan, y0, sd, positive, factor_cfl=0.5, max_step=REALMA
 
 
 def hji_solve(data0, tau, sd, comp_method="minVOverTime", obstacle=None, target=None, weno="as_shipped",
-              factor_cfl=0.8):
-    """The driver loop of ValueFuncs/hji_solver.py:509-656 in ``keepLast`` mode (the only storage mode
+              factor_cfl=0.8, discount=None, discount_mode=None, stop_converge=False, converge_threshold=1e-5):
+    """The driver loop of ValueFuncs/hji_solver.py:509-728 in ``keepLast`` mode (the only storage mode
     that works in general): for each tau[i] single-step odeCFL3 until tau[i]-1e-4
-    (:536-542, small=1e-4 at :127... used at :536), then the compMethod epilogue (:566-599) and the obstacle
-    mask (:641-644, intended pointwise max; the shipped ``omax`` returns a scalar, matlab_utils.py:102-112).
+    (:536-542, small=1e-4 at :127... used at :536), then the compMethod epilogue (:566-599), discounting (:603-637,
+    intended: the shipped branch trips over ``eisfield`` / ``extraArgs.targets``) and the obstacle mask (:641-644,
+    intended pointwise max; the shipped ``omax`` returns a scalar, matlab_utils.py:102-112).  ``obstacle`` / ``target``
+    with one more dim than the grid are time-varying: slice i serves the interval ending at tau[i] (:642-650; slice 0
+    masks data0, :213-222).  ``stop_converge``: stop after the interval whose max |y - y(tau[i-1])| is below the
+    threshold (:661-672, :700-726).
 
     Returns (data, [all dt], [t after every step])."""
     small = 1e-4
     grid = sd.grid
+    gdim = len(grid.shape)
     data = np.asarray(data0, dtype=np.float64)
-    obs = None if obstacle is None else np.expand_dims(np.asarray(obstacle, dtype=np.float64).flatten(), 1)
+    col = lambda a: np.expand_dims(np.asarray(a, dtype=np.float64).flatten(), 1)
+    obs_tv = obstacle is not None and np.ndim(obstacle) == gdim + 1
+    tgt_tv = target is not None and np.ndim(target) == gdim + 1
+    obs = None if obstacle is None else col(obstacle[0] if obs_tv else obstacle)
     if obstacle is not None:
-        data = np.maximum(data, -np.asarray(obstacle, dtype=np.float64))   # :222: data0 is masked before the march
-    d0 = np.expand_dims(data.flatten(), 1)                                  # 'minVWithV0' sees the masked data0
-    tgt = None if target is None else np.expand_dims(np.asarray(target, dtype=np.float64).flatten(), 1)
+        data = np.maximum(data, -obs.reshape(grid.shape))                   # :222: data0 is masked before the march
+    d0 = col(data)                                                          # 'minVWithV0' sees the masked data0
+    tgt = None if target is None else col(target[0] if tgt_tv else target)
     dts, ts = [], []
     for i in range(1, len(tau)):
-        y = np.expand_dims(data.flatten(), 1)                              # :532
+        y = col(data)                                                       # :532
+        y_start = y
         t_now = tau[i - 1]
+        if obs_tv:
+            obs = col(obstacle[i])                                          # :642-643
+        if tgt_tv:
+            tgt = col(target[i])                                            # :596, :648-650
         while t_now < tau[i] - small:                                      # :536
             y_last = y
             t_now, y, dt = ode_cfl3(                                       # :542 (singleStep='on', factorCFL=0.8 :445)
@@ -436,23 +449,47 @@ def hji_solve(data0, tau, sd, comp_method="minVOverTime", obstacle=None, target=
             ts.append(t_now)
             if np.any(np.isnan(y)):                                        # :544
                 raise ValueError("Nans encountered in the integrated result of HJI PDE data")
-            if comp_method in (None, "none", "set", "zero"):
-                pass
-            elif comp_method == "minVOverTime":
-                y = np.minimum(y, y_last)                                  # :571-573
-            elif comp_method == "maxVOverTime":
-                y = np.maximum(y, y_last)
-            elif comp_method == "minVWithV0":
-                y = np.minimum(y, d0)
-            elif comp_method == "maxVWithV0":
-                y = np.maximum(y, d0)
-            elif comp_method in ("minVWithL", "minVwithL", "minVWithTarget"):                # :592
-                y = np.minimum(y, tgt)
-            elif comp_method in ("maxVWithL", "maxVwithL", "maxVWithTarget"):                # :583
-                y = np.maximum(y, tgt)
+            is_min = comp_method in ("minVWithL", "minVwithL", "minVWithTarget")
+            is_max = comp_method in ("maxVWithL", "maxVwithL", "maxVWithTarget")
+            if discount and discount_mode == "Kene":                        # :615-637
+                if tgt is None:
+                    raise ValueError("Need to define target function l(x)!")
+                max_val = np.max(np.abs(tgt))
+                yt = (y - max_val) * discount
+                tt = tgt - max_val
+                if is_min:
+                    yt = np.minimum(yt, tt)
+                elif is_max:
+                    yt = np.maximum(yt, tt)
+                else:
+                    raise ValueError("check your compMethod!")
+                y = yt + max_val
             else:
-                raise ValueError("Check which compMethod you are using")
+                if comp_method in (None, "none", "set", "zero"):
+                    pass
+                elif comp_method == "minVOverTime":
+                    y = np.minimum(y, y_last)                              # :571-573
+                elif comp_method == "maxVOverTime":
+                    y = np.maximum(y, y_last)
+                elif comp_method == "minVWithV0":
+                    y = np.minimum(y, d0)
+                elif comp_method == "maxVWithV0":
+                    y = np.maximum(y, d0)
+                elif is_min:                                               # :592
+                    y = np.minimum(y, tgt)
+                elif is_max:                                               # :583
+                    y = np.maximum(y, tgt)
+                else:
+                    raise ValueError("Check which compMethod you are using")
+                if discount:                                               # :603-611
+                    y = y * discount
+                    y = y + (1 - discount) * (tgt if tgt is not None else d0)
             if obs is not None:
                 y = np.maximum(y, -obs)                                    # :641-644 (intended)
         data = y.reshape(grid.shape)                                       # :652
+        if stop_converge and np.max(np.abs(y - y_start)) < converge_threshold:   # :672, :700
+            hji_solve.last_index = i
+            break
+    else:
+        hji_solve.last_index = len(tau) - 1
     return data, dts, ts

@@ -44,10 +44,13 @@ def test_no_cpu_fallback_without_gpu(lsp):
     with pytest.raises(Exception) as ei:
         lsp.termLaxFriedrichs(0.0, np.zeros((441, 1)), sd)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
-    with pytest.raises(NotImplementedError):
-        s.hamiltonian(0, None, None, None)
-    with pytest.raises(NotImplementedError):
-        lsp.artificialDissipationGLF(0, None, None, None, None)
+    # the single hooks are device operators too (hj_ham / hj_diss_glf): without a GPU they fail the same loud way
+    z = [np.zeros((21, 21)), np.zeros((21, 21))]
+    for call in (lambda: s.hamiltonian(0, z[0], z, None),
+                 lambda: lsp.artificialDissipationGLF(0, z[0], z, z, sd)):
+        with pytest.raises(Exception) as ei:
+            call()
+        assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
 
 
 def test_product_package_never_imports_oracle():

@@ -193,3 +193,103 @@ def test_ode_cfl3_single_refuses_flock(lsp):
     y = np.ascontiguousarray(gold["data0"].reshape(-1)).copy()
     with pytest.raises(NotImplementedError):
         eng.ode_cfl3_single(0.0, 1.0, 0.8, np.finfo(np.float64).max, y)
+
+
+def _fields(g, nt):
+    x = np.meshgrid(*[v.reshape(-1) for v in g.vs], indexing="ij")
+    s = np.linspace(0.0, 1.0, nt).reshape(-1, 1, 1, 1)
+    target = np.sqrt((x[0] - 3.0 - 2.0 * s) ** 2 + (x[1] + 1.0) ** 2) - 4.0 + 0.2 * np.cos(x[2])
+    obstacle = np.sqrt((x[0] - 10.0) ** 2 + (x[1] - 2.0 + 3.0 * s) ** 2) - 3.0 + 0.0 * x[2]
+    return target, obstacle
+
+
+def test_hjipde_time_varying_target_and_obstacle(lsp):
+    """Moving target / obstacle stacks (len(tau),) + grid.shape: slice i serves the interval ending at tau[i]
+    (hji_solver.py:596, :642-650), slice 0 masks data0 (:213-222); static and moving fields mix freely."""
+    g, d0 = air3d(lsp, [24, 20, 18], perturb=0.05)
+    sd, osd = bundles(lsp, g)
+    tau = np.array([0.0, 0.05, 0.1, 0.15])
+    tgt, obs = _fields(g, len(tau))
+    for comp, t_arg, o_arg in (("minVWithTarget", tgt, obs), ("maxVWithTarget", tgt, obs[1]), ("minVOverTime", None, obs),
+                               ("minVWithL", tgt[2], obs)):
+        extra = lsp.Bundle(dict(quiet=True, keepLast=True, obstacleFunction=o_arg))
+        if t_arg is not None:
+            extra.targetFunction = t_arg
+        data, _, out = lsp.HJIPDE_solve(d0, tau, sd, comp, extra)
+        want, dts, _ = orc.hji_solve(d0, tau, osd, comp, obstacle=o_arg, target=t_arg)
+        assert list(out.dts) == list(dts)
+        assert float(np.max(np.abs(data - want))) <= FIELD_TOL * rng_of(want), comp
+    with pytest.raises(ValueError, match="Inconsistent"):
+        lsp.HJIPDE_solve(d0, tau, sd, "minVWithTarget", lsp.Bundle(dict(quiet=True, keepLast=True, targetFunction=tgt[:, :5])))
+
+
+@pytest.mark.parametrize("mode", [None, "Kene"])
+def test_hjipde_discounting(lsp, mode):
+    """Discounted value functions (hji_solver.py:603-637): default mode y = gamma y + (1 - gamma) l after the compMethod
+    epilogue, 'Kene' mode shifts below zero, discounts, then takes the min / max with the shifted target; the obstacle
+    mask follows both (:641-644)."""
+    g, d0 = air3d(lsp, [24, 20, 18], perturb=0.05)
+    sd, osd = bundles(lsp, g)
+    tau = np.array([0.0, 0.05, 0.1])
+    tgt, obs = _fields(g, len(tau))
+    cases = [("minVWithTarget", tgt[0], None), ("maxVWithL", tgt, obs[0])]
+    if mode is None:
+        cases += [("minVOverTime", None, None), ("set", None, obs)]          # discount towards data0 (:610)
+    for comp, t_arg, o_arg in cases:
+        extra = lsp.Bundle(dict(quiet=True, keepLast=True, discountFactor=0.97))
+        if mode:
+            extra.discountMode = mode
+        if t_arg is not None:
+            extra.targetFunction = t_arg
+        if o_arg is not None:
+            extra.obstacleFunction = o_arg
+        data, _, out = lsp.HJIPDE_solve(d0, tau, sd, comp, extra)
+        want, dts, _ = orc.hji_solve(d0, tau, osd, comp, obstacle=o_arg, target=t_arg, discount=0.97, discount_mode=mode)
+        assert list(out.dts) == list(dts)
+        assert float(np.max(np.abs(data - want))) <= FIELD_TOL * rng_of(want), (comp, mode)
+    if mode == "Kene":
+        with pytest.raises(ValueError):
+            lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, keepLast=True, discountFactor=0.9,
+                                                                       discountMode="Kene", targetFunction=tgt[0])))
+
+
+def test_hjipde_stop_conditions(lsp):
+    """stopConverge from the device-side change reduction (no frame leaves the GPU for it in keepLast mode), stopInit
+    (:676-685) and stopSetIntersect / stopSetInclude (:688-698) against the host evaluation of the same rules on the
+    frames of an unstopped run."""
+    g, d0 = air3d(lsp, [24, 20, 18])
+    sd, osd = bundles(lsp, g)
+    tau = np.linspace(0.0, 0.3, 7)
+    frames, _, _ = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True)))
+    changes = [float(np.max(np.abs(frames[i] - frames[i - 1]))) for i in range(1, len(tau))]
+    thr = 0.5 * (changes[2] + changes[3]) if changes[3] < changes[2] else 1.0001 * max(changes)
+    first = next(i for i, c in enumerate(changes, 1) if c < thr)
+    data, tau_c, out = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime",
+                                        lsp.Bundle(dict(quiet=True, keepLast=True, stopConverge=True, convergeThreshold=thr)))
+    assert len(tau_c) == first + 1 and out.stoptau == tau[first]
+    assert np.array_equal(data, frames[first])
+    want, _, _ = orc.hji_solve(d0, tau, osd, "minVOverTime", stop_converge=True, converge_threshold=thr)
+    assert orc.hji_solve.last_index == first
+    assert float(np.max(np.abs(data - want))) <= FIELD_TOL * rng_of(want)
+    # stopInit: a state the growing reachable set reaches (value <= 0 at that state, multilinear interpolation)
+    p = np.array([5.6, 0.3, 1.0])
+    from levelsetpy_b200.solver import _interp_at
+    vals = [_interp_at(g, frames[i], p) for i in range(len(tau))]
+    assert vals[0] > 0 and vals[-1] <= 0, vals
+    hit = next(i for i in range(1, len(tau)) if vals[i] <= 0)
+    _, tau_i, out_i = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, keepLast=True, stopInit=p)))
+    assert len(tau_i) == hit + 1 and out_i.stoptau == tau[hit]
+    with pytest.raises(ValueError):
+        lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, stopInit=p[:2])))
+    # stop sets: a small ball around that state; Intersect fires when any of its nodes is inside, Include when all are
+    x = np.meshgrid(*[v.reshape(-1) for v in g.vs], indexing="ij")
+    ball = np.sqrt((x[0] - p[0]) ** 2 + (x[1] - p[1]) ** 2) - 1.2 + 0.0 * x[2]
+    inside = [frames[i][ball < 0] <= 0 for i in range(len(tau))]
+    any_i = next((i for i in range(1, len(tau)) if inside[i].any()), None)
+    all_i = next((i for i in range(1, len(tau)) if inside[i].all()), None)
+    assert any_i is not None
+    _, tau_s, _ = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, keepLast=True, stopSetIntersect=ball)))
+    assert len(tau_s) == any_i + 1
+    _, tau_a, _ = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, keepLast=True, stopSetInclude=ball)))
+    assert len(tau_a) == (all_i + 1 if all_i is not None else len(tau))
+    assert all_i is None or all_i >= any_i

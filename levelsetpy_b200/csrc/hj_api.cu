@@ -502,8 +502,11 @@ int hj_device_count(void) {
 
 static bool use_tma(hj_ctx* c) {
   if (c->backend == HJ_BACKEND_GATHER) return false;
-  if (c->weno == HJ_SCHEME_ENO3A || c->weno == HJ_SCHEME_ENO2) {      // the ENO functors run on the gather backend
-    c->plan_err = "upwindFirstENO2 / upwindFirstENO3a are compiled for the gather backend only";
+  if ((c->weno == HJ_SCHEME_ENO3A || c->weno == HJ_SCHEME_ENO2) &&
+      !(c->system_id == HJ_SYS_DUBINS_REL || c->system_id == HJ_SYS_FLOCK)) {
+    // the ENO functors are compiled into the plane-ring kernel for whole 3-D systems; product systems, 2-D grids and
+    // batches take the gather backend
+    c->plan_err = "upwindFirstENO2 / upwindFirstENO3a: plane-ring kernels exist for whole 3-D systems only";
     return false;
   }
   if (!c->plan_tried) {

@@ -301,15 +301,19 @@ struct RedAcc {
     for (int d = 0; d < D; ++d) { amax[d] = -INFINITY; dmin[d] = INFINITY; dmax[d] = -INFINITY; }
     nan = 0;
   }
-  // block-wide: warp shuffles, then one atomic per warp per slot (REDG on distinct addresses)
+  // block-wide: warp shuffles, then at most one atomic per warp per slot -- and only when the warp's value would
+  // change the record (a plain load of the current record filters almost all of them: half a million CTAs hammering
+  // 3 D addresses serialise in L2 otherwise; a stale read only costs a redundant atomic)
   HJ_DEV void flush(unsigned long long* red) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const double a = warp_max(amax[d]), lo = warp_min(dmin[d]), hi = warp_max(dmax[d]);
       if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0) {
-        atomicMax(red + d, enc_ordered(a));
-        atomicMin(red + D + d, enc_ordered(lo));
-        atomicMax(red + 2 * D + d, enc_ordered(hi));
+        const volatile unsigned long long* cur = red;
+        const unsigned long long ea = enc_ordered(a), el = enc_ordered(lo), eh = enc_ordered(hi);
+        if (ea > cur[d]) atomicMax(red + d, ea);
+        if (el < cur[D + d]) atomicMin(red + D + d, el);
+        if (eh > cur[2 * D + d]) atomicMax(red + 2 * D + d, eh);
       }
     }
     const int any = __any_sync(0xffffffffu, nan);

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) k_alpha_max(const KGrid g, const KSys ks,
     amax = fmax(amax, Sys::alpha(dl, pt, ks));
   }
   amax = warp_max(amax);
-  if (threadIdx.x % 32 == 0) atomicMax(red + dl, enc_ordered(amax));
+  if (threadIdx.x % 32 == 0 && enc_ordered(amax) > *(const volatile unsigned long long*)(red + dl))
+    atomicMax(red + dl, enc_ordered(amax));
 }
 
 // intended WENO: eps_d = 1e-6 * max(D1_d^2) + 1e-99 over the unstripped D1 table (upwind_first_weno5a.py:154-156).
@@ -191,7 +192,10 @@ __global__ void __launch_bounds__(BX* BY) k_maxd1sq(const KGrid g, const double*
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const double m = warp_max(mx[d]);
-    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && m > 0.0) atomicMax(epsmax + d, enc_ordered(m));
+    // only a value that raises the record is worth an atomic (see RedAcc::flush)
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && m > 0.0 &&
+        enc_ordered(m) > *(const volatile unsigned long long*)(epsmax + d))
+      atomicMax(epsmax + d, enc_ordered(m));
   }
 }
 

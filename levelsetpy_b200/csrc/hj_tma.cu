@@ -36,6 +36,22 @@ template <class Sys> struct WholeCfg { using type = ProdCfg; };
 #define HJ_FB_R 8
 #endif
 template <> struct WholeCfg<SysFlockBatch> { using type = TmaCfg<HJ_FB_R, HJ_FB_MINB, 1, HJ_FB_TY, HJ_FB_TXP, false, 143, HJ_FB_GW, HJ_FB_XPAD>; };
+// 'intended' (true) WENO5 of a whole system: the smoothness indicators and the two divisions per dim need ~170 live
+// registers; at the 128 of two 256-thread CTAs per SM the body spills 90-400 bytes per thread.  One CTA of 384 threads
+// (32 x 24 tile) gets 168 registers: no spills, and the kernel is FP64-bound anyway (12 warps keep the pipe busy).
+#ifndef HJ_INT_TY
+#define HJ_INT_TY 24
+#define HJ_INT_MINB 1
+#endif
+template <class Sys, int WENO> struct WholeCfgW { using type = typename WholeCfg<Sys>::type; };
+template <> struct WholeCfgW<SysDubinsRel, HJ_WENO_INTENDED> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
+template <> struct WholeCfgW<SysFlock, HJ_WENO_INTENDED> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
+// upwindFirstENO3a / upwindFirstENO2 as CoStateCalc on the plane-ring backend: whole 3-D systems, the
+// same roomy configuration (the divided-difference tables of both sides are live together)
+template <> struct WholeCfgW<SysDubinsRel, HJ_SCHEME_ENO3A> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
+template <> struct WholeCfgW<SysDubinsRel, HJ_SCHEME_ENO2> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
+template <> struct WholeCfgW<SysFlock, HJ_SCHEME_ENO3A> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
+template <> struct WholeCfgW<SysFlock, HJ_SCHEME_ENO2> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
 template <class Sys> struct SplitCfg;
 // tile shapes of the 6-D pair; the -D overrides are a developer hook (HJ_EXTRA_NVCC_FLAGS in build.py).
 //   pass 1: 41 x 41 planes as two 42 x 21 tiles (14 consumer warps + two ghost warps on alternate planes, 1 CTA/SM,
@@ -154,9 +170,9 @@ struct TmaLauncher {
     const CUtensorMap& tm = p->tmap[in_buf];
     launches = 1;
     switch (st.stage) {
-      case 1: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 1, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
-      case 2: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 2, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
-      case 3: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 3, typename WholeCfg<Sys>::type>(p, tm, g, ks, st, s);
+      case 1: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 1, typename WholeCfgW<Sys, WENO>::type>(p, tm, g, ks, st, s);
+      case 2: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 2, typename WholeCfgW<Sys, WENO>::type>(p, tm, g, ks, st, s);
+      case 3: return launch_one<Sys, Sys::BASE_DIM + Sys::ND, WENO, RED, 3, typename WholeCfgW<Sys, WENO>::type>(p, tm, g, ks, st, s);
       default: return cudaErrorNotSupported;
     }
   }
@@ -203,7 +219,12 @@ struct TmaLauncher {
       else err = red ? split_by_stage<Sys, HJ_WENO_INTENDED, true>() : split_by_stage<Sys, HJ_WENO_INTENDED, false>();
     } else if constexpr (Sys::ND >= 3) {
       if (weno == HJ_WENO_AS_SHIPPED) err = red ? by_stage<Sys, HJ_WENO_AS_SHIPPED, true>() : by_stage<Sys, HJ_WENO_AS_SHIPPED, false>();
-      else err = red ? by_stage<Sys, HJ_WENO_INTENDED, true>() : by_stage<Sys, HJ_WENO_INTENDED, false>();
+      else if (weno == HJ_WENO_INTENDED) err = red ? by_stage<Sys, HJ_WENO_INTENDED, true>() : by_stage<Sys, HJ_WENO_INTENDED, false>();
+      else if constexpr (Sys::NSCRATCH == 0) {           // ENO functors: whole 3-D systems (not the batch functor)
+        if (weno == HJ_SCHEME_ENO3A) err = red ? by_stage<Sys, HJ_SCHEME_ENO3A, true>() : by_stage<Sys, HJ_SCHEME_ENO3A, false>();
+        else if (weno == HJ_SCHEME_ENO2) err = red ? by_stage<Sys, HJ_SCHEME_ENO2, true>() : by_stage<Sys, HJ_SCHEME_ENO2, false>();
+        else err = cudaErrorNotSupported;
+      } else err = cudaErrorNotSupported;
     } else {
       err = cudaErrorNotSupported;
     }
@@ -214,7 +235,7 @@ struct TmaLauncher {
 struct PlanShape {
   int txp = ProdCfg::TXP, ty = ProdCfg::TY, bw = ProdCfg::BW;
   bool split = false, thin = false;
-  int n0 = 0;
+  int n0 = 0, weno = HJ_WENO_AS_SHIPPED;
   int ns = 0, vb = 0, ta = 0, tb = 0;
   template <class Sys>
   void operator()() {
@@ -226,6 +247,9 @@ struct PlanShape {
       split = true;
       thin = pick_thin<P2, P2T>(n0);
       ns = P2::NS; vb = P2::VB; ta = thin ? P2T::TA : P2::TA; tb = thin ? P2T::TB : P2::TB;
+    } else if (weno != HJ_WENO_AS_SHIPPED) {              // intended WENO and the ENO functors share one configuration
+      using W = typename WholeCfgW<Sys, HJ_WENO_INTENDED>::type;
+      txp = W::TXP; ty = W::TY; bw = W::BW;
     } else {
       using W = typename WholeCfg<Sys>::type;
       txp = W::TXP; ty = W::TY; bw = W::BW;
@@ -235,10 +259,10 @@ struct PlanShape {
 
 HjTmaPlan* hj_tma_plan_create(const KGrid& g, int system_id, int weno, double* const bufs[3], int halo0, char* err,
                               int errlen, int tile_y) {
-  (void)weno;
   const int D = g.D;
   PlanShape shape;
   shape.n0 = g.N[0];
+  shape.weno = weno;
   if (!hj_dispatch_system(system_id, shape)) { snprintf(err, errlen, "unknown system"); return nullptr; }
   const int TY = tile_y > 0 ? tile_y : shape.ty;
   const int TX = 2 * shape.txp;

@@ -140,8 +140,11 @@ HJ_DEV void pc_hd(const double v0, const double v1, const double v2, const doubl
     hd = g.cb[d] * t;
     if (need_lr) { L = pc - hd; Rr = pc + hd; }
   } else {
+    // true WENO5, or the ENO3a / ENO2 candidates picked by minimum modulus (upwind_first_eno3a.py:104-140,
+    // upwind_first_eno2.py:137-148) -- the same device functions the gather backend runs, so the divided-difference
+    // tables and the choices made from them are bit-identical on both backends
     const double v[7] = {v0, v1, v2, v3, v4, v5, v6};
-    upwind5_weno(v, g.dxinv[d], inv_eps, L, Rr);
+    upwind5<WENO>(v, g.dxinv[d], inv_eps, L, Rr, g.dx[d]);
     pc = 0.5 * (L + Rr);
     hd = 0.5 * (Rr - L);
   }

@@ -114,19 +114,30 @@ def test_device_eno_vs_golden(lsp, name, scheme):
 
 
 @pytest.mark.gpu
-def test_device_eno_refuses_tma_backend(lsp):
-    """The ENO functors are compiled for the gather backend: forcing the plane-ring backend fails loudly."""
+@pytest.mark.parametrize("scheme", ["eno2", "eno3a"])
+def test_device_eno_on_both_backends(lsp, scheme):
+    """The ENO functors run in the plane-ring (TMA) kernel too for whole 3-D systems: same device functions, so the two
+    backends agree bit for bit, and both match the reference-generated golden after three odeCFL3 steps."""
     from levelsetpy_b200 import _lib as L
     gold = load_golden("eno_schemes")
     g, mk, d0 = _case(lsp, gold, "air3d")
     s = mk(lsp)
+    fn = lsp.upwindFirstENO2 if scheme == "eno2" else lsp.upwindFirstENO3a
     sd = lsp.Bundle(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation,
-                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=lsp.upwindFirstENO2))
-    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
-    eng = lsp.engine_for_grid(g, "eno2")
-    eng.set_backend(L.BACKEND_TMA)
+                         dissFunc=lsp.artificialDissipationGLF, CoStateCalc=fn))
+    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="off")))
+    eng = lsp.engine_for_grid(g, scheme)
+    out = {}
     try:
-        with pytest.raises(Exception):
-            lsp.odeCFL3(lsp.termLaxFriedrichs, [0.0, 1.0], np.expand_dims(d0.flatten(), 1), opts, sd)
+        for be in (L.BACKEND_GATHER, L.BACKEND_TMA):
+            eng.set_backend(be)
+            t, y, _ = lsp.odeCFL3(lsp.termLaxFriedrichs, [0.0, float(gold["air3d_%s_t" % scheme][2])],
+                                  np.expand_dims(d0.flatten(), 1), opts, sd)
+            out[be] = y
+            assert t == gold["air3d_%s_t" % scheme][2]
     finally:
         eng.set_backend(L.BACKEND_AUTO)
+    want = gold["air3d_%s_y" % scheme]
+    rng = float(want.max() - want.min())
+    assert np.max(np.abs(out[L.BACKEND_TMA] - want)) <= 1e-9 * rng
+    assert np.array_equal(out[L.BACKEND_GATHER], out[L.BACKEND_TMA])

@@ -272,10 +272,14 @@ def test_hjipde_stop_conditions(lsp):
     assert orc.hji_solve.last_index == first
     assert float(np.max(np.abs(data - want))) <= FIELD_TOL * rng_of(want)
     # stopInit: a state the growing reachable set reaches (value <= 0 at that state, multilinear interpolation)
-    p = np.array([5.6, 0.3, 1.0])
     from levelsetpy_b200.solver import _interp_at
+    cand = np.argwhere((frames[0] > 0) & (frames[-1] <= 0))            # nodes the growing reachable set swallows
+    assert len(cand) > 0
+    node = cand[len(cand) // 2]
+    p = np.array([float(np.asarray(g.vs[d]).reshape(-1)[node[d]]) for d in range(3)])
     vals = [_interp_at(g, frames[i], p) for i in range(len(tau))]
     assert vals[0] > 0 and vals[-1] <= 0, vals
+    assert vals[2] == frames[2][tuple(node)]                           # at a node the interpolant is the node value
     hit = next(i for i in range(1, len(tau)) if vals[i] <= 0)
     _, tau_i, out_i = lsp.HJIPDE_solve(d0, tau, sd, "minVOverTime", lsp.Bundle(dict(quiet=True, keepLast=True, stopInit=p)))
     assert len(tau_i) == hit + 1 and out_i.stoptau == tau[hit]

@@ -160,7 +160,11 @@ __global__ void __launch_bounds__(BX* BY) k_maxd1sq(const KGrid g, const double*
   double mx[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) mx[d] = 0.0;
-  for (long long o = blockIdx.y; o < nouter; o += gridDim.y) {
+  // a CTA walks a CONTIGUOUS run of outer indices (the +1 neighbour along the slowest dims is then the next
+  // iteration's node: an L1 / L2 hit), and the grid is a few CTAs per SM, not one CTA per 256 nodes
+  const long long per = (nouter + gridDim.y - 1) / gridDim.y;
+  const long long o_end = min(nouter, (long long)(blockIdx.y + 1) * per);
+  for (long long o = (long long)blockIdx.y * per; o < o_end; ++o) {
     if (!active) continue;
     int idx[D];
     decompose_outer<D>(o, g, idx);
@@ -249,6 +253,14 @@ long long outer_count(const KGrid& g) {
 inline dim3 tile_grid(const KGrid& g, int D, long long nouter) {
   const int xt = (g.N[D - 1] + BX - 1) / BX, yt = (g.N[D - 2] + BY - 1) / BY;
   return dim3((unsigned)(xt * yt), (unsigned)(nouter < 65535 ? nouter : 65535), 1);
+}
+
+// (X, Y) tiles x as many runs of the outer index as give ~16 CTAs per SM
+inline dim3 walk_grid(const KGrid& g, int D, long long nouter) {
+  const int xt = (g.N[D - 1] + BX - 1) / BX, yt = (g.N[D - 2] + BY - 1) / BY;
+  long long gy = (148LL * 16 + (long long)xt * yt - 1) / ((long long)xt * yt);
+  gy = gy < 1 ? 1 : (gy > nouter ? nouter : gy);
+  return dim3((unsigned)(xt * yt), (unsigned)(gy < 65535 ? gy : 65535), 1);
 }
 
 inline int flat_blocks(long long n) {
@@ -440,11 +452,11 @@ cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long lo
                               cudaStream_t s) {
   const dim3 block(BX, BY);
   switch (g.D) {
-    case 2: { long long no = outer_count<2>(g); k_maxd1sq<2><<<tile_grid(g, 2, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
-    case 3: { long long no = outer_count<3>(g); k_maxd1sq<3><<<tile_grid(g, 3, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
-    case 4: { long long no = outer_count<4>(g); k_maxd1sq<4><<<tile_grid(g, 4, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
-    case 5: { long long no = outer_count<5>(g); k_maxd1sq<5><<<tile_grid(g, 5, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
-    case 6: { long long no = outer_count<6>(g); k_maxd1sq<6><<<tile_grid(g, 6, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 2: { long long no = outer_count<2>(g); k_maxd1sq<2><<<walk_grid(g, 2, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 3: { long long no = outer_count<3>(g); k_maxd1sq<3><<<walk_grid(g, 3, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 4: { long long no = outer_count<4>(g); k_maxd1sq<4><<<walk_grid(g, 4, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 5: { long long no = outer_count<5>(g); k_maxd1sq<5><<<walk_grid(g, 5, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
+    case 6: { long long no = outer_count<6>(g); k_maxd1sq<6><<<walk_grid(g, 6, no), block, 0, s>>>(g, in, epsmax, no, only_dim); break; }
     default: return cudaErrorInvalidValue;
   }
   hj_count_launch(1);

@@ -36,16 +36,16 @@ template <class Sys> struct WholeCfg { using type = ProdCfg; };
 #define HJ_FB_R 8
 #endif
 template <> struct WholeCfg<SysFlockBatch> { using type = TmaCfg<HJ_FB_R, HJ_FB_MINB, 1, HJ_FB_TY, HJ_FB_TXP, false, 143, HJ_FB_GW, HJ_FB_XPAD>; };
-// 'intended' (true) WENO5 of a whole system: the smoothness indicators and the two divisions per dim need ~170 live
-// registers; at the 128 of two 256-thread CTAs per SM the body spills 90-400 bytes per thread.  One CTA of 384 threads
-// (32 x 24 tile) gets 168 registers: no spills, and the kernel is FP64-bound anyway (12 warps keep the pipe busy).
+// 'intended' (true) WENO5 of a whole system keeps the production tile: the body spills 90-400 bytes per thread at the
+// 128 registers of two 256-thread CTAs per SM, but one 384-thread CTA at 168 registers (no spills) measured SLOWER
+// (256^3: 0.63 / 0.59 / 1.81 ms per stage against 0.58 / 0.51 / 0.55 ms) -- the FP64 pipe is the bound (70 % busy) and
+// 16 resident warps feed it better than 12.  The ENO functors (divided-difference tables of both sides live together)
+// take the roomy configuration.
 #ifndef HJ_INT_TY
 #define HJ_INT_TY 24
 #define HJ_INT_MINB 1
 #endif
 template <class Sys, int WENO> struct WholeCfgW { using type = typename WholeCfg<Sys>::type; };
-template <> struct WholeCfgW<SysDubinsRel, HJ_WENO_INTENDED> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
-template <> struct WholeCfgW<SysFlock, HJ_WENO_INTENDED> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
 // upwindFirstENO3a / upwindFirstENO2 as CoStateCalc on the plane-ring backend: whole 3-D systems, the
 // same roomy configuration (the divided-difference tables of both sides are live together)
 template <> struct WholeCfgW<SysDubinsRel, HJ_SCHEME_ENO3A> { using type = TmaCfg<8, HJ_INT_MINB, 1, HJ_INT_TY, 16>; };
@@ -80,8 +80,14 @@ template <class Sys> struct SplitCfg;
 #define HJ_P2_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, HJ_P2_TA, HJ_P2_TB, HJ_P2_GW, HJ_P2_OPT>
 #define HJ_P1_6D TmaCfg<HJ_P1_R, HJ_P1_MINB, 1, HJ_P1_TY, HJ_P1_TXP, false, HJ_P1_OPT, HJ_P1_GW, HJ_P1_XPAD>
 // P2T: pass-2 tile for THIN dim-0 extents (slabs of a multi-GPU job: 41 planes over 8 ranks are 5..6 planes each, of
-// which a 4-row tile wastes a third); chosen per context by pick_thin() below
-#define HJ_P2T_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, 6, 5>
+// which a 4-row tile wastes a third); chosen per context by pick_thin() below.  6 x 4 with a ghost warp (224 threads)
+// measured 6.9 / 7.5 / 7.7 ms per stage on a 6 x 41^5 slab against 8.3 / 9.0 / 10.7 ms for 6 x 5 without one (which
+// would need 288 threads and spill at 112 registers with one)
+#ifndef HJ_P2T_TB
+#define HJ_P2T_TB 4
+#define HJ_P2T_GW 1
+#endif
+#define HJ_P2T_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, 6, HJ_P2T_TB, HJ_P2T_GW>
 template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; using P2T = HJ_P2T_6D; };
 #ifndef HJ_P1_4D_GW
 #define HJ_P1_4D_GW 0
@@ -247,8 +253,8 @@ struct PlanShape {
       split = true;
       thin = pick_thin<P2, P2T>(n0);
       ns = P2::NS; vb = P2::VB; ta = thin ? P2T::TA : P2::TA; tb = thin ? P2T::TB : P2::TB;
-    } else if (weno != HJ_WENO_AS_SHIPPED) {              // intended WENO and the ENO functors share one configuration
-      using W = typename WholeCfgW<Sys, HJ_WENO_INTENDED>::type;
+    } else if (weno == HJ_SCHEME_ENO3A || weno == HJ_SCHEME_ENO2) {
+      using W = typename WholeCfgW<Sys, HJ_SCHEME_ENO3A>::type;
       txp = W::TXP; ty = W::TY; bw = W::BW;
     } else {
       using W = typename WholeCfg<Sys>::type;

@@ -116,8 +116,10 @@ def test_device_eno_vs_golden(lsp, name, scheme):
 @pytest.mark.gpu
 @pytest.mark.parametrize("scheme", ["eno2", "eno3a"])
 def test_device_eno_on_both_backends(lsp, scheme):
-    """The ENO functors run in the plane-ring (TMA) kernel too for whole 3-D systems: same device functions, so the two
-    backends agree bit for bit, and both match the reference-generated golden after three odeCFL3 steps."""
+    """The ENO functors run in the plane-ring (TMA) kernel too for whole 3-D systems: the same device functions build the
+    divided-difference tables and make the minimum-modulus choices, so the two backends agree to rounding of the
+    Hamiltonian / stage algebra (a flipped choice would be an O(dx^2) difference), and both match the
+    reference-generated golden after three odeCFL3 steps."""
     from levelsetpy_b200 import _lib as L
     gold = load_golden("eno_schemes")
     g, mk, d0 = _case(lsp, gold, "air3d")
@@ -141,4 +143,4 @@ def test_device_eno_on_both_backends(lsp, scheme):
     want = gold["air3d_%s_y" % scheme]
     rng = float(want.max() - want.min())
     assert np.max(np.abs(out[L.BACKEND_TMA] - want)) <= 1e-9 * rng
-    assert np.array_equal(out[L.BACKEND_GATHER], out[L.BACKEND_TMA])
+    assert np.max(np.abs(out[L.BACKEND_GATHER] - out[L.BACKEND_TMA])) <= 1e-12 * rng

@@ -28,10 +28,8 @@ def fb(ty=8, txp=51, minb=1, gw=1, xpad=0, r=8):
 
 
 VARIANTS = {
-    "p2nofill": p2(opt=256),                                          # bound-finding: pass-2 ghost warp without fill
-    "p2nogw": p2(gw=0),                                               # pass 2 without ghost warp (register patches)
-    "p1gw3": p1(gw=3),                                                # three ghost warps in pass 1
-    "p2t77": p2(minb=1, ta=7, tb=7, r=6, gw=2),                       # pass 2: 7 x 7 tile (49 x 8 pairs, 13 + 2 warps), 1 CTA/SM
+    "thin64gw": ["HJ_P2T_TB=4", "HJ_P2T_GW=1"],                       # thin-slab pass 2: 6 x 4 tile + ghost warp (224 threads)
+    "thin65gw": ["HJ_P2T_TB=5", "HJ_P2T_GW=1"],                       # 6 x 5 tile + ghost warp (288 threads, 112 registers)
 }
 
 

@@ -187,7 +187,7 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
     if world > 1:
         import torch.distributed as dist
         from levelsetpy_b200.slab import SlabSolver
-        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport)
+        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport, fused=not args.no_fused)
         eng, lo, hi = solver.eng, solver.lo, solver.hi
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
         barrier = dist.barrier
@@ -210,11 +210,13 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
     if solver is not None:
         plane_bytes = eng.plane_elems * 8
         faces = (1 if solver.lo_peer is not None else 0) + (1 if solver.hi_peer is not None else 0)
-        out.update({"planes_per_rank": [hi - lo], "transport": "peer memory (copy engines)" if solver.peer else "NCCL send/recv",
+        out.update({"planes_per_rank": [hi - lo], "transport": ("peer memory (%s)" % ("stores from inside pass 2" if (solver.overlapped() and solver.fused())
+                                                        else "copy engines")) if solver.peer else "NCCL send/recv",
                     "protocol": "two_pass" if solver.two_pass() else ("ranged" if solver.ranged() else "exchange_first"),
                     "halo_bytes_in_per_step_per_rank": 3 * faces * L.HJ_GHOST * plane_bytes})
         # attribution: the same step with the exchange switched off, and the exchange alone (results are discarded:
         # the state is re-made before verification)
+        out["fused_halo_push"] = bool(solver.overlapped() and solver.fused())
         out["pieces"] = len(solver.pieces() or [None])
         solver.set_mode("compute")
         out["compute_only_ms"] = _timed(step, steps, barrier, world, torch)
@@ -725,6 +727,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "p2p"],
                     help="slab halos: peer-memory pushes on the copy engines (default) or NCCL send/recv")
+    ap.add_argument("--no-fused", action="store_true",
+                    help="product systems: halos through the copy engines piece by piece instead of from inside pass 2")
     ap.add_argument("--blocks", default="all", choices=["all", "none", "dubins6d", "dint4d", "flockbatch"],
                     help="also measure + verify configs[2..4] in the default run ('workloads' in the JSON line)")
     ap.add_argument("--block-steps", type=int, default=5, help="timed steps of each workloads block (<= --steps)")

@@ -232,12 +232,20 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
  *                    pieces are still being computed); 0, 0, 0 = whole planes.
  *   hj_halo_wait     makes `stream` wait until `npush` further pushes of `buf` from each neighbour have landed and
  *                    my own outbound copies have left.  Every rank must push and await each buffer equally often.
- *   hj_halo_attached bit 0 / bit 1: a lower / upper neighbour is attached.                                        */
+ *   hj_halo_attached bit 0 / bit 1: a lower / upper neighbour is attached.
+ *   hj_halo_set_fused  product systems on the dimension-split path: pass 2 (hj_stage_pass(2) / hj_stage_pass_cols) stores
+ *                    the nodes of its three lowest / highest dim-0 planes ALSO into the neighbours' halo planes of the
+ *                    buffer it writes -- one kernel computes the stage and moves its halo over NVLink (peer stores), the
+ *                    transfer overlaps the kernel tile by tile.  The host then calls hj_halo_signal instead of
+ *                    hj_halo_push for that buffer.
+ *   hj_halo_signal   ordered behind `stream`: bump the neighbours' arrival counters of `buf` (after a fused pass 2).  */
 #define HJ_HALO_DESC_BYTES 512
 int hj_halo_export(hj_ctx* ctx, void* desc);
 int hj_halo_attach(hj_ctx* ctx, const void* lower_desc, const void* upper_desc);
 int hj_halo_detach(hj_ctx* ctx);
 int hj_halo_attached(const hj_ctx* ctx);
+int hj_halo_set_fused(hj_ctx* ctx, int on);
+int hj_halo_signal(hj_ctx* ctx, void* stream, int buf);
 int hj_halo_push(hj_ctx* ctx, void* stream, int buf, int64_t col_begin, int64_t col_end, int64_t row_len);
 int hj_halo_wait(hj_ctx* ctx, void* stream, int buf, int npush);
 

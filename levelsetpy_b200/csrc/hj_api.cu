@@ -553,6 +553,7 @@ static int stage_impl(hj_ctx* c, cudaStream_t s, int stage, double dt, const dou
   for (int d = 0; d < c->D; ++d) st.out_stride[d] = c->gp.stride[d];
   st.red = c->red + slot * RED_STRIDE;
   st.epsmax = c->eps;
+  if (c->halo && which_pass == 2) hj_halo_fused_targets(c, out_[stage], &st.push_lo, &st.push_hi);
   if (st.comp == HJ_COMP_MIN_WITH_AUX || st.comp == HJ_COMP_MAX_WITH_AUX)
     if (!st.aux) return fail(HJ_ERR_STATE, "Need to define target function l(x)!");   // hji_solver.py:584
   if (st.use_obs && !st.obs) return fail(HJ_ERR_STATE, "obstacle field not uploaded");

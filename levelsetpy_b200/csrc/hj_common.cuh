@@ -50,6 +50,11 @@ struct KStage {
   const double* obs;  // obstacle (stage 3)
   double* out;
   long long out_stride[HJ_MAX_DIM];  // stride of out/y0/aux/obs (pitched or dense)
+  // slab jobs, pass 2 of the dimension-split path with fused halo pushes (hj_halo_set_fused): the nodes of my three
+  // lowest / highest dim-0 planes are ALSO stored into the lower / upper neighbour's stored halo planes of the output
+  // buffer (peer memory over NVLink): push_lo / push_hi + the node's own offset is the peer address, or nullptr
+  double* push_lo;
+  double* push_hi;
   unsigned long long* red;           // HJ_REDUCE_LEN(D) ordered-uint64 slots, or nullptr
   const unsigned long long* epsmax;  // D ordered-uint64 raw max(D1^2) (intended WENO), or nullptr
 };

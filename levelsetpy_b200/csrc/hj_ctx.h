@@ -48,6 +48,7 @@ struct hj_ctx {
   HjHalo* halo = nullptr;         // peer-memory halo transport (hj_halo_attach)
 };
 
+void hj_halo_fused_targets(hj_ctx* c, int out_buf, double** lo, double** hi);   // hj_halo.cu
 void hj_halo_destroy(hj_ctx* c);   // hj_halo.cu: unmap neighbours, free the flag array (called by hj_destroy)
 
 // sets the thread's hj_last_error() text and returns `code`

@@ -40,6 +40,7 @@ struct HjHalo {
   HjHaloPeer peer[2];                     // 0 = lower neighbour, 1 = upper neighbour
   unsigned long long pushed[3] = {}, waited[3] = {};
   cudaEvent_t ev_ready = nullptr;         // "the planes to push are written" on the producing stream
+  bool fused = false;                     // pass 2 of the split path stores its edge planes into the neighbours itself
 };
 
 namespace {
@@ -111,7 +112,44 @@ void hj_halo_destroy(hj_ctx* c) {
   c->halo = nullptr;
 }
 
+// peer addresses for the fused push of pass 2 (KStage::push_lo / push_hi): base such that base + (offset of a node of my
+// 3 lowest / highest planes, relative to my first interior node) is that node's place in the neighbour's upper / lower
+// halo of RK buffer `out_buf`
+void hj_halo_fused_targets(hj_ctx* c, int out_buf, double** lo, double** hi) {
+  *lo = *hi = nullptr;
+  if (!c->halo || !c->halo->fused) return;
+  const HjHaloPeer& pl = c->halo->peer[0];
+  const HjHaloPeer& ph = c->halo->peer[1];
+  if (pl.present) *lo = pl.buf[out_buf] + (pl.n0 + HJ_GHOST) * c->plane;
+  if (ph.present) *hi = ph.buf[out_buf] - (long long)(c->gp.N[0] - HJ_GHOST) * c->plane;
+}
+
 extern "C" {
+
+int hj_halo_set_fused(hj_ctx* c, int on) {
+  if (!c) return hj_fail(HJ_ERR_INVALID, "hj_halo_set_fused: null ctx");
+  if (!c->halo) return hj_fail(HJ_ERR_STATE, "hj_halo_set_fused: no neighbour attached (hj_halo_attach)");
+  if (on && c->gp.N[0] < 2 * HJ_GHOST)
+    ;   // planes that are in BOTH neighbours' halos are stored twice: fine, push_lo and push_hi are independent
+  c->halo->fused = on != 0;
+  return HJ_OK;
+}
+
+// after a pass-2 launch with fused pushes: bump the neighbours' arrival counters of `buf`, ordered behind `stream`
+int hj_halo_signal(hj_ctx* c, void* stream, int buf) {
+  if (!c || buf < 0 || buf > 2) return hj_fail(HJ_ERR_INVALID, "hj_halo_signal: bad argument");
+  if (!c->halo) return hj_fail(HJ_ERR_STATE, "hj_halo_signal: no neighbour attached (hj_halo_attach)");
+  HJ_CK(cudaSetDevice(c->device));
+  HjHalo* h = c->halo;
+  const unsigned long long seq = ++h->pushed[buf];
+  for (int side = 0; side < 2; ++side) {
+    HjHaloPeer& p = h->peer[side];
+    if (!p.present) continue;
+    k_flag_set<<<1, 1, 0, (cudaStream_t)stream>>>(p.flags + (side == 1 ? 0 : 3) + buf, seq);
+    HJ_CK(cudaGetLastError());
+  }
+  return HJ_OK;
+}
 
 int hj_halo_export(hj_ctx* c, void* desc_out) {
   if (!c || !desc_out) return hj_fail(HJ_ERR_INVALID, "hj_halo_export: null argument");

@@ -255,6 +255,9 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
   const int myoff = ((aa + 3) * Cfg::HB + (NS == 3 ? ab + 3 : 0)) * VB + 2 * vp;
   RedAcc<GD> acc;
   acc.init();
+  // does this thread's dim-0 plane belong to a neighbour's halo?  (dim 0 is the tiled dim DA; loop-invariant)
+  const bool push_lo = st.push_lo != nullptr && ia < HJ_GHOST;
+  const bool push_hi = st.push_hi != nullptr && ia >= NA - HJ_GHOST;
 
   // ---- prologue (see k_stage_tma)
   double2 q[3];
@@ -418,6 +421,16 @@ k_stage_vec(const __grid_constant__ CUtensorMap tmap, const KGrid g, const KSys 
     }
     if (ok1) *reinterpret_cast<double2*>(st.out + off) = make_double2(oA, oB);
     else if (ok0) st.out[off] = oA;
+    // fused halo push: the same values go straight into the neighbours' halo planes over NVLink (posted stores: the
+    // transfer for the next stage overlaps this kernel instead of following it)
+    if (push_lo) {
+      if (ok1) *reinterpret_cast<double2*>(st.push_lo + off) = make_double2(oA, oB);
+      else if (ok0) st.push_lo[off] = oA;
+    }
+    if (push_hi) {
+      if (ok1) *reinterpret_cast<double2*>(st.push_hi + off) = make_double2(oA, oB);
+      else if (ok0) st.push_hi[off] = oA;
+    }
     if (red && ((ok0 && oA != oA) || (ok1 && oB != oB))) acc.nan = 1;
 
     q[0] = q[1]; q[1] = q[2]; q[2] = ctr;

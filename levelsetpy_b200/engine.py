@@ -481,6 +481,13 @@ class Engine:
         b, e, n = cols if cols is not None else (0, 0, 0)
         L.check(self.lib.hj_halo_push(self.h, self.stream(), int(which), int(b), int(e), int(n)))
 
+    def halo_set_fused(self, on=True):
+        """Pass 2 of the split path stores its edge planes into the neighbours' halos itself (hj_halo_set_fused)."""
+        L.check(self.lib.hj_halo_set_fused(self.h, int(bool(on))))
+
+    def halo_signal(self, which):
+        L.check(self.lib.hj_halo_signal(self.h, self.stream(), int(which)))
+
     def halo_wait(self, which, npush=1):
         L.check(self.lib.hj_halo_wait(self.h, self.stream(), int(which), int(npush)))
 

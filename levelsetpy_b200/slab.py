@@ -121,12 +121,15 @@ class SlabSolver:
     ``engine_factory(grid, weno, device, slab, backend)`` builds the per-slab context (default: the CUDA Engine)."""
 
     def __init__(self, schemeData, device=0, backend=None, comm=None, engine_factory=None, transport="auto", overlap=True,
-                 pieces="auto"):
+                 pieces="auto", fused="auto"):
         """``transport``: "peer" (copy-engine pushes into peer memory, hj_halo_*), "p2p" (send/recv of the group) or
         "auto" (peer wherever the per-slab engine offers it).  ``overlap=False``: exchange first, then compute (the
         protocol of the gather / intended paths; attribution runs).  ``pieces``: product systems over the peer
         transport advance pass 2 in that many column pieces and push each finished piece of the edge planes while the
-        next is computed ("auto": 4 when the halo is a large fraction of the slab, else 1 = whole-plane pushes)."""
+        next is computed ("auto": 4 when the halo is a large fraction of the slab, else 1 = whole-plane pushes).
+        ``fused`` ("auto" = on for product systems over the peer transport): pass 2 itself stores its edge planes into
+        the neighbours' halo planes (peer stores over NVLink inside the stage kernel, hj_halo_set_fused) -- compute and
+        halo transfer are ONE kernel, no copy follows it; ``pieces`` is then irrelevant."""
         sd = schemeData
         for f in ("grid", "hamFunc", "partialFunc"):
             assert isfield(sd, f), "%s not in bundle thisschemeData" % f
@@ -154,6 +157,8 @@ class SlabSolver:
         self._no_overlap = not overlap
         self.mode = "full"        # attribution runs (bench.py): "compute" = no exchange, "comm" = no stage kernels
         self._pieces_arg = pieces
+        self._fused_arg = fused
+        self._fused = None
         self._cols = None
         self._primed = False      # pieces protocol: the halos of the state the next step reads are on their way
         if transport not in ("auto", "peer", "p2p"):
@@ -191,7 +196,7 @@ class SlabSolver:
         """Collective.  The resident state was replaced (upload, or written through ``eng.buffer_tensor``): halo pieces
         pushed ahead for the old state are consumed and dropped."""
         if self._primed and self.mode != "compute":
-            self.eng.halo_wait(0, len(self._cols[1]))
+            self.eng.halo_wait(0, 1 if self.fused() else len(self._cols[1]))
         self._primed = False
 
     def set_mode(self, mode):
@@ -340,11 +345,43 @@ class SlabSolver:
                                 and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
         return self._ranged
 
+    def fused(self):
+        """Product system over the peer transport: pass 2 pushes its own edge planes (one kernel computes and moves)."""
+        if self._fused is None:
+            self._fused = bool(self._fused_arg and self.peer and self.two_pass() and hasattr(self.eng, "halo_set_fused")
+                               and self.world > 1)
+        return self._fused
+
+    def _step_fused(self, comp, use_obstacle):
+        """Every stage: pass 1 | wait for the neighbours' planes of the buffer this stage reads (stored into my halos by
+        THEIR pass 2 of the previous stage) | pass 2, whose stores of my edge planes go to the neighbours' halos of the
+        buffer it writes as well | signal.  No copy is ever queued in the steady state."""
+        t, dt, blocks = self._step
+        talk, work = self.mode != "compute", self.mode != "comm"
+        self.eng.halo_set_fused(self.mode == "full")
+        if not self._primed:
+            if talk:
+                self.eng.halo_push(0)                     # the state as uploaded: one copy-engine push of whole planes
+            self._primed = True
+        for stage in (1, 2, 3):
+            b_in, b_out = self.eng.stage_io(stage)
+            self.run_stage(stage, comp, use_obstacle, which_pass=1)
+            self.finish_halos(b_in)
+            if talk:
+                self.eng.halo_wait(b_in, 1)
+            if work:
+                self.run_stage(stage, comp, use_obstacle, which_pass=2)
+            if talk:
+                if self.mode == "full":
+                    self.eng.halo_signal(b_out)
+                else:
+                    self.eng.halo_push(b_out)             # attribution ("comm"): the same planes through the copy engines
+
     def pieces(self):
         """Column pieces [(begin, end), ...] of pass 2 and the axis length, or None for whole-plane pushes."""
         if self._cols is None:
             k = self._pieces_arg
-            if not (self.peer and self.two_pass() and hasattr(self.eng, "split_cols")):
+            if not (self.peer and self.two_pass() and hasattr(self.eng, "split_cols")) or self.fused():
                 k = 1
             elif k == "auto":
                 k = 4 if 2 * GHOST * 4 > self.n0 else 1           # the halo is more than a quarter of the slab
@@ -390,6 +427,9 @@ class SlabSolver:
     def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):
         """One CFL-limited TVD-RK3 step of the distributed field.  Returns (t_new, dt)."""
         dt = self.begin_step(t, t_end, factorCFL, maxStep)
+        if self.overlapped() and self.fused():
+            self._step_fused(comp, use_obstacle)
+            return rk3_times(t, dt)[2], dt
         if self.overlapped() and self.pieces() is not None:
             self._step_pieces(comp, use_obstacle)
             return rk3_times(t, dt)[2], dt
@@ -427,10 +467,11 @@ class LocalWorld:
 
     poison_halos = False     # tests: NaN the halo planes a stage will receive before its pass 1 runs
 
-    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None, transport="auto", pieces="auto"):
+    def __init__(self, schemeData, world, device=0, backend=None, engine_factory=None, transport="auto", pieces="auto",
+                 fused="auto"):
         self.world = int(world)
-        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory, transport, True, pieces)
-                      for r in range(self.world)]
+        self.slabs = [SlabSolver(schemeData, device, backend, _LocalComm(self, r), engine_factory, transport, True, pieces,
+                                 fused) for r in range(self.world)]
         self.peer = all(s.peer for s in self.slabs) and self.world > 1
         if self.peer:                       # contexts of one process attach by pointer (hj_halo_attach)
             descs = [s.eng.halo_export() for s in self.slabs]
@@ -460,6 +501,26 @@ class LocalWorld:
                 (rlo if tag == 0 else rhi).copy_(t)
         for s in self.slabs:
             s.finish_halos(b)
+
+    def _step_fused(self, comp, use_obstacle):
+        """SlabSolver._step_fused for every slab in lock-step on one stream (a wait only depends on signals queued in the
+        previous stage, or when the state was primed)."""
+        for s in self.slabs:
+            s.eng.halo_set_fused(True)
+            if not s._primed:
+                s.eng.halo_push(0)
+                s._primed = True
+        for stage in (1, 2, 3):
+            b_in, b_out = self.slabs[0].eng.stage_io(stage)
+            for s in self.slabs:
+                t_, dt_, blocks = s._step
+                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, which_pass=1)
+                s.finish_halos(b_in)
+            for s in self.slabs:
+                t_, dt_, blocks = s._step
+                s.eng.halo_wait(b_in, 1)
+                s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, which_pass=2)
+                s.eng.halo_signal(b_out)
 
     def _step_pieces(self, comp, use_obstacle):
         """SlabSolver._step_pieces for every slab in lock-step on one stream: all pushes a wait depends on were queued in
@@ -497,6 +558,9 @@ class LocalWorld:
                 s._alpha = [float(x) for x in amax]
         dts = [s.begin_step(t, t_end, factorCFL, maxStep) for s in self.slabs]
         assert all(d == dts[0] for d in dts), "dt must be identical on every rank"
+        if self.peer and self.slabs[0].overlapped() and self.slabs[0].fused():
+            self._step_fused(comp, use_obstacle)
+            return rk3_times(t, dts[0])[2], dts[0]
         if self.peer and self.slabs[0].overlapped() and self.slabs[0].pieces() is not None:
             self._step_pieces(comp, use_obstacle)
             return rk3_times(t, dts[0])[2], dts[0]

@@ -72,9 +72,12 @@ def main():
                 t, dt = rk3_step_resident(eng, ad, g, t, 1.0, 0.8, np.finfo(np.float64).max, L.COMP_MIN_OVER_TIME)
                 ref_dts.append(dt)
             ref = eng.download(shape=g.shape)
-        for transport in ("peer", "p2p"):
-            for overlap in (True, False):
-                solver = SlabSolver(sd, device=local, transport=transport, overlap=overlap)
+        # peer + overlap: product systems push their halos from inside pass 2 (fused) or piece by piece through the
+        # copy engines (fused off); whole 3-D systems advance the interior range under a whole-plane push either way
+        for transport, overlap, fused in (("peer", True, True), ("peer", True, False), ("peer", False, False),
+                                          ("p2p", True, False), ("p2p", False, False)):
+            if True:
+                solver = SlabSolver(sd, device=local, transport=transport, overlap=overlap, fused=fused)
                 solver.upload(np.ascontiguousarray(d0[solver.lo:solver.hi]))
                 t, dts = 0.0, []
                 for _ in range(nsteps):
@@ -92,7 +95,8 @@ def main():
                     ok = bool(err == 0.0 and same_dt)
                     failures += 0 if ok else 1
                     print(json.dumps({"case": name, "weno": weno, "world": world, "transport": transport,
-                                      "overlap": overlap, "pieces": len(solver.pieces() or [None]) if solver.overlapped() else 1,
+                                      "overlap": overlap, "fused": bool(solver.overlapped() and solver.fused()),
+                                      "pieces": len(solver.pieces() or [None]) if solver.overlapped() else 1,
                                       "protocol": "two_pass" if solver.two_pass() else (
                                           "ranged" if solver.ranged() else "exchange_first"),
                                       "max_abs_err": err, "max_rel_err": err / rng_, "bit_identical": err == 0.0,

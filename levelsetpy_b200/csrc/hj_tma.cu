@@ -93,10 +93,12 @@ template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = 
 #define HJ_P1_4D_GW 0
 #define HJ_P2_4D_GW 0
 #endif
+// 4-D pair: pass 2 tiles dim 0 in 16 rows; slabs of 20-21 planes (161 over 8 ranks) take the 11-row tile (2 tiles = 22
+// rows instead of 32)
 template <> struct SplitCfg<SysDoubleIntPair> {
   using P1 = TmaCfg<8, 2, 1, 9, 27, false, 143, HJ_P1_4D_GW>;
   using P2 = VecCfg<2, 8, 2, 16, 16, 1, HJ_P2_4D_GW>;
-  using P2T = P2;
+  using P2T = VecCfg<2, 8, 2, 16, 11, 1, HJ_P2_4D_GW>;
 };
 // rows of dim 0 a tiling of height `ta` processes per useful row
 static double tile_waste(int n0, int ta) { return (double)((n0 + ta - 1) / ta * ta) / n0; }

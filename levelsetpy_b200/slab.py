@@ -341,16 +341,26 @@ class SlabSolver:
         """Whole 3-D systems on the plane-ring backend under as_shipped WENO: the planes whose dim-0 stencil stays
         inside the slab are advanced under the halo exchange, the two 3-plane edge ranges after it (hj_stage_range)."""
         if self._ranged is None:
-            self._ranged = bool(self.weno != "intended" and not self._no_overlap and self.eng.D == 3 and self.n0 > 2 * GHOST
-                                and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
+            r = bool(self.weno != "intended" and not self._no_overlap and self.eng.D == 3 and self.n0 > 2 * GHOST
+                     and not self.two_pass() and getattr(self.eng, "supports_range", lambda: False)())
+            if not self._ready():
+                return r
+            self._ranged = r
         return self._ranged
 
     def fused(self):
         """Product system over the peer transport: pass 2 pushes its own edge planes (one kernel computes and moves)."""
         if self._fused is None:
-            self._fused = bool(self._fused_arg and self.peer and self.two_pass() and hasattr(self.eng, "halo_set_fused")
-                               and self.world > 1)
+            f = bool(self._fused_arg and self.peer and self.two_pass() and hasattr(self.eng, "halo_set_fused")
+                     and self.world > 1)
+            if not self._ready():
+                return f                      # asked before the first step: the context cannot tell yet, do not cache
+            self._fused = f
         return self._fused
+
+    def _ready(self):
+        """The per-slab context knows its system and holds a state (true from the first begin_step on)."""
+        return getattr(self, "_step", None) is not None
 
     def _step_fused(self, comp, use_obstacle):
         """Every stage: pass 1 | wait for the neighbours' planes of the buffer this stage reads (stored into my halos by
@@ -420,8 +430,10 @@ class SlabSolver:
 
     def two_pass(self):
         if self._overlap is None:
-            self._overlap = bool(self.weno != "intended" and not self._no_overlap
-                                 and getattr(self.eng, "is_split", lambda: False)())
+            o = bool(self.weno != "intended" and not self._no_overlap and getattr(self.eng, "is_split", lambda: False)())
+            if not self._ready():
+                return o
+            self._overlap = o
         return self._overlap
 
     def step(self, t, t_end, factorCFL, comp=L.COMP_NONE, use_obstacle=False, maxStep=np.finfo(np.float64).max):

@@ -144,7 +144,6 @@ def test_slabs_6d_pair_split_path(lsp):
         # as soon as it is computed (hj_halo_push with columns) and awaited piece by piece in the next stage
         # "fused": pass 2 stores its edge planes into the neighbour's halo planes itself (hj_halo_set_fused + hj_halo_signal)
         w = LocalWorld(sd, 2, backend=be, pieces=1 if pieces == "fused" else pieces, fused=pieces == "fused")
-        assert w.slabs[0].fused() == (pieces == "fused")
         w.poison_halos = True        # pass 1 (hj_stage_pass) runs on NaN halos: it must not read them
         w.upload(d0)
         t = 0.0
@@ -152,6 +151,7 @@ def test_slabs_6d_pair_split_path(lsp):
             t, dt = w.step(t, 1.0, 0.8, comp=L.COMP_MIN_OVER_TIME)
         assert w.slabs[0].two_pass() == (be == L.BACKEND_TMA)   # the two-kernel protocol is what ran on the TMA backend
         assert (w.slabs[0].pieces() is not None) == (be == L.BACKEND_TMA and pieces not in (1, "fused"))
+        assert w.slabs[0].fused() == (pieces == "fused")
         assert t == to
         got[(be, pieces)] = w.download()
         assert np.max(np.abs(got[(be, pieces)] - want)) <= 1e-9 * (want.max() - want.min())

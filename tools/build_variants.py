@@ -28,8 +28,7 @@ def fb(ty=8, txp=51, minb=1, gw=1, xpad=0, r=8):
 
 
 VARIANTS = {
-    "thin64gw": ["HJ_P2T_TB=4", "HJ_P2T_GW=1"],                       # thin-slab pass 2: 6 x 4 tile + ghost warp (224 threads)
-    "thin65gw": ["HJ_P2T_TB=5", "HJ_P2T_GW=1"],                       # 6 x 5 tile + ghost warp (288 threads, 112 registers)
+    "gw4d": ["HJ_P1_4D_GW=1", "HJ_P2_4D_GW=1"],                       # ghost warps in the 4-D pair's kernels (288 threads)
 }
 
 

@@ -187,7 +187,7 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
     if world > 1:
         import torch.distributed as dist
         from levelsetpy_b200.slab import SlabSolver
-        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport, fused=not args.no_fused)
+        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport, fused={"both": True, "hybrid": "hybrid", "off": False}[args.fused])
         eng, lo, hi = solver.eng, solver.lo, solver.hi
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
         barrier = dist.barrier
@@ -216,7 +216,7 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
                     "halo_bytes_in_per_step_per_rank": 3 * faces * L.HJ_GHOST * plane_bytes})
         # attribution: the same step with the exchange switched off, and the exchange alone (results are discarded:
         # the state is re-made before verification)
-        out["fused_halo_push"] = bool(solver.overlapped() and solver.fused())
+        out["fused_halo_push"] = args.fused if (solver.overlapped() and solver.fused()) else "off"
         out["pieces"] = len(solver.pieces() or [None])
         solver.set_mode("compute")
         out["compute_only_ms"] = _timed(step, steps, barrier, world, torch)
@@ -727,8 +727,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "p2p"],
                     help="slab halos: peer-memory pushes on the copy engines (default) or NCCL send/recv")
-    ap.add_argument("--no-fused", action="store_true",
-                    help="product systems: halos through the copy engines piece by piece instead of from inside pass 2")
+    ap.add_argument("--fused", default="both", choices=["both", "hybrid", "off"],
+                    help="product systems: halo planes stored into the neighbours from inside pass 2 (both sides), one "
+                         "side that way and the other through the copy engines (hybrid), or all through the copy engines "
+                         "piece by piece (off)")
     ap.add_argument("--blocks", default="all", choices=["all", "none", "dubins6d", "dint4d", "flockbatch"],
                     help="also measure + verify configs[2..4] in the default run ('workloads' in the JSON line)")
     ap.add_argument("--block-steps", type=int, default=5, help="timed steps of each workloads block (<= --steps)")

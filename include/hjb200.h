@@ -226,27 +226,30 @@ int hj_fill_edge_halo(hj_ctx* ctx, void* stream, int buf, int side);
  *   hj_halo_export   fills `desc` (CUDA IPC handles of the three RK buffers and of the arrival counters; POD bytes).
  *   hj_halo_attach   maps the lower / upper neighbour's descriptor (NULL = no neighbour on that side; contexts of one
  *                    process are attached by pointer).  For a two-rank periodic ring pass the same descriptor twice.
- *   hj_halo_push     ordered behind `stream`: copy my edge planes of RK buffer `buf` into both neighbours' halos on
- *                    dedicated copy streams, then bump their arrival counters.  col_begin/col_end/row_len select
+ *   hj_halo_push     ordered behind `stream`: copy my edge planes of RK buffer `buf` into the halos of the neighbours in
+ *                    `sides` (bit 0 lower, bit 1 upper; 3 = both) on dedicated copy streams, then bump their arrival
+ *                    counters.  col_begin/col_end/row_len select
  *                    columns of every row_len-element row of the planes (pushing a buffer in pieces while later
  *                    pieces are still being computed); 0, 0, 0 = whole planes.
  *   hj_halo_wait     makes `stream` wait until `npush` further pushes of `buf` from each neighbour have landed and
  *                    my own outbound copies have left.  Every rank must push and await each buffer equally often.
  *   hj_halo_attached bit 0 / bit 1: a lower / upper neighbour is attached.
  *   hj_halo_set_fused  product systems on the dimension-split path: pass 2 (hj_stage_pass(2) / hj_stage_pass_cols) stores
- *                    the nodes of its three lowest / highest dim-0 planes ALSO into the neighbours' halo planes of the
- *                    buffer it writes -- one kernel computes the stage and moves its halo over NVLink (peer stores), the
- *                    transfer overlaps the kernel tile by tile.  The host then calls hj_halo_signal instead of
- *                    hj_halo_push for that buffer.
- *   hj_halo_signal   ordered behind `stream`: bump the neighbours' arrival counters of `buf` (after a fused pass 2).  */
+ *                    the nodes of its three lowest / highest dim-0 planes ALSO into the halo planes of the lower / upper
+ *                    neighbour (`sides` bit 0 / bit 1; 0 = off) of the buffer it writes -- one kernel computes the stage
+ *                    and moves its halo over NVLink (peer stores), the transfer overlaps the kernel tile by tile.  The
+ *                    host then calls hj_halo_signal instead of hj_halo_push for those sides.  With one side fused and
+ *                    the other pushed by the copy engines the two transports share the link.
+ *   hj_halo_signal   ordered behind `stream`: bump the arrival counters of `buf` at the neighbours in `sides` (after a
+ *                    fused pass 2).                                                                                */
 #define HJ_HALO_DESC_BYTES 512
 int hj_halo_export(hj_ctx* ctx, void* desc);
 int hj_halo_attach(hj_ctx* ctx, const void* lower_desc, const void* upper_desc);
 int hj_halo_detach(hj_ctx* ctx);
 int hj_halo_attached(const hj_ctx* ctx);
-int hj_halo_set_fused(hj_ctx* ctx, int on);
-int hj_halo_signal(hj_ctx* ctx, void* stream, int buf);
-int hj_halo_push(hj_ctx* ctx, void* stream, int buf, int64_t col_begin, int64_t col_end, int64_t row_len);
+int hj_halo_set_fused(hj_ctx* ctx, int sides);
+int hj_halo_signal(hj_ctx* ctx, void* stream, int buf, int sides);
+int hj_halo_push(hj_ctx* ctx, void* stream, int buf, int sides, int64_t col_begin, int64_t col_end, int64_t row_len);
 int hj_halo_wait(hj_ctx* ctx, void* stream, int buf, int npush);
 
 /* odeCFL3(schemeFunc, [t, t_end], y, options{factorCFL,maxStep,singleStep='on'}, schemeData)

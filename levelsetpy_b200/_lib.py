@@ -79,8 +79,8 @@ SIGNATURES = {
     "hj_halo_detach": (_i, [_vp]),
     "hj_halo_attached": (_i, [_vp]),
     "hj_halo_set_fused": (_i, [_vp, _i]),
-    "hj_halo_signal": (_i, [_vp, _vp, _i]),
-    "hj_halo_push": (_i, [_vp, _vp, _i, _i64, _i64, _i64]),
+    "hj_halo_signal": (_i, [_vp, _vp, _i, _i]),
+    "hj_halo_push": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i64]),
     "hj_halo_wait": (_i, [_vp, _vp, _i, _i]),
 }
 

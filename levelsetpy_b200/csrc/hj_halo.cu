@@ -38,9 +38,10 @@ struct HjHaloPeer {
 struct HjHalo {
   unsigned long long* flags = nullptr;    // my arrival counters: [side of MY halo: 0 lower, 1 upper][buffer]
   HjHaloPeer peer[2];                     // 0 = lower neighbour, 1 = upper neighbour
-  unsigned long long pushed[3] = {}, waited[3] = {};
+  unsigned long long pushed[2][3] = {}, waited[3] = {};   // pushes towards [lower, upper] neighbour / waits, per buffer
   cudaEvent_t ev_ready = nullptr;         // "the planes to push are written" on the producing stream
-  bool fused = false;                     // pass 2 of the split path stores its edge planes into the neighbours itself
+  int fused = 0;                          // pass 2 of the split path stores its edge planes into the lower (bit 0) /
+                                          // upper (bit 1) neighbour itself
 };
 
 namespace {
@@ -120,32 +121,31 @@ void hj_halo_fused_targets(hj_ctx* c, int out_buf, double** lo, double** hi) {
   if (!c->halo || !c->halo->fused) return;
   const HjHaloPeer& pl = c->halo->peer[0];
   const HjHaloPeer& ph = c->halo->peer[1];
-  if (pl.present) *lo = pl.buf[out_buf] + (pl.n0 + HJ_GHOST) * c->plane;
-  if (ph.present) *hi = ph.buf[out_buf] - (long long)(c->gp.N[0] - HJ_GHOST) * c->plane;
+  if (pl.present && (c->halo->fused & 1)) *lo = pl.buf[out_buf] + (pl.n0 + HJ_GHOST) * c->plane;
+  if (ph.present && (c->halo->fused & 2)) *hi = ph.buf[out_buf] - (long long)(c->gp.N[0] - HJ_GHOST) * c->plane;
 }
 
 extern "C" {
 
-int hj_halo_set_fused(hj_ctx* c, int on) {
+int hj_halo_set_fused(hj_ctx* c, int sides) {
   if (!c) return hj_fail(HJ_ERR_INVALID, "hj_halo_set_fused: null ctx");
   if (!c->halo) return hj_fail(HJ_ERR_STATE, "hj_halo_set_fused: no neighbour attached (hj_halo_attach)");
-  if (on && c->gp.N[0] < 2 * HJ_GHOST)
-    ;   // planes that are in BOTH neighbours' halos are stored twice: fine, push_lo and push_hi are independent
-  c->halo->fused = on != 0;
+  if (sides < 0 || sides > 3) return hj_fail(HJ_ERR_INVALID, "hj_halo_set_fused: sides is a bit mask (1 lower, 2 upper)");
+  c->halo->fused = sides;   // a plane in BOTH neighbours' halos (thin slabs) is simply stored twice
   return HJ_OK;
 }
 
-// after a pass-2 launch with fused pushes: bump the neighbours' arrival counters of `buf`, ordered behind `stream`
-int hj_halo_signal(hj_ctx* c, void* stream, int buf) {
+// after a pass-2 launch with fused pushes: bump the arrival counters of `buf` at the neighbours in `sides`, ordered
+// behind `stream`
+int hj_halo_signal(hj_ctx* c, void* stream, int buf, int sides) {
   if (!c || buf < 0 || buf > 2) return hj_fail(HJ_ERR_INVALID, "hj_halo_signal: bad argument");
   if (!c->halo) return hj_fail(HJ_ERR_STATE, "hj_halo_signal: no neighbour attached (hj_halo_attach)");
   HJ_CK(cudaSetDevice(c->device));
   HjHalo* h = c->halo;
-  const unsigned long long seq = ++h->pushed[buf];
   for (int side = 0; side < 2; ++side) {
     HjHaloPeer& p = h->peer[side];
-    if (!p.present) continue;
-    k_flag_set<<<1, 1, 0, (cudaStream_t)stream>>>(p.flags + (side == 1 ? 0 : 3) + buf, seq);
+    if (!p.present || !(sides & (1 << side))) continue;
+    k_flag_set<<<1, 1, 0, (cudaStream_t)stream>>>(p.flags + (side == 1 ? 0 : 3) + buf, ++h->pushed[side][buf]);
     HJ_CK(cudaGetLastError());
   }
   return HJ_OK;
@@ -247,7 +247,7 @@ int hj_halo_attached(const hj_ctx* c) {
 
 // columns [col_begin, col_end) of every row of `row_len` elements of the three edge planes (row_len must divide the
 // plane; 0, 0, 0 = the whole planes in one contiguous copy)
-int hj_halo_push(hj_ctx* c, void* stream, int buf, int64_t col_begin, int64_t col_end, int64_t row_len) {
+int hj_halo_push(hj_ctx* c, void* stream, int buf, int sides, int64_t col_begin, int64_t col_end, int64_t row_len) {
   if (!c || buf < 0 || buf > 2) return hj_fail(HJ_ERR_INVALID, "hj_halo_push: bad argument");
   if (!c->halo) return hj_fail(HJ_ERR_STATE, "hj_halo_push: no neighbour attached (hj_halo_attach)");
   const bool whole = row_len == 0;
@@ -258,10 +258,10 @@ int hj_halo_push(hj_ctx* c, void* stream, int buf, int64_t col_begin, int64_t co
   cudaStream_t s = (cudaStream_t)stream;
   const long long n0 = c->gp.N[0], plane = c->plane;
   HJ_CK(cudaEventRecord(h->ev_ready, s));
-  const unsigned long long seq = ++h->pushed[buf];
   for (int side = 0; side < 2; ++side) {
     HjHaloPeer& p = h->peer[side];
-    if (!p.present) continue;
+    if (!p.present || !(sides & (1 << side))) continue;
+    const unsigned long long seq = ++h->pushed[side][buf];
     // to the upper neighbour: my top 3 interior planes -> its lower halo; to the lower one: my bottom 3 -> its upper halo
     const double* src = c->buf[buf] + (side == 1 ? n0 : (long long)HJ_GHOST) * plane;
     double* dst = p.buf[buf] + (side == 1 ? 0 : (p.n0 + HJ_GHOST) * plane);

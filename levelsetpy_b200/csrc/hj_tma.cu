@@ -90,10 +90,11 @@ template <class Sys> struct SplitCfg;
 #define HJ_P2T_6D VecCfg<3, HJ_P2_R, HJ_P2_MINB, HJ_P2_VP, 6, HJ_P2T_TB, HJ_P2T_GW>
 template <> struct SplitCfg<SysDubinsRelPair> { using P1 = HJ_P1_6D; using P2 = HJ_P2_6D; using P2T = HJ_P2T_6D; };
 #ifndef HJ_P1_4D_GW
-#define HJ_P1_4D_GW 0
-#define HJ_P2_4D_GW 0
+#define HJ_P1_4D_GW 1
+#define HJ_P2_4D_GW 1
 #endif
-// 4-D pair: pass 2 tiles dim 0 in 16 rows; slabs of 20-21 planes (161 over 8 ranks) take the 11-row tile (2 tiles = 22
+// 4-D pair: both kernels with a ghost warp (288 threads, 2 CTAs/SM; measured at 161^4: pass 1 3.07 ms against 3.80,
+// pass 2 4.4 / 5.1 / 5.2 ms against 4.9 / 5.5 / 5.8, 23.9 ms per step against 27.5).  Pass 2 tiles dim 0 in 16 rows; slabs of 20-21 planes (161 over 8 ranks) take the 11-row tile (2 tiles = 22
 // rows instead of 32)
 template <> struct SplitCfg<SysDoubleIntPair> {
   using P1 = TmaCfg<8, 2, 1, 9, 27, false, 143, HJ_P1_4D_GW>;

@@ -475,18 +475,19 @@ class Engine:
         keep = [C.create_string_buffer(d, L.HJ_HALO_DESC_BYTES) if d is not None else None for d in (lower, upper)]
         L.check(self.lib.hj_halo_attach(self.h, *[C.cast(k, C.c_void_p) if k is not None else None for k in keep]))
 
-    def halo_push(self, which, cols=None):
-        """Push my edge planes of RK buffer ``which`` into the neighbours' halos, ordered behind the current stream.
-        ``cols`` = (begin, end, row_len): only those columns of every row (see hj_halo_push)."""
+    def halo_push(self, which, cols=None, sides=3):
+        """Push my edge planes of RK buffer ``which`` into the neighbours' halos (``sides``: bit 0 lower, bit 1 upper),
+        ordered behind the current stream.  ``cols`` = (begin, end, row_len): only those columns of every row."""
         b, e, n = cols if cols is not None else (0, 0, 0)
-        L.check(self.lib.hj_halo_push(self.h, self.stream(), int(which), int(b), int(e), int(n)))
+        L.check(self.lib.hj_halo_push(self.h, self.stream(), int(which), int(sides), int(b), int(e), int(n)))
 
-    def halo_set_fused(self, on=True):
-        """Pass 2 of the split path stores its edge planes into the neighbours' halos itself (hj_halo_set_fused)."""
-        L.check(self.lib.hj_halo_set_fused(self.h, int(bool(on))))
+    def halo_set_fused(self, sides=3):
+        """Pass 2 of the split path stores its edge planes into the halos of the neighbours in ``sides`` (bit 0 lower,
+        bit 1 upper; 0 = off) itself (hj_halo_set_fused)."""
+        L.check(self.lib.hj_halo_set_fused(self.h, int(sides)))
 
-    def halo_signal(self, which):
-        L.check(self.lib.hj_halo_signal(self.h, self.stream(), int(which)))
+    def halo_signal(self, which, sides=3):
+        L.check(self.lib.hj_halo_signal(self.h, self.stream(), int(which), int(sides)))
 
     def halo_wait(self, which, npush=1):
         L.check(self.lib.hj_halo_wait(self.h, self.stream(), int(which), int(npush)))

@@ -129,7 +129,9 @@ class SlabSolver:
         next is computed ("auto": 4 when the halo is a large fraction of the slab, else 1 = whole-plane pushes).
         ``fused`` ("auto" = on for product systems over the peer transport): pass 2 itself stores its edge planes into
         the neighbours' halo planes (peer stores over NVLink inside the stage kernel, hj_halo_set_fused) -- compute and
-        halo transfer are ONE kernel, no copy follows it; ``pieces`` is then irrelevant."""
+        halo transfer are ONE kernel, no copy follows it; ``pieces`` is then irrelevant.  ``fused="hybrid"``: only the
+        planes for the upper neighbour go that way, those for the lower one are pushed by the copy engines behind the
+        kernel (under the next stage's pass 1), so that the two transports share the link."""
         sd = schemeData
         for f in ("grid", "hamFunc", "partialFunc"):
             assert isfield(sd, f), "%s not in bundle thisschemeData" % f
@@ -368,7 +370,8 @@ class SlabSolver:
         buffer it writes as well | signal.  No copy is ever queued in the steady state."""
         t, dt, blocks = self._step
         talk, work = self.mode != "compute", self.mode != "comm"
-        self.eng.halo_set_fused(self.mode == "full")
+        sides = (2 if self._fused_arg == "hybrid" else 3) if self.mode == "full" else 0
+        self.eng.halo_set_fused(sides)
         if not self._primed:
             if talk:
                 self.eng.halo_push(0)                     # the state as uploaded: one copy-engine push of whole planes
@@ -382,10 +385,10 @@ class SlabSolver:
             if work:
                 self.run_stage(stage, comp, use_obstacle, which_pass=2)
             if talk:
-                if self.mode == "full":
-                    self.eng.halo_signal(b_out)
-                else:
-                    self.eng.halo_push(b_out)             # attribution ("comm"): the same planes through the copy engines
+                if sides:
+                    self.eng.halo_signal(b_out, sides)
+                if sides != 3:                            # the other side(s): copy engines, behind the kernel (hybrid;
+                    self.eng.halo_push(b_out, sides=3 & ~sides)   # attribution mode "comm": everything)
 
     def pieces(self):
         """Column pieces [(begin, end), ...] of pass 2 and the axis length, or None for whole-plane pushes."""
@@ -517,8 +520,10 @@ class LocalWorld:
     def _step_fused(self, comp, use_obstacle):
         """SlabSolver._step_fused for every slab in lock-step on one stream (a wait only depends on signals queued in the
         previous stage, or when the state was primed)."""
+        hybrid = self.slabs[0]._fused_arg == "hybrid"
+        sides = 2 if hybrid else 3
         for s in self.slabs:
-            s.eng.halo_set_fused(True)
+            s.eng.halo_set_fused(sides)
             if not s._primed:
                 s.eng.halo_push(0)
                 s._primed = True
@@ -532,7 +537,9 @@ class LocalWorld:
                 t_, dt_, blocks = s._step
                 s.eng.halo_wait(b_in, 1)
                 s.eng.stage(stage, t_, dt_, blocks[stage - 1], comp, use_obstacle, which_pass=2)
-                s.eng.halo_signal(b_out)
+                s.eng.halo_signal(b_out, sides)
+                if sides != 3:
+                    s.eng.halo_push(b_out, sides=3 & ~sides)
 
     def _step_pieces(self, comp, use_obstacle):
         """SlabSolver._step_pieces for every slab in lock-step on one stream: all pushes a wait depends on were queued in

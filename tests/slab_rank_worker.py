@@ -74,8 +74,8 @@ def main():
             ref = eng.download(shape=g.shape)
         # peer + overlap: product systems push their halos from inside pass 2 (fused) or piece by piece through the
         # copy engines (fused off); whole 3-D systems advance the interior range under a whole-plane push either way
-        for transport, overlap, fused in (("peer", True, True), ("peer", True, False), ("peer", False, False),
-                                          ("p2p", True, False), ("p2p", False, False)):
+        for transport, overlap, fused in (("peer", True, True), ("peer", True, "hybrid"), ("peer", True, False),
+                                          ("peer", False, False), ("p2p", True, False), ("p2p", False, False)):
             if True:
                 solver = SlabSolver(sd, device=local, transport=transport, overlap=overlap, fused=fused)
                 solver.upload(np.ascontiguousarray(d0[solver.lo:solver.hi]))
@@ -95,7 +95,7 @@ def main():
                     ok = bool(err == 0.0 and same_dt)
                     failures += 0 if ok else 1
                     print(json.dumps({"case": name, "weno": weno, "world": world, "transport": transport,
-                                      "overlap": overlap, "fused": bool(solver.overlapped() and solver.fused()),
+                                      "overlap": overlap, "fused": (fused if (solver.overlapped() and solver.fused()) else False),
                                       "pieces": len(solver.pieces() or [None]) if solver.overlapped() else 1,
                                       "protocol": "two_pass" if solver.two_pass() else (
                                           "ranged" if solver.ranged() else "exchange_first"),

@@ -31,7 +31,7 @@ def test_slab_ranks_match_single_domain(world):
     lines = [json.loads(x) for x in r.stdout.splitlines() if x.startswith("{")]
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
-    assert len(lines) == 5 * 5, "every case x (transport, overlap, fused) must report"
+    assert len(lines) == 5 * 6, "every case x (transport, overlap, fused) must report"
     assert any(x["fused"] for x in lines) and any(x["pieces"] > 1 for x in lines)
     assert all(x["ok"] and x["bit_identical"] and x["dt_identical"] for x in lines)
     assert {x["protocol"] for x in lines} == {"two_pass", "ranged", "exchange_first"}

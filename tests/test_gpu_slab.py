@@ -139,25 +139,28 @@ def test_slabs_6d_pair_split_path(lsp):
     want = yo.reshape(g.shape)
     got = {}
     for be, pieces in ((L.BACKEND_GATHER, 1), (L.BACKEND_TMA, 1), (L.BACKEND_TMA, 3), (L.BACKEND_TMA, "auto"),
-                       (L.BACKEND_TMA, "fused")):
+                       (L.BACKEND_TMA, "fused"), (L.BACKEND_TMA, "hybrid")):
         # pieces > 1: pass 2 in column pieces (hj_stage_pass_cols), each piece of the edge planes pushed to the neighbour
         # as soon as it is computed (hj_halo_push with columns) and awaited piece by piece in the next stage
         # "fused": pass 2 stores its edge planes into the neighbour's halo planes itself (hj_halo_set_fused + hj_halo_signal)
-        w = LocalWorld(sd, 2, backend=be, pieces=1 if pieces == "fused" else pieces, fused=pieces == "fused")
+        # "hybrid": that for the upper neighbour only, the planes for the lower one go through the copy engines
+        fz = {"fused": True, "hybrid": "hybrid"}.get(pieces, False)
+        w = LocalWorld(sd, 2, backend=be, pieces=1 if fz else pieces, fused=fz)
         w.poison_halos = True        # pass 1 (hj_stage_pass) runs on NaN halos: it must not read them
         w.upload(d0)
         t = 0.0
         for _ in range(2):
             t, dt = w.step(t, 1.0, 0.8, comp=L.COMP_MIN_OVER_TIME)
         assert w.slabs[0].two_pass() == (be == L.BACKEND_TMA)   # the two-kernel protocol is what ran on the TMA backend
-        assert (w.slabs[0].pieces() is not None) == (be == L.BACKEND_TMA and pieces not in (1, "fused"))
-        assert w.slabs[0].fused() == (pieces == "fused")
+        assert (w.slabs[0].pieces() is not None) == (be == L.BACKEND_TMA and pieces not in (1, "fused", "hybrid"))
+        assert w.slabs[0].fused() == (pieces in ("fused", "hybrid"))
         assert t == to
         got[(be, pieces)] = w.download()
         assert np.max(np.abs(got[(be, pieces)] - want)) <= 1e-9 * (want.max() - want.min())
     assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, 3)])      # the pieces change nothing, bit for bit
     assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, "auto")])
     assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, "fused")])
+    assert np.array_equal(got[(L.BACKEND_TMA, 1)], got[(L.BACKEND_TMA, "hybrid")])
 
 
 def test_stage_pass_equals_stage(lsp):

@@ -29,6 +29,8 @@ def fb(ty=8, txp=51, minb=1, gw=1, xpad=0, r=8):
 
 VARIANTS = {
     "gw4d": ["HJ_P1_4D_GW=1", "HJ_P2_4D_GW=1"],                       # ghost warps in the 4-D pair's kernels (288 threads)
+    "p2r7": p2(r=7, ta=4, tb=6),                                      # pass 2: 4 x 6 tile, 7-slot ring (3 planes of slack)
+    "p2r8": p2(r=8, ta=4, tb=5),                                      # pass 2: 4 x 5 tile, 8-slot ring (4 planes of slack)
 }
 
 

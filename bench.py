@@ -187,7 +187,7 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
     if world > 1:
         import torch.distributed as dist
         from levelsetpy_b200.slab import SlabSolver
-        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport, fused={"both": True, "hybrid": "hybrid", "off": False}[args.fused])
+        solver = SlabSolver(sd, device=local, backend=backend, transport=args.transport, fused={"auto": "auto", "both": True, "hybrid": "hybrid", "off": False}[args.fused])
         eng, lo, hi = solver.eng, solver.lo, solver.hi
         step = lambda t: solver.step(t, 1e9, 0.8, comp)[0]
         barrier = dist.barrier
@@ -210,13 +210,15 @@ def product_block(args, lsp, L, kind, world, rank, local, hbm_peak, comp, backen
     if solver is not None:
         plane_bytes = eng.plane_elems * 8
         faces = (1 if solver.lo_peer is not None else 0) + (1 if solver.hi_peer is not None else 0)
-        out.update({"planes_per_rank": [hi - lo], "transport": ("peer memory (%s)" % ("stores from inside pass 2" if (solver.overlapped() and solver.fused())
-                                                        else "copy engines")) if solver.peer else "NCCL send/recv",
+        out.update({"planes_per_rank": [hi - lo], "transport": ("peer memory (%s)" % (("stores from inside pass 2" + (" towards one neighbour, copy engines towards "
+                                                                                      "the other" if solver.hybrid() else ""))
+                                                        if (solver.overlapped() and solver.fused()) else "copy engines"))
+                    if solver.peer else "NCCL send/recv",
                     "protocol": "two_pass" if solver.two_pass() else ("ranged" if solver.ranged() else "exchange_first"),
                     "halo_bytes_in_per_step_per_rank": 3 * faces * L.HJ_GHOST * plane_bytes})
         # attribution: the same step with the exchange switched off, and the exchange alone (results are discarded:
         # the state is re-made before verification)
-        out["fused_halo_push"] = args.fused if (solver.overlapped() and solver.fused()) else "off"
+        out["fused_halo_push"] = ("hybrid" if solver.hybrid() else "both") if (solver.overlapped() and solver.fused()) else "off"
         out["pieces"] = len(solver.pieces() or [None])
         solver.set_mode("compute")
         out["compute_only_ms"] = _timed(step, steps, barrier, world, torch)
@@ -727,7 +729,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "p2p"],
                     help="slab halos: peer-memory pushes on the copy engines (default) or NCCL send/recv")
-    ap.add_argument("--fused", default="both", choices=["both", "hybrid", "off"],
+    ap.add_argument("--fused", default="auto", choices=["auto", "both", "hybrid", "off"],
                     help="product systems: halo planes stored into the neighbours from inside pass 2 (both sides), one "
                          "side that way and the other through the copy engines (hybrid), or all through the copy engines "
                          "piece by piece (off)")

@@ -139,6 +139,11 @@ int64_t hj_plane_elems(const hj_ctx* ctx);        /* pitched elements of one dim
  * data/derivL/derivR: dense device arrays of hj_num_nodes doubles (HJ_BC_HALO contexts: not supported). */
 int hj_deriv(hj_ctx* ctx, void* stream, const double* data_dev, int dim, double* derivL_dev, double* derivR_dev);
 
+/* dL, dR, _ = upwindFirstENO3aHelper(grid, data, dim) -- SpatialDerivative/ENO3aHelper.py:11-191: the three left and
+ * three right third-order ENO candidates (what upwindFirstWENO5a / upwindFirstENO3a return for generateAll = True,
+ * upwind_first_weno5a.py:73-75).  out6_dev: 6 dense arrays of n doubles, [dL0, dL1, dL2, dR0, dR1, dR2].              */
+int hj_deriv_candidates(hj_ctx* ctx, void* stream, const double* data_dev, int dim, double* out6_dev);
+
 /* addGhostExtrapolate / addGhostPeriodic (dataIn, dim, width) -> dataOut, dense device arrays.
  * BoundaryCondition/add_ghost_extrapolate.py:16, add_ghost_periodic.py:12.                          */
 int hj_add_ghost(hj_ctx* ctx, void* stream, const double* data_dev, int dim, int width, double* out_dev);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "hj_state_ptr": (_i, [_vp, _i, C.POINTER(_vp)]),
     "hj_plane_elems": (_i64, [_vp]),
     "hj_deriv": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "hj_deriv_candidates": (_i, [_vp, _vp, _vp, _i, _vp]),
     "hj_add_ghost": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "hj_rhs": (_i, [_vp, _vp, _d, _vp, _vp, _pd, _pd]),
     "hj_ham": (_i, [_vp, _vp, _d, C.POINTER(_vp), _vp]),

@@ -310,6 +310,15 @@ int hj_deriv(hj_ctx* c, void* stream, const double* data_dev, int dim, double* d
   return HJ_OK;
 }
 
+int hj_deriv_candidates(hj_ctx* c, void* stream, const double* data_dev, int dim, double* out6_dev) {
+  if (!c || !data_dev || !out6_dev) return fail(HJ_ERR_INVALID, "hj_deriv_candidates: null argument");
+  if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "Illegal dim parameter");   // ENO3aHelper.py:54-55
+  if (c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_deriv_candidates: not available on a slab (halo) context");
+  CK(cudaSetDevice(c->device));
+  CK(hj_launch_deriv_all(c->gd, data_dev, dim, out6_dev, (cudaStream_t)stream));
+  return HJ_OK;
+}
+
 int hj_add_ghost(hj_ctx* c, void* stream, const double* data_dev, int dim, int width, double* out_dev) {
   if (!c || !data_dev || !out_dev) return fail(HJ_ERR_INVALID, "hj_add_ghost: null argument");
   if (dim < 0 || dim >= c->D) return fail(HJ_ERR_INVALID, "Illegal dim parameter");

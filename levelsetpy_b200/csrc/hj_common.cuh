@@ -195,16 +195,26 @@ HJ_DEV void eno_tables(const double v[7], double dxinv, EnoTables& T, bool third
 
 // upwindFirstENO3a (upwind_first_eno3a.py:87-142): candidates of ENO3aHelper.py:116-189, the one built on the
 // minimum-modulus D2 and then D3 neighbours is taken (:104-140).
-HJ_DEV void upwind_eno3a(const double v[7], double dx, double dxinv, double& L, double& R) {
-  EnoTables T;
-  eno_tables(v, dxinv, T, true);
+// the three left and three right third-order candidates of upwindFirstENO3aHelper (ENO3aHelper.py:116-189) -- what
+// upwindFirstWENO5a / upwindFirstENO3a return for generateAll = True (upwind_first_weno5a.py:73-75)
+HJ_DEV void eno3a_candidates(const EnoTables& T, double dx, double dL[3], double dR[3]) {
   const double dx2 = __dmul_rn(dx, dx), cLL = __dmul_rn(2.0, dx2), cLR = -dx2;
   const double l01 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[1])), l2 = __dadd_rn(T.a[2], __dmul_rn(dx, T.b[2]));
   const double r01 = __dadd_rn(T.a[3], __dmul_rn(-dx, T.b[2])), r2 = __dadd_rn(T.a[3], __dmul_rn(-dx, T.b[3]));
-  const double dL0 = __dadd_rn(l01, __dmul_rn(cLL, T.c[0])), dL1 = __dadd_rn(l01, __dmul_rn(cLL, T.c[1])),
-               dL2 = __dadd_rn(l2, __dmul_rn(cLR, T.c[2]));
-  const double dR0 = __dadd_rn(r01, __dmul_rn(cLR, T.c[1])), dR1 = __dadd_rn(r01, __dmul_rn(cLR, T.c[2])),
-               dR2 = __dadd_rn(r2, __dmul_rn(cLL, T.c[3]));
+  dL[0] = __dadd_rn(l01, __dmul_rn(cLL, T.c[0]));
+  dL[1] = __dadd_rn(l01, __dmul_rn(cLL, T.c[1]));
+  dL[2] = __dadd_rn(l2, __dmul_rn(cLR, T.c[2]));
+  dR[0] = __dadd_rn(r01, __dmul_rn(cLR, T.c[1]));
+  dR[1] = __dadd_rn(r01, __dmul_rn(cLR, T.c[2]));
+  dR[2] = __dadd_rn(r2, __dmul_rn(cLL, T.c[3]));
+}
+
+HJ_DEV void upwind_eno3a(const double v[7], double dx, double dxinv, double& L, double& R) {
+  EnoTables T;
+  eno_tables(v, dxinv, T, true);
+  double cL[3], cR[3];
+  eno3a_candidates(T, dx, cL, cR);
+  const double dL0 = cL[0], dL1 = cL[1], dL2 = cL[2], dR0 = cR[0], dR1 = cR[1], dR2 = cR[2];
   const bool t0 = fabs(T.c[0]) < fabs(T.c[1]), t1 = fabs(T.c[1]) < fabs(T.c[2]), t2 = fabs(T.c[2]) < fabs(T.c[3]);
   {  // left: index i of the masks
     const bool sL = fabs(T.b[1]) < fabs(T.b[2]);

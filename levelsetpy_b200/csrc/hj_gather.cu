@@ -99,6 +99,21 @@ __global__ void __launch_bounds__(256) k_deriv(const KGrid g, const double* __re
   }
 }
 
+// upwindFirstENO3aHelper (ENO3aHelper.py:11): the six third-order candidates, out = [dL0, dL1, dL2, dR0, dR1, dR2][n]
+__global__ void __launch_bounds__(256) k_deriv_all(const KGrid g, const double* __restrict__ in, const int dim,
+                                                   double* __restrict__ out, const long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)((e / g.stride[dim]) % g.N[dim]);
+    double v[7], dL[3], dR[3];
+    load_stencil(in + e, i, g.N[dim], g.stride[dim], g.bc[dim], g.slope_mult[dim], v);
+    EnoTables T;
+    eno_tables(v, g.dxinv[dim], T, true);
+    eno3a_candidates(T, g.dx[dim], dL, dR);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out[(long long)k * n + e] = dL[k]; out[(long long)(3 + k) * n + e] = dR[k]; }
+  }
+}
+
 // addGhostExtrapolate / addGhostPeriodic: dense (.., N_dim, ..) -> dense (.., N_dim + 2*width, ..)
 __global__ void __launch_bounds__(256) k_add_ghost(const KGrid g, const double* __restrict__ in, const int dim,
                                                    const int width, double* __restrict__ out, const long long nout) {
@@ -427,6 +442,14 @@ cudaError_t hj_launch_deriv(int weno, const KGrid& g, const double* in, int dim,
     case HJ_SCHEME_ENO2: k_deriv<HJ_SCHEME_ENO2><<<flat_blocks(n), 256, 0, s>>>(g, in, dim, dl, dr, epsmax, n); break;
     default: return cudaErrorInvalidValue;
   }
+  hj_count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_deriv_all(const KGrid& g, const double* in, int dim, double* out6, cudaStream_t s) {
+  long long n = 1;
+  for (int d = 0; d < g.D; ++d) n *= g.N[d];
+  k_deriv_all<<<flat_blocks(n), 256, 0, s>>>(g, in, dim, out6, n);
   hj_count_launch(1);
   return cudaGetLastError();
 }

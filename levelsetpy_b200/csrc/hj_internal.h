@@ -15,6 +15,7 @@ cudaError_t hj_launch_deriv(int weno, const KGrid& g, const double* in, int dim,
                             const unsigned long long* epsmax, cudaStream_t s);
 cudaError_t hj_launch_sys_op(int system_id, int op, const KGrid& g, const KSys& ks, const double* const* a,
                              const double* const* b, double* out, int dl, unsigned long long* red, cudaStream_t s);
+cudaError_t hj_launch_deriv_all(const KGrid& g, const double* in, int dim, double* out6, cudaStream_t s);
 cudaError_t hj_launch_add_ghost(const KGrid& g, const double* in, int dim, int width, double* out, cudaStream_t s);
 cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, unsigned long long* red,
                                 cudaStream_t s);

@@ -235,6 +235,15 @@ class Engine:
         L.check(self.lib.hj_deriv(self.h, self.stream(), pin, int(dim), pL, pR))
         return getL(), getR()
 
+    def deriv_candidates(self, data, dim):
+        """upwindFirstENO3aHelper: ([dL0, dL1, dL2], [dR0, dR1, dR2]), same kind / shape as ``data``."""
+        keep, pin = self._to_device(data)
+        shape = tuple(data.shape)
+        o, po, _, get = self._like(data, 6 * self.nodes, (6,) + shape)
+        L.check(self.lib.hj_deriv_candidates(self.h, self.stream(), pin, int(dim), po))
+        a = get()
+        return [a[0], a[1], a[2]], [a[3], a[4], a[5]]
+
     def add_ghost(self, data, dim, width):
         keep, pin = self._to_device(data)
         shape = list(self.shape)

@@ -11,8 +11,8 @@ def upwindFirstWENO5a(grid, data, dim, generateAll=False, wenoMode="as_shipped")
     ``wenoMode``: 'as_shipped' (the reference's behaviour) or 'intended' (true WENO5 weights)."""
     if dim < 0 or dim > grid.dim:
         raise ValueError("Illegal dim parameter")           # upwind_first_weno5a.py:59-60
-    if generateAll:
-        raise NotImplementedError("generateAll=True (the three raw ENO candidates) is outside the hot path")
+    if generateAll:                                         # :73-75: the three ENO approximations of the helper
+        return engine_for_grid(grid, wenoMode).deriv_candidates(data, dim)
     return engine_for_grid(grid, wenoMode).deriv(data, dim)
 
 
@@ -25,7 +25,9 @@ def _eno(grid, data, dim, generateAll, scheme):
     if dim < 0 or dim > grid.dim:
         raise ValueError("Illegal dim parameter")           # upwind_first_eno2.py:52-53, upwind_first_eno3a.py:77-78
     if generateAll:
-        raise NotImplementedError("generateAll=True (the raw ENO candidates) is outside the hot path")
+        if scheme != "eno3a":
+            raise NotImplementedError("generateAll=True of upwindFirstENO2 (its two second-order candidates) is outside the hot path")
+        return engine_for_grid(grid, scheme).deriv_candidates(data, dim)    # upwind_first_eno3a.py:82-84
     return engine_for_grid(grid, scheme).deriv(data, dim)
 
 

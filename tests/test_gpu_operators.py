@@ -104,3 +104,19 @@ def test_llf_equals_glf_for_scalar_alphas(lsp):
     assert sb == wsb == osb
     assert np.array_equal(diss, np.broadcast_to(wdiss, g.shape))
     assert b.dissipation(0.0, d0, None, None, None, 1) == ob.dissipation(0.0, d0, None, None, osd, 1)
+
+
+def test_generate_all_candidates_bit_exact(lsp):
+    """upwindFirstWENO5a / upwindFirstENO3a(..., generateAll=True) = the six candidates of upwindFirstENO3aHelper
+    (upwind_first_weno5a.py:73-75, ENO3aHelper.py:116-189): un-fused arithmetic in the reference's order, so bit for bit."""
+    g, d0 = _air3d(lsp, (21, 17, 13))
+    for d in range(3):
+        for fn in (lsp.upwindFirstWENO5a, lsp.upwindFirstENO3a):
+            dL, dR = fn(g, d0, d, True)
+            wL, wR, _, _ = orc.eno3a_helper(g, d0, d)
+            assert len(dL) == 3 and len(dR) == 3
+            for k in range(3):
+                assert np.array_equal(np.asarray(dL[k]), wL[k]), (d, k)
+                assert np.array_equal(np.asarray(dR[k]), wR[k]), (d, k)
+    with pytest.raises(ValueError):
+        lsp.upwindFirstWENO5a(g, d0, 4, True)

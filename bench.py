@@ -431,6 +431,19 @@ def cpu_port_step_rate(sample_n, steps, warmup=0):
     return sample_n ** 3 * steps / dt, dt
 
 
+def literal_reference_record():
+    """The LITERAL reference's timing on configs[0], measured where its checkout exists (tools/time_reference_literal.py,
+    build container, through oracle/ref_shim.py) and committed: it cannot travel to the GPU box, so the CPU arm times
+    the oracle port live and quotes this next to it (the port is ~3x faster than the literal code, same bits)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_literal_cpu.json")) as fh:
+            d = json.load(fh)
+        return {k: d[k] for k in ("what", "literal_reference_s_per_step", "literal_reference_point_steps_per_s",
+                                  "oracle_port_s_per_step", "port_over_literal", "identical_result", "where")}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -444,7 +457,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "cpu_sample": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
+                         "host_cores": os.cpu_count(), "literal_reference": literal_reference_record()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -708,6 +721,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         rate, csecs = cpu_port_step_rate(args.cpu_sample, args.cpu_steps)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                                "literal_reference": literal_reference_record(),
                                 "sample": "air3D %d^3, %d TVD-RK3 steps of the numpy oracle port (%.1f s)" % (
                                     args.cpu_sample, args.cpu_steps, csecs)}
     print(json.dumps(line))

@@ -132,7 +132,7 @@ class SlabSolver:
         halo transfer are ONE kernel, no copy follows it; ``pieces`` is then irrelevant.  ``fused="hybrid"``: only the
         planes for the upper neighbour go that way, those for the lower one are pushed by the copy engines behind the
         kernel (under the next stage's pass 1), so that the two transports share the link.  "auto" picks hybrid when the
-        halo is more than a quarter of the slab (41 planes over 8 ranks: 49.2 ms per step against 53.3 ms with both
+        halo is more than half of the slab (41 planes over 8 ranks: 49.2 ms per step against 53.3 ms with both
         sides stored from the kernel and 57.7 ms with copy-engine pieces), both sides otherwise."""
         sd = schemeData
         for f in ("grid", "hamFunc", "partialFunc"):
@@ -366,7 +366,7 @@ class SlabSolver:
         """Fused pushes towards the upper neighbour only, copy engines towards the lower one."""
         if self._fused_arg == "hybrid":
             return True
-        return self._fused_arg == "auto" and 2 * GHOST * 4 > self.n0
+        return self._fused_arg == "auto" and 2 * GHOST * 2 > self.n0        # both halos together exceed half the slab
 
     def _ready(self):
         """The per-slab context knows its system and holds a state (true from the first begin_step on)."""

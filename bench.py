@@ -482,12 +482,15 @@ def workload_name(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 def committed_traffic():
-    """dram bytes per stage launch from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            return float(json.load(fh)["avg_bytes_per_launch"])
-    except Exception:
-        return None
+    """dram bytes per stage launch from the committed ncu --set full capture (profiles/r02_traffic.json, made from
+    profiles/r02_ncu_stage_summary.txt), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                return float(json.load(fh)["avg_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def run_ours(args):

@@ -200,7 +200,7 @@ class SlabSolver:
         """Collective.  The resident state was replaced (upload, or written through ``eng.buffer_tensor``): halo pieces
         pushed ahead for the old state are consumed and dropped."""
         if self._primed and self.mode != "compute":
-            self.eng.halo_wait(0, 1 if self.fused() else len(self._cols[1]))
+            self.eng.halo_wait(0, 1 if self.fused() else len(self.pieces() or [None]))
         self._primed = False
 
     def set_mode(self, mode):

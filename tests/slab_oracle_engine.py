@@ -204,3 +204,107 @@ def _extrap(*a, **k):
 
 
 _extrap.__name__ = "addGhostExtrapolate"
+
+
+class PeerOracleSlabEngine(TwoPassOracleSlabEngine):
+    """The peer-memory halo interface of the CUDA context (hj_halo_export / attach / push / wait / set_fused / signal,
+    hj_split_cols / hj_stage_pass_cols) on CPU buffers, for the protocols of LocalWorld: a descriptor is a key into a
+    process-wide registry, a push copies the edge planes (optionally only some columns of the flattened trailing dims)
+    into the neighbour's halo planes and bumps its arrival counter, a wait ASSERTS that the pushes it depends on have
+    been made (one process, one "stream": a wait that would have to block is a protocol bug), and pass 2 with fused
+    sides writes its edge planes into those neighbours itself."""
+
+    registry = {}
+
+    def __init__(self, *a, **k):
+        TwoPassOracleSlabEngine.__init__(self, *a, **k)
+        self.flags = np.zeros((2, 3), dtype=np.int64)       # [side of MY halo: 0 lower, 1 upper][buffer]
+        self.pushed = np.zeros((2, 3), dtype=np.int64)      # [towards lower, upper neighbour][buffer]
+        self.waited = np.zeros(3, dtype=np.int64)
+        self.peers = [None, None]
+        self.fused_sides = 0
+        self.calls = []
+
+    def halo_export(self):
+        key = len(PeerOracleSlabEngine.registry)
+        PeerOracleSlabEngine.registry[key] = self
+        return key.to_bytes(8, "little") + bytes(504)
+
+    def halo_attach(self, lower, upper):
+        pick = lambda d: None if d is None else PeerOracleSlabEngine.registry[int.from_bytes(d[:8], "little")]
+        self.peers = [pick(lower), pick(upper)]
+
+    def halo_detach(self):
+        self.peers = [None, None]
+
+    def _planes(self, side):
+        """(my source planes, the neighbour's destination planes) towards the neighbour on ``side`` of buffer views."""
+        n0 = self.n0
+        return (slice(G, 2 * G), slice(self.peers[0].n0 + G, self.peers[0].n0 + 2 * G)) if side == 0 else \
+               (slice(n0, n0 + G), slice(0, G))
+
+    def _copy(self, b, side, cols):
+        src_sl, dst_sl = self._planes(side)
+        peer = self.peers[side]
+        src = self._buf[b].reshape(self.n0 + 2 * G, -1)[src_sl]
+        dst = peer._buf[b].reshape(peer.n0 + 2 * G, -1)[dst_sl]
+        if cols is None:
+            dst[...] = src
+        else:
+            a, e, row_len = cols
+            assert src.shape[1] % row_len == 0
+            src.reshape(G, -1, row_len)[:, :, a:e].shape  # noqa: B018 (shape check)
+            dst.reshape(G, -1, row_len)[:, :, a:e] = src.reshape(G, -1, row_len)[:, :, a:e]
+
+    def _bump(self, b, side):
+        self.pushed[side][b] += 1
+        self.peers[side].flags[1 - side][b] = self.pushed[side][b]       # my upper neighbour's LOWER halo, and vice versa
+
+    def halo_push(self, b, cols=None, sides=3):
+        self.calls.append(("push", b, cols, sides))
+        for side in (0, 1):
+            if self.peers[side] is not None and sides & (1 << side):
+                self._copy(b, side, cols)
+                self._bump(b, side)
+
+    def halo_signal(self, b, sides=3):
+        self.calls.append(("signal", b, sides))
+        for side in (0, 1):
+            if self.peers[side] is not None and sides & (1 << side):
+                self._bump(b, side)
+
+    def halo_wait(self, b, npush=1):
+        self.calls.append(("wait", b, npush))
+        self.waited[b] += npush
+        for side in (0, 1):
+            if self.peers[side] is not None:
+                assert self.flags[side][b] >= self.waited[b], \
+                    "wait on buffer %d (side %d) before the push it depends on: %d < %d" % (
+                        b, side, self.flags[side][b], self.waited[b])
+
+    def halo_set_fused(self, sides=3):
+        self.fused_sides = int(sides)
+
+    def split_cols(self):
+        return int(np.prod(self.N[1:])), 2
+
+    def stage(self, stage, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=False, which_pass=0):
+        TwoPassOracleSlabEngine.stage(self, stage, t, dt, params, comp, use_obstacle, want_reduce, which_pass)
+        if which_pass == 2 and self.fused_sides:           # the kernel's own stores into the neighbours' halo planes
+            o = self.stage_io(stage)[1]
+            for side in (0, 1):
+                if self.peers[side] is not None and self.fused_sides & (1 << side):
+                    self._copy(o, side, None)
+
+    def stage_cols(self, stage, a, e, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=0):
+        """Pass 2 on columns [a, e) of the flattened trailing dims: the whole stage is evaluated from the buffer as it
+        is -- the halo columns outside [a, e) may be stale -- and only the columns [a, e) of the result are kept (a
+        star stencil reads the dim-0 halos at its own column only)."""
+        self.log.append(("cols", stage, a, e))
+        i, o = self.stage_io(stage)
+        keep = self._buf[o].copy()
+        OracleSlabEngine.stage(self, stage, t, dt, params, comp, use_obstacle, want_reduce)
+        new = self._buf[o].reshape(self.n0 + 2 * G, -1)
+        old = keep.reshape(self.n0 + 2 * G, -1)
+        old[G:G + self.n0, a:e] = new[G:G + self.n0, a:e]
+        self._buf[o][...] = keep

@@ -142,3 +142,41 @@ def test_partition():
     assert partition(12, 4) == [(0, 3), (3, 6), (6, 9), (9, 12)]
     with pytest.raises(ValueError):
         partition(16, 8)
+
+
+@pytest.mark.parametrize("mode", ["whole", "pieces", "fused", "hybrid"])
+@pytest.mark.parametrize("world,periodic0", [(2, False), (3, True), (4, False)])
+def test_peer_halo_protocols_on_cpu(world, periodic0, mode):
+    """The host side of the peer-memory halo protocols (levelsetpy_b200/slab.py) with a CPU stand-in for
+    the per-slab context (tests/slab_oracle_engine.py::PeerOracleSlabEngine): whole-plane pushes, pass 2 in column
+    pieces with early pushes, halo planes stored by pass 2 itself (both sides / hybrid).  A wait that precedes the push
+    it depends on trips an assertion in the stand-in; the result must equal the single-domain oracle."""
+    from slab_oracle_engine import PeerOracleSlabEngine
+    from levelsetpy_b200.slab import LocalWorld
+    lsp, g, d0, sd = _case(periodic0)
+    kw = {"whole": dict(pieces=1, fused=False), "pieces": dict(pieces=3, fused=False),
+          "fused": dict(pieces=1, fused=True), "hybrid": dict(pieces=1, fused="hybrid")}[mode]
+    w = LocalWorld(sd, world, engine_factory=PeerOracleSlabEngine, **kw)
+    assert w.peer
+    w.upload(d0)
+    t, ts = 0.0, []
+    for _ in range(2):
+        t, dt = w.step(t, 1.0, 0.8, comp=1)
+        ts.append(t)
+    want_ts, want = _oracle(g, d0, 2, True)
+    assert ts == want_ts
+    assert np.max(np.abs(w.download() - want)) <= 1e-12 * (want.max() - want.min())
+    s0 = w.slabs[0]
+    kinds = [c[0] for c in s0.eng.calls]
+    assert s0.fused() == (mode in ("fused", "hybrid")) and (s0.pieces() is not None) == (mode == "pieces")
+    if mode == "fused":          # one priming push, then only signals: no copy is queued in the steady state
+        assert kinds.count("push") == 1 and kinds.count("signal") == 6
+    if mode == "hybrid":         # every stage: signal towards the upper neighbour, copy-engine push towards the lower one
+        assert [c[3] for c in s0.eng.calls if c[0] == "push"][1:] == [1] * 6
+        assert [c[2] for c in s0.eng.calls if c[0] == "signal"] == [2] * 6
+    if mode == "pieces":
+        assert kinds.count("push") == 3 * (1 + 6) and kinds.count("wait") == 3 * 6
+    # a second upload drops what was pushed ahead for the old state and the march still matches
+    w.upload(d0)
+    t2, _ = w.step(0.0, 1.0, 0.8, comp=1)
+    assert t2 == want_ts[0]

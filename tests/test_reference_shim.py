@@ -176,3 +176,31 @@ def test_reference_driver_zero_is_set_and_full_horizon(ref):
     want, dts, _ = orc.hji_solve(d0, tau, osd, "minVOverTime")
     assert len(dts) >= 8
     assert np.array_equal(full, want), "oracle == literal reference after the full horizon (%d steps)" % len(dts)
+
+
+def test_reference_llf_as_shipped(ref):
+    """artificialDissipationLLF as shipped (diss_local_laxfried.py:126-134): `stepBoundInv` is summed un-maximised, so with
+    an ARRAY alpha `(1 / stepBoundInv).get().item()` raises ValueError -- the behaviour this package reproduces
+    (levelsetpy_b200/dissipation.py, term.py) -- while GLF on the same inputs runs; and the reference's host-side
+    validation of this package's schemeData for LLF gives the same verdict without touching a GPU."""
+    from LevelSetPy.ExplicitIntegration.Dissipation import artificialDissipationLLF
+    import levelsetpy_b200 as lsp
+    N = [13, 11, 9]
+    g = ref["G"].createGrid(col([-6, -10, 0]), col([20, 10, 2 * np.pi * (1 - 1 / N[2])]), col(N, np.int64), pdDims=2)
+    d0 = np.ascontiguousarray(np.sqrt(g.xs[0] ** 2 + g.xs[1] ** 2) - 5 + 0.2 * np.sin(g.xs[2]))
+    B = ref["U"].Bundle
+    s = ref["DS"].DubinsVehicleRel(g, 5, 1)
+    sd = B(dict(grid=g, hamFunc=s.hamiltonian, partialFunc=s.dissipation, dissFunc=ref["EI"].artificialDissipationGLF,
+                CoStateCalc=ref["SD"].upwindFirstWENO5a))
+    _, sb, _ = ref["EI"].termLaxFriedrichs(0.0, d0.reshape(-1, 1), sd)
+    assert sb > 0
+    sd.dissFunc = artificialDissipationLLF
+    with pytest.raises(ValueError, match="size 1"):
+        ref["EI"].termLaxFriedrichs(0.0, d0.reshape(-1, 1), sd)
+    # this package, same bundle shape: the LLF token with an array-alpha system is refused with the same error, before
+    # any device call (prepare_scheme resolves the functor on the host)
+    from levelsetpy_b200.term import prepare_scheme
+    mine = lsp.DubinsVehicleRel(g, 5, 1)
+    with pytest.raises(ValueError, match="size 1"):
+        prepare_scheme(lsp.Bundle(dict(grid=g, hamFunc=mine.hamiltonian, partialFunc=mine.dissipation,
+                                       dissFunc=lsp.artificialDissipationLLF, CoStateCalc=lsp.upwindFirstWENO5a)))

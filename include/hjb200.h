@@ -272,6 +272,9 @@ int hj_ode_cfl3_single(hj_ctx* ctx, void* stream, double t, double t_end, double
 int hj_ode_cfl3_step(hj_ctx* ctx, void* stream, double t, double t_end, double factor_cfl, double max_step,
                      const double* y_in, double* y_out, int is_host, int comp, int use_obstacle, double* t_new,
                      double* dt_out);
+/* Chunk height (dim-0 planes) of that software pipeline; 0 = the library's default.  A tuning knob: results do not depend
+ * on it (every chunking is bit-identical to the resident step). */
+int hj_set_pipeline_planes(hj_ctx* ctx, int planes);
 /* Pinned (page-locked) host memory for those buffers. */
 int hj_host_alloc(int64_t bytes, void** out);
 int hj_host_free(void* p);

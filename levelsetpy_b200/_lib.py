@@ -71,6 +71,7 @@ SIGNATURES = {
     "hj_change": (_i, [_vp, _vp, _pd, _pi]),
     "hj_discount": (_i, [_vp, _vp, _d, _i, _i, _d]),
     "hj_set_restrict": (_i, [_vp, _i]),
+    "hj_set_pipeline_planes": (_i, [_vp, _i]),
     "hj_step_rk2": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_create_batch": (_i, [C.POINTER(_vp), _i, _i, _i, _pi64, _pd, _pi, _pi, _i]),
     "hj_step_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i]),

@@ -730,6 +730,13 @@ int hj_discount(hj_ctx* c, void* stream, double gamma, int mode, int take_max, d
   return HJ_OK;
 }
 
+int hj_set_pipeline_planes(hj_ctx* c, int planes) {
+  if (!c) return fail(HJ_ERR_INVALID, "null ctx");
+  if (planes < 0) return fail(HJ_ERR_INVALID, "hj_set_pipeline_planes: planes must be >= 0 (0 = default)");
+  c->pipe_planes = planes;
+  return HJ_OK;
+}
+
 int hj_set_restrict(hj_ctx* c, int sign) {
   if (!c) return fail(HJ_ERR_INVALID, "null ctx");
   c->restrict_sign = sign > 0 ? 1 : (sign < 0 ? -1 : 0);
@@ -764,11 +771,12 @@ int hj_step_reductions(hj_ctx* c, void* stream, double* reduce_host) {
   return HJ_OK;
 }
 
-// Host-buffer stepping as a software pipeline (3-D grids whose dim 0 is the marched Z dim): dim 0 is cut into chunks;
-// chunk k+1 is on its way up while the stage kernels of chunks <= k run as a wavefront S1(w), S2(w-1), S3(w-2) on the
-// compute stream (stream order satisfies every +-3-plane stencil dependency, and stage 3's in-place write of chunk k
-// comes after every stage-1 read of it), and chunk w-2 goes down on a third stream as soon as its stage 3 is done.
-// With pinned host memory the two PCIe directions overlap each other and the compute.
+// Host-buffer stepping as a software pipeline (3-D grids whose dim 0 is the marched Z dim): dim 0 is uploaded in chunks;
+// as soon as chunk w is up, stage 1 advances every plane whose +3-plane stencil is now resident (up to hi(w) - 3), stage 2
+// the planes 3 further down (up to hi(w) - 6), stage 3 those up to hi(w) - 9, and these finished planes go down on a third
+// stream at once: the download runs one chunk + 9 planes behind the upload.  Stream order on the compute stream satisfies
+// every +-3-plane dependency; stage 3 writes buffer 0 in place only below hi(w) - 9, which no later launch reads and no
+// later upload touches.  With pinned host memory the two PCIe directions overlap each other and the compute.
 static bool can_pipeline(hj_ctx* c, int is_host) {
   if (!is_host || c->D != 3 || c->halo0 || c->nbatch || c->weno != HJ_WENO_AS_SHIPPED) return false;
   if (c->pitch != c->gp.N[2] || c->gp.bc[0] == HJ_BC_PERIODIC || c->gp.N[0] < 64) return false;
@@ -776,10 +784,17 @@ static bool can_pipeline(hj_ctx* c, int is_host) {
   return use_tma(c) && !hj_tma_plan_is_split(c->plan);
 }
 
+// default chunk of the pipelined step.  Measured at 512^3 (tools/e2e_chunk_sweep.py, profiles/r02_e2e_chunk_sweep.jsonl):
+// 16- and 32-plane chunks (32 / 64 MB) 24.0 ms per step, 8 planes 25.5, 4 planes 28.1 (a chunk's three launches re-load a
+// 6-plane lead-in); the bare full-duplex transfer of the field is 21.6 ms, the same chunked copies without kernels 22.4.
+static constexpr long long PIPE_CHUNK_BYTES = 32ll << 20;
+
 static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, const double* y_host, double* y_out, int comp, int use_obs) {
   const int N0 = c->gp.N[0];
-  int P = (N0 + 15) / 16;
-  if (P < 32) P = 32;
+  int P = c->pipe_planes;
+  if (P <= 0) P = (int)((PIPE_CHUNK_BYTES + c->plane * 8 - 1) / (c->plane * 8));
+  if (P > (N0 + 7) / 8) P = (N0 + 7) / 8;   // at least 8 chunks
+  if (P < 1) P = 1;
   const int C = (N0 + P - 1) / P;
   if (!c->s_h2d) {
     CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
@@ -806,21 +821,22 @@ static int pipelined_step(hj_ctx* c, cudaStream_t s, double dt, const double* y_
     CK(cudaEventRecord(c->ev_up[k], c->s_h2d));
   }
   c->have_state = true;
-  for (int w = 0; w < C + 2; ++w) {
-    int r;
-    if (w < C) {
-      CK(cudaStreamWaitEvent(s, c->ev_up[w + 1 < C ? w + 1 : C - 1], 0));     // the +3-plane halo lives in chunk w+1
-      if ((r = stage_impl(c, s, 1, dt, nullptr, comp, use_obs, 0, false, false, lo(w), hi(w)))) return r;
+  int done[4] = {0, 0, 0, 0};                    // planes [0, done[st]) of stage st are launched
+  for (int w = 0; w < C; ++w) {
+    CK(cudaStreamWaitEvent(s, c->ev_up[w], 0));
+    const int d2h_from = done[3];
+    for (int stg = 1; stg <= 3; ++stg) {
+      int upto = w == C - 1 ? N0 : hi(w) - 3 * stg;
+      if (upto <= done[stg]) continue;
+      int r;
+      if ((r = stage_impl(c, s, stg, dt, nullptr, comp, use_obs, 0, false, false, done[stg], upto))) return r;
+      done[stg] = upto;
     }
-    if (w >= 1 && w - 1 < C)
-      if ((r = stage_impl(c, s, 2, dt, nullptr, comp, use_obs, 0, false, false, lo(w - 1), hi(w - 1)))) return r;
-    if (w >= 2) {
-      const int k = w - 2;
-      if ((r = stage_impl(c, s, 3, dt, nullptr, comp, use_obs, 0, false, false, lo(k), hi(k)))) return r;
-      CK(cudaEventRecord(c->ev_done[k], s));
-      CK(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
-      CK(cudaMemcpyAsync(y_out + lo(k) * plane, c->buf[0] + lo(k) * plane, (hi(k) - lo(k)) * plane * sizeof(double),
-                         cudaMemcpyDeviceToHost, c->s_d2h));
+    if (done[3] > d2h_from) {
+      CK(cudaEventRecord(c->ev_done[w], s));
+      CK(cudaStreamWaitEvent(c->s_d2h, c->ev_done[w], 0));
+      CK(cudaMemcpyAsync(y_out + d2h_from * plane, c->buf[0] + d2h_from * plane,
+                         (size_t)(done[3] - d2h_from) * plane * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
     }
   }
   CK(cudaStreamSynchronize(c->s_d2h));

@@ -42,6 +42,7 @@ struct hj_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_done;
   cudaEvent_t ev_start = nullptr;
+  int pipe_planes = 0;           // dim-0 planes per chunk of the pipelined step (0: the default policy)
   HjTmaPlan* plan = nullptr;
   bool plan_tried = false;
   std::string plan_err;

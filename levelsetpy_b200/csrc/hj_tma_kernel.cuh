@@ -476,12 +476,15 @@ k_stage_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     mbar_wait(land_s + 8 * k, 0);
     if (k < 3) q[k] = lds2(ring + (size_t)k * SLOT + myoff);
   }
-  if (bcz == HJ_BC_EXTRAPOLATE && z0 == 0) {
-    const double2 e0 = lds2(ring + (size_t)3 * SLOT + myoff), e1 = lds2(ring + (size_t)4 * SLOT + myoff);
+  if (bcz == HJ_BC_EXTRAPOLATE && z0 < 3) {
+    // planes below the grid (ring positions k < 3 - z0; a plane range may start at z0 = 1 or 2) from planes 0, 1
+    const double2 e0 = lds2(ring + (size_t)(3 - z0) * SLOT + myoff), e1 = lds2(ring + (size_t)(4 - z0) * SLOT + myoff);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {                            // planes -3,-2,-1 from planes 0,1
-      q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - k, g.slope_mult[DZ]);
-      q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - k, g.slope_mult[DZ]);
+    for (int k = 0; k < 3; ++k) {
+      if (k < 3 - z0) {
+        q[k].x = ghost_extrapolate(e0.x, e1.x, 3 - z0 - k, g.slope_mult[DZ]);
+        q[k].y = ghost_extrapolate(e0.y, e1.y, 3 - z0 - k, g.slope_mult[DZ]);
+      }
     }
   }
   __syncwarp();

@@ -388,6 +388,10 @@ class Engine:
         """termRestrictUpdate: +1 -> ydot = max(ydot, 0); -1 -> min(ydot, 0); 0 -> off."""
         L.check(self.lib.hj_set_restrict(self.h, int(sign)))
 
+    def set_pipeline_planes(self, planes):
+        """Chunk height of the pipelined host-buffer step (hj_ode_cfl3_step); 0 = default.  Results do not depend on it."""
+        L.check(self.lib.hj_set_pipeline_planes(self.h, int(planes)))
+
     def step_rk2(self, t, dt, stage_params=None, comp=L.COMP_NONE, use_obstacle=False, want_reduce=False):
         p = None
         if stage_params is not None:

@@ -271,4 +271,12 @@ def test_pipelined_host_step_is_bit_identical(lsp, N, pd):
         assert np.array_equal(y, want), "comp=%d: max diff %.3e" % (comp, np.max(np.abs(y - want)))
         if comp == L.COMP_NONE:
             assert_close(y.reshape(-1, 1), yo, FIELD_TOL, "pipelined step vs oracle")
+        # the chunk height is a tuning knob only (hj_set_pipeline_planes): every chunking gives the same bits, down to the
+        # smallest one the +-3-plane stencil allows, and with a ragged last chunk
+        for planes in (1, 3, 5, 11, 32, N[0]):
+            eng.set_pipeline_planes(planes)
+            y2 = np.ascontiguousarray(d0.reshape(-1)).copy()
+            t2, _, _ = eng.ode_cfl3_single(0.0, 1.0, 0.8, np.finfo(np.float64).max, y2, comp)
+            assert t2 == to and np.array_equal(y2, want), "planes=%d comp=%d" % (planes, comp)
+        eng.set_pipeline_planes(0)
     eng.set_backend(L.BACKEND_AUTO)

@@ -17,6 +17,7 @@
 
 #include "../levelsetpy_b200/csrc/hj_internal.h"
 #include "../levelsetpy_b200/csrc/hj_tma_kernel.cuh"
+#include "hj_quad_kernel.cuh"
 #include "../levelsetpy_b200/csrc/hj_tma_plan.h"
 
 using namespace hjtma;
@@ -42,6 +43,24 @@ __global__ void k_xor(const unsigned long long* p, long long n, unsigned long lo
   if ((threadIdx.x & 31) == 0) atomicXor(out, acc);
 }
 
+// max |a - b|, number of differing words and the first differing index (debugging a new variant against the reference)
+__global__ void k_diff(const double* a, const double* b, long long n, unsigned long long* out) {
+  double m = 0.0;
+  unsigned long long cnt = 0, first = ~0ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = a[i], y = b[i];
+    if (__double_as_longlong(x) != __double_as_longlong(y)) {
+      ++cnt;
+      if ((unsigned long long)i < first) first = (unsigned long long)i;
+      const double d = fabs(x - y);
+      m = (d == d) ? fmax(m, d) : INFINITY;
+    }
+  }
+  atomicAdd(out, cnt);
+  atomicMin(out + 1, first);
+  atomicMax(out + 2, (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like integers
+}
+
 struct Problem {
   int N;
   KGrid g;
@@ -51,6 +70,8 @@ struct Problem {
   const char* only;          // substring filter on the variant name
   unsigned long long* xor_dev;
   double peak;
+  double* ref_out[3];        // stage outputs of the first variant (device copies), for k_diff
+  int cz_override;           // > 0: planes per Z chunk for the quad variants
 };
 
 static unsigned long long checksum(Problem& P, const double* p) {
@@ -61,9 +82,15 @@ static unsigned long long checksum(Problem& P, const double* p) {
   return h;
 }
 
-template <class Cfg, int STAGE>
+template <class Cfg, int STAGE, bool QUAD>
+static auto pick_kernel() {
+  if constexpr (QUAD) return k_stage_quad<SysDubinsRel, HJ_WENO_AS_SHIPPED, false, STAGE, Cfg>;
+  else return k_stage_tma<SysDubinsRel, 3, HJ_WENO_AS_SHIPPED, false, STAGE, Cfg>;
+}
+
+template <class Cfg, int STAGE, bool QUAD = false>
 static float run_stage(Problem& P, int reps, unsigned long long* sum) {
-  auto kern = k_stage_tma<SysDubinsRel, 3, HJ_WENO_AS_SHIPPED, false, STAGE, Cfg>;
+  auto kern = pick_kernel<Cfg, STAGE, QUAD>();
   constexpr size_t smem = Cfg::template smem_bytes<STAGE>();
   constexpr int NTHREADS = Cfg::NTHREADS;
   if (!P.plans[Cfg::TY]) {
@@ -71,7 +98,13 @@ static float run_stage(Problem& P, int reps, unsigned long long* sum) {
     P.plans[Cfg::TY] = hj_tma_plan_create(P.g, HJ_SYS_DUBINS_REL, HJ_WENO_AS_SHIPPED, P.buf, 0, err, sizeof err, Cfg::TY);
     if (!P.plans[Cfg::TY]) { printf("plan: %s\n", err); exit(1); }
   }
-  HjTmaPlan* plan = P.plans[Cfg::TY];
+  HjTmaPlan planv = *P.plans[Cfg::TY];
+  HjTmaPlan* plan = &planv;
+  if (QUAD && P.cz_override > 0) {
+    plan->geo.cz = P.cz_override;
+    plan->geo.nzc = (P.N + plan->geo.cz - 1) / plan->geo.cz;
+    plan->nblocks = plan->tiles * plan->geo.nzc;
+  }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
@@ -98,6 +131,25 @@ static float run_stage(Problem& P, int reps, unsigned long long* sum) {
   float ms;
   CK(cudaEventElapsedTime(&ms, e0, e1));
   *sum = checksum(P, st.out);
+  const long long n = (long long)P.N * P.N * P.N;
+  if (!P.ref_out[STAGE - 1]) {
+    CK(cudaMalloc(&P.ref_out[STAGE - 1], n * 8));
+    CK(cudaMemcpy(P.ref_out[STAGE - 1], st.out, n * 8, cudaMemcpyDeviceToDevice));
+  } else if (QUAD) {
+    unsigned long long h[3] = {0, ~0ull, 0}, *d;
+    CK(cudaMalloc(&d, 24));
+    CK(cudaMemcpy(d, h, 24, cudaMemcpyHostToDevice));
+    k_diff<<<1184, 256>>>(st.out, P.ref_out[STAGE - 1], n, d);
+    CK(cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost));
+    CK(cudaFree(d));
+    if (h[0]) {
+      double m;
+      memcpy(&m, &h[2], 8);
+      const long long i = (long long)h[1];
+      printf("\n   stage %d: %llu words differ, first at (z %lld, y %lld, x %lld), max |diff| %.3e\n   ", STAGE, h[0],
+             i / ((long long)P.N * P.N), (i / P.N) % P.N, i % P.N, m);
+    }
+  }
   if (STAGE == 1) printf("[occ %d regs ", occ);
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
@@ -105,15 +157,15 @@ static float run_stage(Problem& P, int reps, unsigned long long* sum) {
   return ms / reps;
 }
 
-template <class Cfg>
+template <class Cfg, class Cfg23 = Cfg, bool QUAD = false>
 static void run_variant(Problem& P, const char* name, int reps, unsigned long long ref[3]) {
-  if (P.only && !strstr(name, P.only)) return;
+  if (P.only && ref[0] && !strstr(name, P.only)) return;     // the first variant always runs: it is the reference
   printf("%-22s ", name);
   unsigned long long s[3];
   // stage order matters: stage 2 reads buf1 (stage-1 output), stage 3 reads buf2 and overwrites buf1
-  const float t1 = run_stage<Cfg, 1>(P, reps, &s[0]);
-  const float t2 = run_stage<Cfg, 2>(P, reps, &s[1]);
-  const float t3 = run_stage<Cfg, 3>(P, reps, &s[2]);
+  const float t1 = run_stage<Cfg, 1, QUAD>(P, reps, &s[0]);
+  const float t2 = run_stage<Cfg23, 2, QUAD>(P, reps, &s[1]);
+  const float t3 = run_stage<Cfg23, 3, QUAD>(P, reps, &s[2]);
   bool same = true;
   for (int i = 0; i < 3; ++i) {
     if (!ref[i]) ref[i] = s[i];
@@ -169,12 +221,22 @@ int main(int argc, char** argv) {
     }
   }
   P.ks.p[0] = 5; P.ks.p[1] = 5; P.ks.p[2] = 1; P.ks.p[3] = 1; P.ks.p[4] = 1;
-  P.only = argc > 4 ? argv[4] : nullptr;
+  P.only = argc > 4 && strcmp(argv[4], "-") ? argv[4] : nullptr;
+  P.cz_override = argc > 5 ? atoi(argv[5]) : 0;
   printf("N=%d reps=%d\n", N, reps);
   unsigned long long ref[3] = {0, 0, 0};
 #define V(R, MINB, U, TY, SEQ, OPT) \
   run_variant<TmaCfg<R, MINB, U, TY, 16, SEQ, OPT>>(P, "R" #R "_b" #MINB "_u" #U "_ty" #TY "_seq" #SEQ "_opt" #OPT, reps, ref)
   V(8, 2, 1, 16, false, 143);   // production
+  // 2 x 2 nodes per thread (hj_quad_kernel.cuh): 32 x 24 tile, 192 threads, 2 CTAs/SM; ring 8 for stage 1, 7 for stages
+  // 2/3 (the y0 tiles share the shared memory); Q1: X windows of plane z+1 prefetched
+#define Q(R1, R23, MINB, TY, OPT) \
+  run_variant<QuadCfg<R1, MINB, TY, 16, OPT>, QuadCfg<R23, MINB, TY, 16, OPT>, true>(P, "quad_R" #R1 "_" #R23 "_b" #MINB "_ty" #TY "_opt" #OPT, reps, ref)
+  Q(8, 7, 2, 24, 0);
+  Q(8, 7, 2, 24, 1);
+  Q(8, 8, 1, 24, 0);            // 1 CTA/SM: no register cap
+  Q(8, 8, 1, 32, 1);            // 256 threads, 1 CTA/SM
+  Q(6, 6, 3, 16, 0);            // 32 x 16 tile, 128 threads, 3 CTAs/SM
   V(8, 3, 1, 12, false, 143);   // 3 CTAs of 192 threads (18 warps/SM, <= 112 registers)
   V(6, 3, 1, 12, false, 143);
   V(8, 2, 1, 16, true, 143);    // one dim at a time

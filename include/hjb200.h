@@ -61,14 +61,19 @@ typedef enum hj_weno {
  *   DOUBLE_INT      DynamicalSystems/double_integrator.py:49-89  2-D
  *   FLOCK           DynamicalSystems/flock.py:190-258 + bird.py:235-372 (also a lone Bird)  3-D
  *   DUBINS_REL_PAIR product of two DUBINS_REL on dims 0-2 / 3-5  6-D  
- *   DOUBLE_INT_PAIR product of two DOUBLE_INT on dims 0-1 / 2-3  4-D        */
+ *   DOUBLE_INT_PAIR product of two DOUBLE_INT on dims 0-1 / 2-3  4-D  
+ *   GENERIC_DUBINS_CAR  genericHam / genericPartial (Hamiltonians/generic_ham.py:5, generic_partial.py:6) over a
+ *                   device dynSys (csrc/hj_systems.cuh: GenericF<Dyn>), here the 3-D Dubins car
+ *                   dx = (v cos x2 + d0, v sin x2 + d1, u + d2).  Its alpha depends on the derivative range of
+ *                   the field (hj_deriv_range): the parameter block is refreshed before every RK stage.     */
 typedef enum hj_system {
   HJ_SYS_NONE = 0,
   HJ_SYS_DUBINS_REL = 1,
   HJ_SYS_DOUBLE_INT = 2,
   HJ_SYS_FLOCK = 3,
   HJ_SYS_DUBINS_REL_PAIR = 4,
-  HJ_SYS_DOUBLE_INT_PAIR = 5
+  HJ_SYS_DOUBLE_INT_PAIR = 5,
+  HJ_SYS_GENERIC_DUBINS_CAR = 6
 } hj_system;
 
 /* Driver epilogue fused into the last RK stage (ValueFuncs/hji_solver.py:566-599). */
@@ -134,6 +139,13 @@ int64_t hj_field_elems(const hj_ctx* ctx);        /* pitched elements incl. halo
  * caller owns its contents from then on. */
 int hj_state_ptr(hj_ctx* ctx, int which_buffer, double** dev_ptr);
 int64_t hj_plane_elems(const hj_ctx* ctx);        /* pitched elements of one dim-0 plane */
+
+/* derivMin / derivMax of artificialDissipationGLF (artificial_diss_glf.py:82-88) on their own: per dim, the minimum and
+ * the maximum over the grid of the upwind pair (derivL, derivR) of the context's CoStateCalc -- what genericPartial
+ * (Hamiltonians/generic_partial.py:28-40) feeds the dynSys's get_opt_u / get_opt_v BEFORE the dissipation of the same RHS
+ * exists.  y_dev: a dense device array, or NULL for the resident buffer RK stage `stage` (1..3) reads.  deriv_min /
+ * deriv_max: D host doubles each.  One reduce-only kernel; synchronises. */
+int hj_deriv_range(hj_ctx* ctx, void* stream, const double* y_dev, int stage, double* deriv_min, double* deriv_max);
 
 /* upwindFirstWENO5a(grid, data, dim) -> (derivL, derivR)   SpatialDerivative/upwind_first_weno5a.py:13.
  * data/derivL/derivR: dense device arrays of hj_num_nodes doubles (HJ_BC_HALO contexts: not supported). */

@@ -13,6 +13,7 @@ from .dissipation import artificialDissipationGLF, artificialDissipationLLF  # n
 from .term import termLaxFriedrichs, termRestrictUpdate  # noqa: F401
 from .integration import odeCFL3, odeCFL2, odeCFLset  # noqa: F401
 from .systems import DubinsVehicleRel, DoubleIntegrator, Bird, Flock, ProductSystem  # noqa: F401
+from .generic import genericHam, genericPartial, DubinsCar  # noqa: F401
 from .solver import HJIPDE_solve  # noqa: F401
 from .engine import Engine, engine_for_grid, clear_engine_cache  # noqa: F401
 

@@ -15,6 +15,7 @@ HJ_OK, HJ_ERR_INVALID, HJ_ERR_CUDA, HJ_ERR_UNSUPPORTED, HJ_ERR_STATE, HJ_ERR_NAN
 BC_EXTRAPOLATE, BC_PERIODIC, BC_HALO = 0, 1, 2
 WENO_AS_SHIPPED, WENO_INTENDED, SCHEME_ENO3A, SCHEME_ENO2 = 0, 1, 2, 3
 SYS_DUBINS_REL, SYS_DOUBLE_INT, SYS_FLOCK, SYS_DUBINS_REL_PAIR, SYS_DOUBLE_INT_PAIR = 1, 2, 3, 4, 5
+SYS_GENERIC_DUBINS_CAR = 6
 COMP_NONE, COMP_MIN_OVER_TIME, COMP_MAX_OVER_TIME, COMP_MIN_WITH_AUX, COMP_MAX_WITH_AUX = 0, 1, 2, 3, 4
 FIELD_STATE, FIELD_AUX, FIELD_OBSTACLE = 0, 1, 2
 BACKEND_AUTO, BACKEND_GATHER, BACKEND_TMA = 0, 1, 2
@@ -72,6 +73,7 @@ SIGNATURES = {
     "hj_discount": (_i, [_vp, _vp, _d, _i, _i, _d]),
     "hj_set_restrict": (_i, [_vp, _i]),
     "hj_set_pipeline_planes": (_i, [_vp, _i]),
+    "hj_deriv_range": (_i, [_vp, _vp, _vp, _i, _pd, _pd]),
     "hj_step_rk2": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _i]),
     "hj_create_batch": (_i, [C.POINTER(_vp), _i, _i, _i, _pi64, _pd, _pi, _pi, _i]),
     "hj_step_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i]),

@@ -218,6 +218,46 @@ __global__ void __launch_bounds__(BX* BY) k_maxd1sq(const KGrid g, const double*
   }
 }
 
+// derivMin / derivMax of artificial_diss_glf.py:82-88 on their own: min and max over the grid of (derivL, derivR) of every
+// dim, without a system -- what genericPartial (generic_partial.py:28-40) needs BEFORE the dissipation of the same RHS can
+// be formed.  Reads the field once per dim through L1 / L2; the record is the one the stage kernels write (RedAcc).
+template <int D, int WENO>
+__global__ void __launch_bounds__(BX* BY) k_deriv_range(const KGrid g, const double* __restrict__ in,
+                                                         const unsigned long long* epsmax, unsigned long long* red,
+                                                         const long long nouter) {
+  const int NX = g.N[D - 1], NY = g.N[D - 2];
+  const int xt = (NX + BX - 1) / BX;
+  const int ix = (blockIdx.x % xt) * BX + threadIdx.x;
+  const int iy = (blockIdx.x / xt) * BY + threadIdx.y;
+  const bool active = ix < NX && iy < NY;
+  double inv_eps[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) inv_eps[d] = (WENO == HJ_WENO_INTENDED) ? inv_eps_from_max(epsmax[d]) : 0.0;
+  RedAcc<D> acc;
+  acc.init();
+  const long long per = (nouter + gridDim.y - 1) / gridDim.y;
+  const long long o_end = min(nouter, (long long)(blockIdx.y + 1) * per);
+  for (long long o = (long long)blockIdx.y * per; o < o_end; ++o) {
+    if (!active) continue;
+    int idx[D];
+    decompose_outer<D>(o, g, idx);
+    idx[D - 2] = iy;
+    idx[D - 1] = ix;
+    long long off = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) off += (long long)idx[d] * g.stride[d];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double v[7], L, R;
+      load_stencil(in + off, idx[d], g.N[d], g.stride[d], g.bc[d], g.slope_mult[d], v);
+      upwind5<WENO>(v, g.dxinv[d], inv_eps[d], L, R, g.dx[d]);
+      acc.dmin[d] = fmin(acc.dmin[d], fmin(L, R));
+      acc.dmax[d] = fmax(acc.dmax[d], fmax(L, R));
+    }
+  }
+  acc.flush(red);
+}
+
 __global__ void k_init_reduce(unsigned long long* red, int D) {
   const int i = threadIdx.x;
   if (i < D) red[i] = enc_ordered(-INFINITY);
@@ -484,6 +524,36 @@ cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long lo
   }
   hj_count_launch(1);
   return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_deriv_range(int weno, const KGrid& g, const double* in, const unsigned long long* epsmax,
+                                      unsigned long long* red, cudaStream_t s) {
+  const long long no = outer_count<D>(g);
+  const dim3 grid = walk_grid(g, D, no), block(BX, BY);
+  switch (weno) {
+    case HJ_WENO_AS_SHIPPED: k_deriv_range<D, HJ_WENO_AS_SHIPPED><<<grid, block, 0, s>>>(g, in, epsmax, red, no); break;
+    case HJ_WENO_INTENDED: k_deriv_range<D, HJ_WENO_INTENDED><<<grid, block, 0, s>>>(g, in, epsmax, red, no); break;
+    case HJ_SCHEME_ENO3A: k_deriv_range<D, HJ_SCHEME_ENO3A><<<grid, block, 0, s>>>(g, in, epsmax, red, no); break;
+    case HJ_SCHEME_ENO2: k_deriv_range<D, HJ_SCHEME_ENO2><<<grid, block, 0, s>>>(g, in, epsmax, red, no); break;
+    default: return cudaErrorNotSupported;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t hj_launch_deriv_range(int weno, const KGrid& g, const double* in, const unsigned long long* epsmax,
+                                  unsigned long long* red, cudaStream_t s) {
+  cudaError_t e;
+  switch (g.D) {
+    case 2: e = launch_deriv_range<2>(weno, g, in, epsmax, red, s); break;
+    case 3: e = launch_deriv_range<3>(weno, g, in, epsmax, red, s); break;
+    case 4: e = launch_deriv_range<4>(weno, g, in, epsmax, red, s); break;
+    case 5: e = launch_deriv_range<5>(weno, g, in, epsmax, red, s); break;
+    case 6: e = launch_deriv_range<6>(weno, g, in, epsmax, red, s); break;
+    default: return cudaErrorInvalidValue;
+  }
+  hj_count_launch(1);
+  return e;
 }
 
 cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s) {

@@ -21,6 +21,8 @@ cudaError_t hj_launch_alpha_max(int system_id, const KGrid& g, const KSys& ks, u
                                 cudaStream_t s);
 cudaError_t hj_launch_maxd1sq(const KGrid& g, const double* in, unsigned long long* epsmax, int only_dim,
                               cudaStream_t s);
+cudaError_t hj_launch_deriv_range(int weno, const KGrid& g, const double* in, const unsigned long long* epsmax,
+                                  unsigned long long* red, cudaStream_t s);
 cudaError_t hj_launch_init_reduce(unsigned long long* red, int D, cudaStream_t s);
 cudaError_t hj_launch_init_eps(unsigned long long* eps, int D, cudaStream_t s);
 cudaError_t hj_launch_edge_halo(double* buf, long long plane, int n0, int side, double m, cudaStream_t s);

@@ -166,6 +166,92 @@ struct FlockBatchF {
   static constexpr unsigned alpha_dims(int) { return 0u; }
 };
 
+// genericHam / genericPartial (Hamiltonians/generic_ham.py:5-57, generic_partial.py:6-58) with a DEVICE dynSys: the
+// reference evaluates them through three Python methods of schemeData.dynSys -- get_opt_u(t, deriv, uMode, x),
+// get_opt_v(t, deriv, dMode, x), dynamics(t, x, u, d) -- which cannot run inside a fused kernel.  A device dynSys is a
+// struct `Dyn` with
+//   NX, NU, NDST, NPAR                  state / control / disturbance dimensions, its own scalar parameters
+//   Pt, load, fetch<GD>, apply<GD>      the state-dependent drift terms of a node (as the other functors)
+//   opt_u(par, p, sgn, u)               get_opt_u for the costate p: sgn = +1 for uMode 'max', -1 for 'min'
+//   opt_d(par, p, sgn, d)               get_opt_v likewise
+//   f(i, q, par, u, d)                  dynamics(t, x, u, d)[i], un-fused arithmetic in the reference's order
+//   alpha_dims(i)                       the dims |f_i| depends on through x
+// and GenericF<Dyn> turns it into the functor interface of the stage kernels:
+//   ham   = sum_i p_i f_i(x, u*(p), d*(p)), negated for tMode 'backward'                  (generic_ham.py:26-50)
+//   alpha = max(|f_i(uU,dU)|, |f_i(uU,dL)|, |f_i(uL,dL)|, |f_i(uL,dU)|)                    (generic_partial.py:44-56)
+// where uU / uL / dU / dL are the dynSys's optimal inputs at derivMax / derivMin -- GRID-WIDE scalars that the host obtains
+// by calling the dynSys's own get_opt_u / get_opt_v on the reduced derivative range (hj_deriv_range) exactly as
+// generic_partial.py:28-40 does, and hands over in the parameter block.  alpha therefore changes with every RHS evaluation.
+// Block layout (doubles): [0] uSign [1] dSign [2] hamSign (-1: tMode 'backward') | uU[NU] uL[NU] dU[NDST] dL[NDST] | Dyn's NPAR.
+// Registered dynSys: DubinsCarDyn (the Dubins car of the helperOC toolbox this API was written for):
+//   dx0 = speed cos x2 + d0,  dx1 = speed sin x2 + d1,  dx2 = u + d2,  |u| <= wMax, |d_i| <= dMax_i;  par = speed wMax dMax[3]
+template <int TB>
+struct DubinsCarDyn {
+  static constexpr int NX = 3, NU = 1, NDST = 3, NPAR = 5;
+  struct Pt { double vc, vs; };                               // speed cos x2, speed sin x2 (products rounded like numpy's)
+  HJ_DEV static Pt load(const int* idx, const KGrid&, const KSys& k, const double* par) {
+    Pt q;
+    q.vc = __dmul_rn(par[0], __ldg(k.tab[TB + 0] + idx[2]));
+    q.vs = __dmul_rn(par[0], __ldg(k.tab[TB + 1] + idx[2]));
+    return q;
+  }
+  template <int GD>
+  HJ_DEV static double2 fetch(int i, const KGrid&, const KSys& k) {
+    if (GD == 2) return make_double2(__ldg(k.tab[TB + 0] + i), __ldg(k.tab[TB + 1] + i));
+    return make_double2(0.0, 0.0);
+  }
+  template <int GD>
+  HJ_DEV static void apply(Pt& q, const double2 r, const double* par) {
+    if (GD == 2) { q.vc = __dmul_rn(par[0], r.x); q.vs = __dmul_rn(par[0], r.y); }
+  }
+  // (deriv >= 0) * wMax + (deriv < 0) * (-wMax) for 'max', the opposite for 'min'
+  HJ_DEV static void opt_u(const double* par, const double* p, double sgn, double* u) {
+    u[0] = (p[2] >= 0.0) ? sgn * par[1] : -(sgn * par[1]);
+  }
+  HJ_DEV static void opt_d(const double* par, const double* p, double sgn, double* d) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[i] = (p[i] >= 0.0) ? sgn * par[2 + i] : -(sgn * par[2 + i]);
+  }
+  HJ_DEV static double f(int i, const Pt& q, const double*, const double* u, const double* d) {
+    if (i == 0) return __dadd_rn(q.vc, d[0]);
+    if (i == 1) return __dadd_rn(q.vs, d[1]);
+    return __dadd_rn(u[0], d[2]);
+  }
+  static constexpr unsigned alpha_dims(int i) { return i < 2 ? (1u << 2) : 0u; }
+};
+
+template <class Dyn>
+struct GenericF {
+  static constexpr int ND = Dyn::NX, BASE_DIM = 0, NSCRATCH = 0;
+  static constexpr int O_UU = 3, O_UL = O_UU + Dyn::NU, O_DU = O_UL + Dyn::NU, O_DL = O_DU + Dyn::NDST,
+                       O_PAR = O_DL + Dyn::NDST, NP = O_PAR + Dyn::NPAR;
+  using Pt = typename Dyn::Pt;
+  HJ_DEV static Pt load(const int* idx, const KGrid& g, const KSys& k, const double* = nullptr) {
+    return Dyn::load(idx, g, k, k.p + O_PAR);
+  }
+  template <int GD>
+  HJ_DEV static double2 fetch(int i, const KGrid& g, const KSys& k) { return Dyn::template fetch<GD>(i, g, k); }
+  template <int GD>
+  HJ_DEV static void apply(Pt& q, const double2 r, const KSys& k) { Dyn::template apply<GD>(q, r, k.p + O_PAR); }
+  HJ_DEV static double ham(const Pt& q, const double* p, const KSys& k) {
+    double u[Dyn::NU], d[Dyn::NDST];
+    Dyn::opt_u(k.p + O_PAR, p, k.p[0], u);                     // generic_ham.py:27
+    Dyn::opt_d(k.p + O_PAR, p, k.p[1], d);                     // :32
+    double h = 0.0;
+#pragma unroll
+    for (int i = 0; i < Dyn::NX; ++i) h += p[i] * Dyn::f(i, q, k.p + O_PAR, u, d);   // :45-47
+    return k.p[2] < 0.0 ? -h : h;                              // :54-55
+  }
+  HJ_DEV static double alpha(int dl, const Pt& q, const KSys& k) {
+    const double* par = k.p + O_PAR;
+    const double *uU = k.p + O_UU, *uL = k.p + O_UL, *dU = k.p + O_DU, *dL = k.p + O_DL;
+    double a = fmax(fabs(Dyn::f(dl, q, par, uU, dU)), fabs(Dyn::f(dl, q, par, uU, dL)));     // generic_partial.py:52
+    a = fmax(a, fabs(Dyn::f(dl, q, par, uL, dL)));                                           // :53
+    return fmax(a, fabs(Dyn::f(dl, q, par, uL, dU)));                                        // :54
+  }
+  static constexpr unsigned alpha_dims(int dl) { return Dyn::alpha_dims(dl); }
+};
+
 template <class A, class B>
 struct PairF {
   static constexpr int ND = A::ND + B::ND, BASE_DIM = 0, NSCRATCH = 0;
@@ -210,6 +296,7 @@ using SysFlock = FlockF;
 using SysDubinsRelPair = PairF<DubinsRelF<0, 0, 0>, DubinsRelF<3, HJ_DUBINS_NP, 2>>;
 using SysDoubleIntPair = PairF<DoubleIntF<0, 0>, DoubleIntF<2, HJ_DINT_NP>>;
 using SysFlockBatch = FlockBatchF;
+using SysGenericDubinsCar = GenericF<DubinsCarDyn<0>>;
 #define HJ_SYS_FLOCK_BATCH 100   // internal id: HJ_SYS_FLOCK registered on a batch context
 
 // host-side dispatch helper: calls f.template operator()<Sys>() for the functor registered under `id`
@@ -222,6 +309,7 @@ inline bool hj_dispatch_system(int id, F&& f) {
     case HJ_SYS_DUBINS_REL_PAIR: f.template operator()<SysDubinsRelPair>(); return true;
     case HJ_SYS_DOUBLE_INT_PAIR: f.template operator()<SysDoubleIntPair>(); return true;
     case HJ_SYS_FLOCK_BATCH: f.template operator()<SysFlockBatch>(); return true;
+    case HJ_SYS_GENERIC_DUBINS_CAR: f.template operator()<SysGenericDubinsCar>(); return true;
     default: return false;
   }
 }
@@ -233,6 +321,7 @@ inline int hj_system_ndim(int id) {
     case HJ_SYS_DUBINS_REL_PAIR: return 6;
     case HJ_SYS_DOUBLE_INT_PAIR: return 4;
     case HJ_SYS_FLOCK_BATCH: return 4;   // grid dims incl. the batch dim
+    case HJ_SYS_GENERIC_DUBINS_CAR: return 3;
     default: return -1;
   }
 }

@@ -264,6 +264,14 @@ class Engine:
         D = self.D
         return get(), sb.value, dict(alphaMax=r[:D], derivMin=r[D:2 * D], derivMax=r[2 * D:3 * D], nan=bool(r[3 * D]))
 
+    def deriv_range(self, y=None, stage=1):
+        """(derivMin, derivMax) of artificial_diss_glf.py:82-88 -- per dim the min / max over the grid of the upwind pair --
+        of a dense array ``y`` (numpy or torch CUDA tensor), or of the resident buffer RK stage ``stage`` reads (hj_deriv_range)."""
+        lo, hi = (C.c_double * self.D)(), (C.c_double * self.D)()
+        keep, pin = (None, None) if y is None else self._to_device(y)
+        L.check(self.lib.hj_deriv_range(self.h, self.stream(), pin, int(stage), lo, hi))
+        return np.array(lo[:]), np.array(hi[:])
+
     def _ptr_list(self, arrays):
         """(keep-alive list, C array of D device pointers) for a list of D dense arrays."""
         if len(arrays) != self.D:

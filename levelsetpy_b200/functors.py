@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib as L
 
-__all__ = ["resolve", "Adapter"]
+__all__ = ["resolve", "Adapter", "generic_adapter"]
 
 
 def _scalar(x, what):
@@ -30,6 +30,7 @@ class Adapter:
     system_id = 0
     time_varying = False       # parameter block changes from one RHS evaluation to the next (Flock)
     host_alpha = False         # alpha_d are host scalars inside the block (Flock)
+    dynamic = False            # the block depends on the derivative range of the field (genericPartial)
 
     def tables(self, grid):
         return []
@@ -163,6 +164,99 @@ class _Flock(Adapter):
         return [float(block[7]), float(block[8]), float(block[9])]
 
 
+class _GenericDubinsCar(Adapter):
+    """genericHam / genericPartial over a ``DubinsCar``-shaped dynSys (Hamiltonians/generic_ham.py, generic_partial.py).
+    Block (csrc/hj_systems.cuh: GenericF<DubinsCarDyn>): uSign dSign hamSign | uU uL | dU[3] dL[3] | speed wMax dMax[3]."""
+    system_id = L.SYS_GENERIC_DUBINS_CAR
+    ndim = 3
+    time_varying = True        # keeps the host-buffer pipeline (one fixed block per step) away
+    dynamic = True
+
+    def __init__(self, scheme):
+        self.sd = scheme
+        self.dyn = scheme.dynSys
+        for f in ("uIn", "dIn", "deriv", "side"):
+            if f in scheme.__dict__ and getattr(scheme, f) is not None:
+                raise NotImplementedError("schemeData.%s (generic_ham.py:21-43) has no device path" % f)
+        if "TIdim" in self.dyn.__dict__ and self.dyn.TIdim:
+            raise NotImplementedError("dynSys.TIdim (generic_ham.py:49-51) has no device path")
+        if "partialFunc" in self.dyn.__dict__:
+            raise NotImplementedError("dynSys.partialFunc (generic_partial.py:10-12) is an arbitrary Python callable")
+
+    def tables(self, grid):
+        x2 = _vs(grid, 2)
+        return [np.cos(x2), np.sin(x2)]            # host numpy trig == what dynSys.dynamics sees (np.cos(x[2]))
+
+    def modes(self):
+        sd = self.sd
+        u = sd.uMode if "uMode" in sd.__dict__ else "min"          # generic_ham.py:11-12
+        d = sd.dMode if "dMode" in sd.__dict__ else "max"          # :14-15 (genericHam runs first in termLaxFriedrichs)
+        tm = sd.tMode if "tMode" in sd.__dict__ else "backward"    # :17-18
+        for m, what in ((u, "uMode"), (d, "dMode")):
+            if m not in ("min", "max"):
+                raise ValueError("Unknown %s!" % what)
+        return u, d, tm
+
+    def block_for_range(self, deriv_min, deriv_max, t=0.0, d_mode=None):
+        """Parameter block for one RHS evaluation.  deriv_min / deriv_max: the D grid-wide scalars of
+        artificial_diss_glf.py:82-88 (None: Hamiltonian only, alpha inputs zeroed)."""
+        dyn = self.dyn
+        u_mode, dm, t_mode = self.modes()
+        d_mode = d_mode or dm
+        if deriv_min is None:
+            uU = uL = 0.0
+            dU = dL = [0.0, 0.0, 0.0]
+        else:
+            lo = [float(np.asarray(v).reshape(-1)[0]) for v in deriv_min]
+            hi = [float(np.asarray(v).reshape(-1)[0]) for v in deriv_max]
+            # generic_partial.py:28-40: the dynSys's own methods, on the scalar range
+            uU = dyn.get_opt_u(t, hi, u_mode, None)
+            uL = dyn.get_opt_u(t, lo, u_mode, None)
+            dU = dyn.get_opt_v(t, hi, d_mode, None)
+            dL = dyn.get_opt_v(t, lo, d_mode, None)
+        return np.array([1.0 if u_mode == "max" else -1.0, 1.0 if d_mode == "max" else -1.0,
+                         -1.0 if t_mode == "backward" else 1.0, _scalar(uU, "uU"), _scalar(uL, "uL")]
+                        + [_scalar(v, "dU") for v in dU] + [_scalar(v, "dL") for v in dL]
+                        + [_scalar(dyn.speed, "speed"), _scalar(dyn.wMax, "wMax")] + [_scalar(v, "dMax") for v in dyn.dMax])
+
+    def block(self):
+        raise NotImplementedError("a generic dynSys needs the derivative range of the field: block_for_range()")
+
+
+_GENERIC = {"DubinsCar": _GenericDubinsCar}
+
+
+def generic_adapter(scheme, set_defaults=None):
+    """Adapter for schemeData.hamFunc = genericHam / partialFunc = genericPartial: schemeData.dynSys must be an instance of
+    a dynSys class with a compiled device functor (recognised by class name + attributes: DubinsCar).
+    ``set_defaults``: 'ham' / 'partial' write the reference's mode defaults into the bundle (generic_ham.py:11-18,
+    generic_partial.py:16-20) as a standalone call of that function does."""
+    if "dynSys" not in scheme.__dict__:
+        raise AttributeError("'Bundle' object has no attribute 'dynSys'")          # generic_ham.py:8
+    if set_defaults:
+        if "uMode" not in scheme.__dict__:
+            scheme.uMode = "min"
+        if "dMode" not in scheme.__dict__:
+            scheme.dMode = "max" if set_defaults == "ham" else "min"
+        if set_defaults == "ham" and "tMode" not in scheme.__dict__:
+            scheme.tMode = "backward"
+    name = type(scheme.dynSys).__name__
+    if name not in _GENERIC:
+        raise NotImplementedError(
+            "schemeData.dynSys is a %s: genericHam / genericPartial call its Python methods get_opt_u / get_opt_v / "
+            "dynamics on full-grid arrays, which cannot run inside the fused kernel; registered device dynSys classes: %s "
+            "(csrc/hj_systems.cuh shows how to add one); there is no CPU fallback" % (name, ", ".join(sorted(_GENERIC))))
+    ad = scheme.__dict__.get("_hjb200_generic")
+    if ad is None or ad.dyn is not scheme.dynSys:
+        ad = _GENERIC[name](scheme)
+        try:
+            scheme._hjb200_generic = ad
+        except Exception:
+            pass
+    ad.sd = scheme
+    return ad
+
+
 def _adapter_for_owner(owner, ham_name, part_name):
     name = type(owner).__name__
     pair = (ham_name, part_name)
@@ -184,9 +278,20 @@ def _adapter_for_owner(owner, ham_name, part_name):
         "fused kernel and there is no CPU fallback" % (name, ham_name, part_name))
 
 
-def resolve(ham_func, partial_func, grid=None):
-    """Adapter for a (hamFunc, partialFunc) pair; raises NotImplementedError for unregistered callables
-    (e.g. genericHam/genericPartial, Hamiltonians/generic_ham.py:5) and ValueError for mismatched pairs."""
+def resolve(ham_func, partial_func, grid=None, scheme=None):
+    """Adapter for a (hamFunc, partialFunc) pair; raises NotImplementedError for unregistered callables and ValueError
+    for mismatched pairs.  genericHam / genericPartial (Hamiltonians/generic_ham.py:5) resolve through
+    ``scheme.dynSys`` (generic_adapter)."""
+    names = (getattr(ham_func, "__name__", None), getattr(partial_func, "__name__", None))
+    if "genericHam" in names or "genericPartial" in names:
+        if names != ("genericHam", "genericPartial"):
+            raise ValueError("genericHam and genericPartial come as a pair (hji_solver.py:413-415)")
+        if scheme is None:
+            raise NotImplementedError("genericHam / genericPartial need schemeData (dynSys, uMode, dMode, tMode)")
+        ad = generic_adapter(scheme)
+        if grid is not None and ad.ndim != grid.dim:
+            raise ValueError("system is %d-D but the grid is %d-D" % (ad.ndim, grid.dim))
+        return ad
     ho, po = getattr(ham_func, "__self__", None), getattr(partial_func, "__self__", None)
     if ho is None or po is None:
         raise NotImplementedError(

@@ -60,6 +60,30 @@ def _step_bound(eng, ad, block):
     return 1 / inv
 
 
+def _rk_step_dynamic(eng, ad, tables, t, t_end, factorCFL, maxStep, safety, comp, use_obstacle, order):
+    """One TVD-RK3 step for a functor whose alpha depends on the derivative range of the field (genericPartial,
+    generic_partial.py:28-56): before each RHS the range of that stage's input is reduced on the device
+    (hj_deriv_range), the dynSys's get_opt_u / get_opt_v turn it into the four input sets, and the stage kernel runs
+    with that block.  deltaT comes from the first RHS's bound (ode_cfl_3.py:142-143); later bounds only warn (:173-175)."""
+    if order != 3:
+        raise NotImplementedError("odeCFL2 with genericHam / genericPartial: the C-ABI steps RK2 in one call")
+    if not hasattr(eng, "deriv_range"):
+        raise NotImplementedError("genericHam / genericPartial run on single-GPU contexts only")
+    deltaT, times = None, [t, t, t]
+    for k in range(3):
+        lo, hi = eng.deriv_range(None, k + 1)
+        eng.set_system(ad.system_id, ad.block_for_range(lo, hi, times[k]), tables)
+        bound = eng.alpha_max()[1]                                      # artificial_diss_glf.py:104-109
+        if k == 0:
+            deltaT = float(np.min(np.hstack((factorCFL * bound, t_end - t, maxStep))))   # ode_cfl_3.py:142-143
+            t1, tHalf, tNew = rk3_times(t, deltaT)
+            times = [t, t1, tHalf]
+        elif deltaT > safety * bound:                                   # :173-175, :215-217
+            warn("%s substep violated CFL effective number %s" % ("Second" if k == 1 else "Third", deltaT / bound))
+        eng.stage(k + 1, times[k], deltaT, None, comp if k == 2 else L.COMP_NONE, use_obstacle and k == 2)
+    return tNew, deltaT
+
+
 def rk2_times(t, dt):
     """New time of one odeCFL2 step, arithmetic verbatim from ode_cfl_2.py (t1 = t+dt; t2 = t1+dt; t = 0.5 (t+t2))."""
     t1 = t + dt
@@ -72,6 +96,8 @@ def rk3_step_resident(eng, ad, grid, t, t_end, factorCFL, maxStep, comp=L.COMP_N
     resident state.  Returns (t_new, dt)."""
     safetyFactorCFL = min(1.0, 1.2 * factorCFL)                         # ode_cfl_3.py:95
     tables = list(enumerate(ad.tables(grid)))
+    if ad.dynamic:
+        return _rk_step_dynamic(eng, ad, tables, t, t_end, factorCFL, maxStep, safetyFactorCFL, comp, use_obstacle, order)
     blocks = [ad.block()]
     eng.set_system(ad.system_id, blocks[0], tables)
     stepBound = _step_bound(eng, ad, blocks[0])

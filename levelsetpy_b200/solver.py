@@ -72,6 +72,10 @@ def HJIPDE_solve(data0, tau, schemeData, compMethod=None, extraArgs=None):
         error("Inconsistent initial condition dimension!")              # hji_solver.py:503
     # numerical approximation functions (hji_solver.py:434); the reference sets `derivFunc` although
     # termLaxFriedrichs reads `CoStateCalc` -- set both so either spelling works
+    if isfield(schemeData, "dynSys"):                                   # hji_solver.py:413-415
+        from .generic import genericHam, genericPartial
+        schemeData.hamFunc = genericHam
+        schemeData.partialFunc = genericPartial
     schemeData.dissFunc = artificialDissipationGLF
     schemeData.derivFunc = upwindFirstWENO5
     if not isfield(schemeData, "CoStateCalc"):

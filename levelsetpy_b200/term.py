@@ -24,8 +24,9 @@ def prepare_scheme(schemeData):
         raise NotImplementedError("dissFunc=%r: only artificialDissipationGLF / artificialDissipationLLF are fused into "
                                   "the stage kernel" % (sd.dissFunc,))
     adapter = sd.__dict__.get("_hjb200_adapter")
-    if adapter is None or adapter[0] is not sd.hamFunc or adapter[1] is not sd.partialFunc:
-        ad = resolve(sd.hamFunc, sd.partialFunc, sd.grid)
+    if (adapter is None or adapter[0] is not sd.hamFunc or adapter[1] is not sd.partialFunc
+            or (adapter[2].dynamic and (adapter[2].dyn is not sd.__dict__.get("dynSys") or adapter[2].sd is not sd))):
+        ad = resolve(sd.hamFunc, sd.partialFunc, sd.grid, sd)
         try:
             sd._hjb200_adapter = (sd.hamFunc, sd.partialFunc, ad)
         except Exception:
@@ -50,8 +51,15 @@ def termLaxFriedrichs(t, y, schemeData):
     eng, ad = prepare_scheme(schemeData)
     if iscell(y):
         y = y[0]
-    block = ad.block()
-    eng.set_system(ad.system_id, block, list(enumerate(ad.tables(eng_grid(schemeData)))))
+    tables = list(enumerate(ad.tables(eng_grid(schemeData))))
+    if ad.dynamic:
+        # genericPartial: alpha needs the derivative range of this very field (generic_partial.py:28-40) -- one
+        # reduce-only pass over it first, the dynSys's get_opt_u / get_opt_v on the range, then the fused RHS
+        lo, hi = eng.deriv_range(y)
+        block = ad.block_for_range(lo, hi, t)
+    else:
+        block = ad.block()
+    eng.set_system(ad.system_id, block, tables)
     ydot, step_bound, red = eng.rhs(t, y)
     if iscell(schemeData):
         schemeData[0] = copy.copy(schemeData[0])
@@ -87,7 +95,12 @@ def termRestrictUpdate(t, y, schemeData):
     eng, ad = prepare_scheme(inner)
     if iscell(y):
         y = y[0]
-    eng.set_system(ad.system_id, ad.block(), list(enumerate(ad.tables(eng_grid(inner)))))
+    if ad.dynamic:
+        lo, hi = eng.deriv_range(y)
+        block = ad.block_for_range(lo, hi, t)
+    else:
+        block = ad.block()
+    eng.set_system(ad.system_id, block, list(enumerate(ad.tables(eng_grid(inner)))))
     eng.set_restrict(sign)
     try:
         ydot, step_bound, _ = eng.rhs(t, y)

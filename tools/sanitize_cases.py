@@ -42,6 +42,14 @@ def main():
         print("%-34s t=%.6g  |y|max=%.6g" % (name, t, float(np.abs(y).max())), flush=True)
 
     g, d0 = air3d([21, 17, 13])
+    # genericHam / genericPartial over a device dynSys: reduce-only pre-pass (hj_deriv_range) + the GenericF stage kernels
+    car = lsp.Bundle(dict(grid=g, dynSys=lsp.DubinsCar(1.3, 0.9, [0.15, 0.25, 0.1]), hamFunc=lsp.genericHam,
+                          partialFunc=lsp.genericPartial, dissFunc=lsp.artificialDissipationGLF,
+                          CoStateCalc=lsp.upwindFirstWENO5a))
+    for be, nm in ((L.BACKEND_TMA, "tma"), (L.BACKEND_GATHER, "gather")):
+        run("generic DubinsCar 21x17x13 " + nm, car, g, d0, be)
+    if "--generic-only" in sys.argv:
+        return
     for weno in ("as_shipped", "intended"):
         run("air3d 21x17x13 tma " + weno, bundle(g, lsp.DubinsVehicleRel(g, 5, 1), weno), g, d0, L.BACKEND_TMA)
     run("air3d 21x17x13 gather", bundle(g, lsp.DubinsVehicleRel(g, 5, 1)), g, d0, L.BACKEND_GATHER)

@@ -409,7 +409,7 @@ int hj_deriv_range(hj_ctx* c, void* stream, const double* y_dev, int stage, doub
     // dt = 0 and its reductions on, its output parked in the buffer that is dead at this point of the step (stage 1 / 3:
     // buffer 1, stage 2: buffer 2 -- the real stage launch that follows overwrites it or no longer reads it).  The
     // derivative range does not depend on the system's parameter block, so a stale block is harmless.  One field read
-    // through the TMA ring (0.8 ms at 512^3) instead of D cached gathers per node (2.1 ms).
+    // through the TMA ring (1.5 ms at 512^3) instead of D cached gathers per node (2.1 ms).
     static const int in_idx[4] = {0, 0, 1, 2}, dead[4] = {0, 1, 2, 1};
     KStage st{};
     st.stage = 1;

@@ -143,7 +143,8 @@ int64_t hj_plane_elems(const hj_ctx* ctx);        /* pitched elements of one dim
 /* derivMin / derivMax of artificialDissipationGLF (artificial_diss_glf.py:82-88) on their own: per dim, the minimum and
  * the maximum over the grid of the upwind pair (derivL, derivR) of the context's CoStateCalc -- what genericPartial
  * (Hamiltonians/generic_partial.py:28-40) feeds the dynSys's get_opt_u / get_opt_v BEFORE the dissipation of the same RHS
- * exists.  y_dev: a dense device array, or NULL for the resident buffer RK stage `stage` (1..3) reads.  deriv_min /
+ * exists.  y_dev: a dense device array, or NULL for the resident buffer RK stage `stage` (1..3; 4 = final stage of
+ * odeCFL2) reads.  deriv_min /
  * deriv_max: D host doubles each.  One reduce-only kernel; synchronises. */
 int hj_deriv_range(hj_ctx* ctx, void* stream, const double* y_dev, int stage, double* deriv_min, double* deriv_max);
 
@@ -198,7 +199,10 @@ int hj_step(hj_ctx* ctx, void* stream, double t, double dt, const double* stage_
 int hj_step_reductions(hj_ctx* ctx, void* stream, double* reduce_host);
 
 /* Multi-GPU slab support: run stage `stage` (1..3) only, so the caller can exchange halos between stages.
- * hj_step == hj_stage(1); hj_stage(2); hj_stage(3) on a single device.                                  */
+ * hj_step == hj_stage(1); hj_stage(2); hj_stage(3) on a single device.
+ * stage 4 (not on slab contexts): the final stage of odeCFL2 (ode_cfl_2.py: y = 0.5 (y + (y1 + dt f(y1)))), so that
+ * hj_step_rk2 == hj_stage(1); hj_stage(4) -- for systems whose parameter block has to be refreshed between the two
+ * RHS evaluations from the field itself (genericPartial, with hj_deriv_range(stage) before each).          */
 int hj_stage(hj_ctx* ctx, void* stream, int stage, double t, double dt, const double* params, int comp,
              int use_obstacle, int want_reduce);
 /* Product systems on the dimension-split path: a stage is two kernels.  Pass 1 (trailing dim block)

@@ -392,9 +392,9 @@ int hj_deriv_range(hj_ctx* c, void* stream, const double* y_dev, int stage, doub
     in = y_dev;
     g = &c->gd;
   } else {
-    if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_deriv_range: stage must be 1..3");
+    if (stage < 1 || stage > 4) return fail(HJ_ERR_INVALID, "hj_deriv_range: stage must be 1..3 (odeCFL3) or 4 (final stage of odeCFL2)");
     if (!c->have_state) return fail(HJ_ERR_STATE, "hj_deriv_range: no resident state (hj_upload first)");
-    static const int in_[4] = {0, 0, 1, 2};
+    static const int in_[5] = {0, 0, 1, 2, 1};
     in = c->buf[in_[stage]] + c->origin;
     g = &c->gp;
   }
@@ -407,10 +407,11 @@ int hj_deriv_range(hj_ctx* c, void* stream, const double* y_dev, int stage, doub
   if (!y_dev && !c->halo0 && c->system_id != HJ_SYS_NONE && use_tma(c) && !hj_tma_plan_is_split(c->plan)) {
     // resident state of a whole system on the plane-ring backend: the reduce-only pass is the stage-1 kernel itself with
     // dt = 0 and its reductions on, its output parked in the buffer that is dead at this point of the step (stage 1 / 3:
-    // buffer 1, stage 2: buffer 2 -- the real stage launch that follows overwrites it or no longer reads it).  The
+    // buffer 1, stage 2 and the RK2 final stage: buffer 2 -- the real stage launch that follows overwrites it or no
+    // longer reads it).  The
     // derivative range does not depend on the system's parameter block, so a stale block is harmless.  One field read
     // through the TMA ring (1.5 ms at 512^3) instead of D cached gathers per node (2.1 ms).
-    static const int in_idx[4] = {0, 0, 1, 2}, dead[4] = {0, 1, 2, 1};
+    static const int in_idx[5] = {0, 0, 1, 2, 1}, dead[5] = {0, 1, 2, 1, 2};
     KStage st{};
     st.stage = 1;
     st.comp = HJ_COMP_NONE;
@@ -655,7 +656,8 @@ int hj_stage(hj_ctx* c, void* stream, int stage, double t, double dt, const doub
   if (r) return r;
   if (c->nbatch) return fail(HJ_ERR_UNSUPPORTED, "hj_stage: use hj_step_batch on a batch context");
   if (!c->have_state) return fail(HJ_ERR_STATE, "hj_stage: no resident state (hj_upload first)");
-  if (stage < 1 || stage > 3) return fail(HJ_ERR_INVALID, "hj_stage: stage must be 1..3");
+  if (stage < 1 || stage > 4) return fail(HJ_ERR_INVALID, "hj_stage: stage must be 1..3 (odeCFL3) or 4 (final stage of odeCFL2)");
+  if (stage == 4 && c->halo0) return fail(HJ_ERR_UNSUPPORTED, "hj_stage: slab contexts drive the RK3 stages");
   CK(cudaSetDevice(c->device));
   // on a slab the caller runs hj_eps_prepass + allreduce itself before each stage
   return stage_impl(c, (cudaStream_t)stream, stage, dt, params, comp, use_obstacle, want_reduce, !c->halo0);

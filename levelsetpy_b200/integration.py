@@ -61,26 +61,30 @@ def _step_bound(eng, ad, block):
 
 
 def _rk_step_dynamic(eng, ad, tables, t, t_end, factorCFL, maxStep, safety, comp, use_obstacle, order):
-    """One TVD-RK3 step for a functor whose alpha depends on the derivative range of the field (genericPartial,
-    generic_partial.py:28-56): before each RHS the range of that stage's input is reduced on the device
-    (hj_deriv_range), the dynSys's get_opt_u / get_opt_v turn it into the four input sets, and the stage kernel runs
-    with that block.  deltaT comes from the first RHS's bound (ode_cfl_3.py:142-143); later bounds only warn (:173-175)."""
-    if order != 3:
-        raise NotImplementedError("odeCFL2 with genericHam / genericPartial: the C-ABI steps RK2 in one call")
+    """One TVD-RK3 (odeCFL3) or TVD-RK2 (odeCFL2) step for a functor whose alpha depends on the derivative range of the
+    field (genericPartial, generic_partial.py:28-56): before each RHS the range of that stage's input is reduced on the
+    device (hj_deriv_range), the dynSys's get_opt_u / get_opt_v turn it into the four input sets, and the stage kernel
+    runs with that block.  deltaT comes from the first RHS's bound (ode_cfl_3.py:142-143 / ode_cfl_2.py); later bounds
+    only warn (ode_cfl_3.py:173-175, :215-217)."""
     if not hasattr(eng, "deriv_range"):
         raise NotImplementedError("genericHam / genericPartial run on single-GPU contexts only")
-    deltaT, times = None, [t, t, t]
-    for k in range(3):
-        lo, hi = eng.deriv_range(None, k + 1)
+    stages = (1, 2, 3) if order == 3 else (1, 4)        # 4: the final stage of the RK2 scheme (reads y1)
+    deltaT, times, tNew = None, [t] * order, t
+    for k, stage in enumerate(stages):
+        lo, hi = eng.deriv_range(None, stage)
         eng.set_system(ad.system_id, ad.block_for_range(lo, hi, times[k]), tables)
         bound = eng.alpha_max()[1]                                      # artificial_diss_glf.py:104-109
         if k == 0:
             deltaT = float(np.min(np.hstack((factorCFL * bound, t_end - t, maxStep))))   # ode_cfl_3.py:142-143
-            t1, tHalf, tNew = rk3_times(t, deltaT)
-            times = [t, t1, tHalf]
+            if order == 3:
+                t1, tHalf, tNew = rk3_times(t, deltaT)
+                times = [t, t1, tHalf]
+            else:
+                times, tNew = [t, t + deltaT], rk2_times(t, deltaT)
         elif deltaT > safety * bound:                                   # :173-175, :215-217
             warn("%s substep violated CFL effective number %s" % ("Second" if k == 1 else "Third", deltaT / bound))
-        eng.stage(k + 1, times[k], deltaT, None, comp if k == 2 else L.COMP_NONE, use_obstacle and k == 2)
+        last = k == order - 1
+        eng.stage(stage, times[k], deltaT, None, comp if last else L.COMP_NONE, use_obstacle and last)
     return tNew, deltaT
 
 

@@ -8,7 +8,7 @@ restatement (oracle/generic.py) asserted bit-identical.
 No class of the reference implements the dynSys API these functions call (get_opt_u / get_opt_v / dynamics), so the dynSys
 is the one the API was written for, a Dubins car with disturbances (oracle/generic.py: DubinsCar, plain numpy).  Recorded
 per mode case on an air3D-shaped 21x17x13 grid: ham and the three alphas of one RHS, termLaxFriedrichs ydot + stepBound,
-three single-step odeCFL3 calls (t and y), and one HJIPDE_solve through schemeData.dynSys (hji_solver.py:413-415).
+three single-step odeCFL3 and odeCFL2 calls (t and y), odeCFL2 over termRestrictUpdate, and one HJIPDE_solve through schemeData.dynSys (hji_solver.py:413-415).
 """
 import os
 import sys
@@ -29,7 +29,8 @@ from LevelSetPy.Utilities import Bundle  # noqa: E402
 from LevelSetPy.Grids import createGrid  # noqa: E402
 from LevelSetPy.InitialConditions import shapeCylinder  # noqa: E402
 from LevelSetPy.SpatialDerivative import upwindFirstWENO5a  # noqa: E402
-from LevelSetPy.ExplicitIntegration import odeCFL3, odeCFLset, termLaxFriedrichs, artificialDissipationGLF  # noqa: E402
+from LevelSetPy.ExplicitIntegration import (odeCFL2, odeCFL3, odeCFLset, termLaxFriedrichs, termRestrictUpdate,  # noqa: E402
+                                             artificialDissipationGLF)
 from LevelSetPy.Hamiltonians import genericHam, genericPartial  # noqa: E402
 from LevelSetPy.ValueFuncs import HJIPDE_solve  # noqa: E402
 
@@ -89,6 +90,30 @@ def main():
             same(y, yo, tag + " y step %d" % k)
             ts.append(float(t))
         out[tag + "_t"], out[tag + "_y"] = np.array(ts), np.asarray(y)
+        # odeCFL2 (ode_cfl_2.py) over the same hooks: three single steps
+        t, to, y, yo, ts = 0.0, 0.0, y0, y0, []
+        for k in range(3):
+            t, y, _ = odeCFL2(termLaxFriedrichs, [t, 1.0], y, opts, rsd)
+            to, yo, _ = orc.ode_cfl2([to, 1.0], yo, osd, factor_cfl=0.8, single_step=True)
+            same(t, to, tag + " rk2 t step %d" % k)
+            same(y, yo, tag + " rk2 y step %d" % k)
+            ts.append(float(t))
+        out[tag + "_rk2_t"], out[tag + "_rk2_y"] = np.array(ts), np.asarray(y)
+    # termRestrictUpdate(positive=False) around the generic term, odeCFL2 -- what the RCBRT notebooks drive (y of shape (n,))
+    dyn = ogen.DubinsCar(**DYN)
+    inner = Bundle(dict(grid=g, dynSys=dyn, hamFunc=genericHam, partialFunc=genericPartial,
+                        dissFunc=artificialDissipationGLF, CoStateCalc=upwindFirstWENO5a))
+    rsd = Bundle(dict(innerFunc=termLaxFriedrichs, innerData=inner, positive=False))
+    osd = orc.OracleSchemeData(grid=g, dynSys=dyn, hamFunc=ogen.generic_ham, partialFunc=ogen.generic_partial)
+    yflat = data0.flatten()
+    t, to, y, yo, ts = 0.0, 0.0, yflat, yflat, []
+    for k in range(3):
+        t, y, _ = odeCFL2(termRestrictUpdate, [t, 1.0], y, opts, rsd)
+        to, yo, _ = orc.ode_cfl2([to, 1.0], yo, osd, factor_cfl=0.8, single_step=True, restrict=False)
+        same(t, to, "restricted rk2 t step %d" % k)
+        same(y, yo, "restricted rk2 y step %d" % k)
+        ts.append(float(t))
+    out["restrict_neg_rk2_t"], out["restrict_neg_rk2_y"] = np.array(ts), np.asarray(y)
     # the driver: schemeData.dynSys alone makes HJIPDE_solve install genericHam / genericPartial (hji_solver.py:413-415)
     dyn = ogen.DubinsCar(**DYN)
     tau = np.array([0.0, 0.15, 0.3])

@@ -65,6 +65,22 @@ def test_oracle_generic_golden_bit_exact(lsp, tag, modes):
         t, y, _ = orc.ode_cfl3([t, 1.0], y, osd, factor_cfl=0.8, single_step=True)
         assert t == gold[tag + "_t"][k]
     assert np.array_equal(y, gold[tag + "_y"])
+    t, y = 0.0, np.expand_dims(d0.flatten(), 1)
+    for k in range(3):
+        t, y, _ = orc.ode_cfl2([t, 1.0], y, osd, factor_cfl=0.8, single_step=True)
+        assert t == gold[tag + "_rk2_t"][k]
+    assert np.array_equal(y, gold[tag + "_rk2_y"])
+
+
+def test_oracle_generic_restricted_rk2_golden_bit_exact(lsp):
+    gold = load_golden("generic_dyn")
+    g = make_grid(lsp, gold)
+    osd = _oracle_sd(g, gold, {})
+    t, y = 0.0, gold["data0"].flatten()
+    for k in range(3):
+        t, y, _ = orc.ode_cfl2([t, 1.0], y, osd, factor_cfl=0.8, single_step=True, restrict=False)
+        assert t == gold["restrict_neg_rk2_t"][k]
+    assert np.array_equal(y, gold["restrict_neg_rk2_y"])
 
 
 def test_oracle_generic_partial_defaults_to_dmode_min():
@@ -214,6 +230,47 @@ def test_device_generic_term_and_ode_vs_golden(lsp, tag, modes):
         assert t == gold[tag + "_t"][k]
     want = gold[tag + "_y"]
     assert np.max(np.abs(y - want)) <= 1e-9 * rng_of(want)
+    assert np.mean(np.sign(y) == np.sign(want)) >= 0.9999
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,modes", CASES)
+def test_device_generic_ode_cfl2_vs_golden(lsp, tag, modes):
+    """odeCFL2 over the generic hooks: hj_stage(1), hj_stage(4) with the derivative range of y resp. y1 reduced before each."""
+    gold = load_golden("generic_dyn")
+    g = make_grid(lsp, gold)
+    sd = lsp.Bundle(dict(grid=g, dynSys=lsp.DubinsCar(**_dyn_args(gold)), hamFunc=lsp.genericHam,
+                         partialFunc=lsp.genericPartial, dissFunc=lsp.artificialDissipationGLF,
+                         CoStateCalc=lsp.upwindFirstWENO5a, **modes))
+    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
+    t, y = 0.0, np.expand_dims(gold["data0"].flatten(), 1)
+    for k in range(3):
+        t, y, _ = lsp.odeCFL2(lsp.termLaxFriedrichs, [t, 1.0], y, opts, sd)
+        assert t == gold[tag + "_rk2_t"][k]
+    want = gold[tag + "_rk2_y"]
+    assert y.shape == want.shape
+    assert np.max(np.abs(y - want)) <= 1e-9 * rng_of(want)
+    assert np.mean(np.sign(y) == np.sign(want)) >= 0.9999
+
+
+@pytest.mark.gpu
+def test_device_generic_restricted_ode_cfl2_vs_golden(lsp):
+    """termRestrictUpdate(positive=False) around the generic term under odeCFL2 (what the RCBRT notebooks drive)."""
+    gold = load_golden("generic_dyn")
+    g = make_grid(lsp, gold)
+    inner = lsp.Bundle(dict(grid=g, dynSys=lsp.DubinsCar(**_dyn_args(gold)), hamFunc=lsp.genericHam,
+                            partialFunc=lsp.genericPartial, dissFunc=lsp.artificialDissipationGLF,
+                            CoStateCalc=lsp.upwindFirstWENO5a))
+    sd = lsp.Bundle(dict(innerFunc=lsp.termLaxFriedrichs, innerData=inner, positive=False))
+    opts = lsp.odeCFLset(lsp.Bundle(dict(factorCFL=0.8, singleStep="on")))
+    t, y = 0.0, gold["data0"].flatten()
+    for k in range(3):
+        t, y, _ = lsp.odeCFL2(lsp.termRestrictUpdate, [t, 1.0], y, opts, sd)
+        assert t == gold["restrict_neg_rk2_t"][k]
+    want = gold["restrict_neg_rk2_y"]
+    assert y.shape == want.shape
+    assert np.max(np.abs(y - want)) <= 1e-9 * rng_of(want)
+    # the restriction clamps ydot at 0: nodes that did not move are exactly data0 in both
     assert np.mean(np.sign(y) == np.sign(want)) >= 0.9999
 
 

@@ -320,3 +320,67 @@ def test_hjipde_solve_installs_generic_hooks_for_a_dynsys(lsp):
     dts = getattr(extra, "dts", None)
     if dts is not None:
         assert list(dts) == list(gold["hji_dts"])
+
+
+# ------------------------------------------------------------------------- CPU: the two-pass stage protocol on the host
+class _RecordingEngine:
+    """Stand-in for Engine: records the order of the C-ABI calls one step makes (no device)."""
+
+    def __init__(self, bounds):
+        self.calls, self.bounds, self.blocks = [], list(bounds), []
+
+    def deriv_range(self, y=None, stage=1):
+        self.calls.append(("deriv_range", stage))
+        return np.array([-1.0, -2.0, -3.0]), np.array([1.0, 2.0, 3.0])
+
+    def set_system(self, system_id, block, tables):
+        self.calls.append(("set_system", system_id))
+        self.blocks.append(np.array(block))
+
+    def alpha_max(self, t=0.0):
+        self.calls.append(("alpha_max",))
+        return np.zeros(3), self.bounds.pop(0)
+
+    def stage(self, stage, t, dt, params=None, comp=0, use_obstacle=False, want_reduce=False, which_pass=0):
+        self.calls.append(("stage", stage, t, dt, comp, bool(use_obstacle)))
+
+
+@pytest.mark.parametrize("order", [3, 2])
+def test_dynamic_step_protocol_on_the_host(lsp, order, caplog):
+    """Before EVERY RHS: reduce the range of that stage's input, refresh the block through the dynSys's own methods, take
+    the bound; dt from the first bound only (ode_cfl_3.py:142-143), later bounds only warn (:173-175); the driver
+    epilogue rides on the last stage; RK2 = stages 1 and 4 with the times of ode_cfl_2.py."""
+    import logging
+    from levelsetpy_b200 import functors, integration
+    from levelsetpy_b200 import _lib as L
+    g = lsp.createGrid(np.array([-1.0, -1.0, 0.0]), np.array([1.0, 1.0, 2 * np.pi * (1 - 1 / 9)]), np.array([11, 10, 9]), pdDims=2)
+    calls = []
+
+    class Car(lsp.DubinsCar):
+        def get_opt_u(self, t, deriv, uMode="min", y=None):
+            calls.append(("u", t, tuple(float(v) for v in deriv), uMode))
+            return super().get_opt_u(t, deriv, uMode, y)
+
+    Car.__name__ = "DubinsCar"                      # registered by class name
+    sd = lsp.Bundle(dict(grid=g, dynSys=Car(1.3, 0.9, [0.15, 0.25, 0.1]), hamFunc=lsp.genericHam, partialFunc=lsp.genericPartial))
+    ad = functors.resolve(sd.hamFunc, sd.partialFunc, g, sd)
+    eng = _RecordingEngine([0.5] + [0.45] * (order - 2) + [0.1])      # the last bound violates CFL: a warning, not a new dt
+    with caplog.at_level(logging.WARNING):
+        t_new, dt = integration.rk3_step_resident(eng, ad, g, 0.25, 10.0, 0.8, 1e9, comp=L.COMP_MIN_OVER_TIME, order=order)
+    assert dt == 0.8 * 0.5
+    stages = (1, 2, 3) if order == 3 else (1, 4)
+    want_times = ([0.25] + list(integration.rk3_times(0.25, dt)[:2])) if order == 3 else [0.25, 0.25 + dt]
+    assert t_new == (integration.rk3_times(0.25, dt)[2] if order == 3 else integration.rk2_times(0.25, dt))
+    per_stage = [eng.calls[4 * k:4 * k + 4] for k in range(order)]
+    for k, (st, grp) in enumerate(zip(stages, per_stage)):
+        assert [c[0] for c in grp] == ["deriv_range", "set_system", "alpha_max", "stage"], grp
+        assert grp[0][1] == st and grp[3][1] == st
+        assert grp[3][2] == want_times[k] and grp[3][3] == dt
+        assert grp[3][4] == (L.COMP_MIN_OVER_TIME if k == order - 1 else L.COMP_NONE)
+    # the dynSys's own get_opt_u saw the reduced range, twice per RHS (derivMax then derivMin), at that RHS's time
+    assert len(calls) == 2 * order
+    assert calls[0] == ("u", 0.25, (1.0, 2.0, 3.0), "min") and calls[1] == ("u", 0.25, (-1.0, -2.0, -3.0), "min")
+    assert [c[1] for c in calls[::2]] == want_times
+    msgs = [r.getMessage() for r in caplog.records]
+    assert any(("Third" if order == 3 else "Second") + " substep violated CFL" in m for m in msgs), msgs
+    assert all(b.shape == (16,) for b in eng.blocks)
